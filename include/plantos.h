@@ -1,0 +1,190 @@
+/*
+ * plantos.h -- C ABI of libplantos_b200.so, the B200 (sm_100a) batched PlantOS simulator.
+ *
+ * This is the drop-in boundary for the env-step hot path of GammaKing2000/RL-Env:
+ * everything an SB3 `VecEnv.reset()/step_async()/step_wait()` does below the VecEnv
+ * call (DummyVecEnv loop -> Monitor -> PlantOSEnv.step/reset, reference
+ * A2C_training.py:116-125,216-218 and plantos_env.py:125-372) is one kernel launch
+ * behind `plantos_step`.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative PLANTOS_E* code otherwise; the
+ *     message for the calling thread's last failure is `plantos_last_error()`;
+ *   - "dev" pointers are device pointers on the handle's GPU, owned by the caller
+ *     (e.g. torch tensors' data_ptr()); "host" pointers are host memory;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  All work
+ *     is enqueued on it asynchronously unless stated otherwise;
+ *   - one caller thread per handle (SB3 is single-threaded); not re-entrant;
+ *   - grid coordinates: x = row = first index, y = column (plantos_env.py:186-190);
+ *   - cell codes: 0 empty, 1 obstacle, 2 hydrated plant, 3 thirsty plant
+ *     (the reference's LIDAR entity ids, plantos_env.py:20-23).
+ */
+#ifndef PLANTOS_B200_H
+#define PLANTOS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLANTOS_ABI_VERSION 1
+
+enum {
+    PLANTOS_OK = 0,
+    PLANTOS_EINVAL = -1,   /* bad argument / config rejected */
+    PLANTOS_ECUDA = -2,    /* CUDA runtime error */
+    PLANTOS_ENOMAPS = -3,  /* injected-map mode: an env ran past its pushed maps */
+    PLANTOS_ESTATE = -4    /* call not valid in the handle's current state */
+};
+
+enum { PLANTOS_MAPS_PHILOX = 0, PLANTOS_MAPS_INJECTED = 1 };
+
+/* kernel selection (plantos_config_t.kernel) */
+enum {
+    PLANTOS_KERNEL_AUTO = 0,     /* fast kernel when the preset qualifies, else generic */
+    PLANTOS_KERNEL_GENERIC = 1,  /* one warp per env, any supported config */
+    PLANTOS_KERNEL_FAST = 2      /* sub-warp per env; G<=32, R<=7, C<=16 (presets T, DFLT) */
+};
+
+/* indices into the reward table (plantos_upload_tables / plantos_compute_tables):
+ * each entry is R_STEP + X summed in the reference's order (plantos_env.py:164-169),
+ * the *_COMPLETE twins add R_COMPLETE_EXPLORATION afterwards (:179-181). */
+enum {
+    PLANTOS_RW_NEW = 0,          /* valid move onto a never-visited cell  (:204-205) */
+    PLANTOS_RW_REVISIT = 1,      /* valid move onto a visited cell        (:206-207) */
+    PLANTOS_RW_INVALID = 2,      /* wall / obstacle                       (:208-211) */
+    PLANTOS_RW_WATER_GOAL = 3,   /* watered a thirsty plant               (:217-219) */
+    PLANTOS_RW_WATER_EMPTY = 4,  /* watered an empty cell                 (:221-222) */
+    PLANTOS_RW_WATER_MISTAKE = 5,/* watered a hydrated plant: documented R_MISTAKE
+                                    (README.md:46; the reference raises TypeError here) */
+    PLANTOS_RW_COUNT = 6         /* table holds 2*COUNT entries: [k] and [COUNT+k] (+complete) */
+};
+
+/* Mirrors PlantOSEnv.__init__ (plantos_env.py:25-27,76-83,120) plus sharding/seed. */
+typedef struct plantos_config {
+    int32_t struct_size;        /* sizeof(plantos_config_t), ABI check */
+    int32_t num_envs;           /* envs simulated by THIS handle / GPU */
+    int64_t env_id_base;        /* global id of local env 0 (rank * num_envs when sharded) */
+    int32_t grid_size;          /* G, 5..128 */
+    int32_t num_plants;         /* P */
+    int32_t num_obstacles;      /* O; O/3 clusters are generated (plantos_env.py:341) */
+    int32_t lidar_range;        /* R, 1..64 */
+    int32_t lidar_channels;     /* C, 1..64 */
+    int32_t max_steps;          /* truncation horizon, 1..65535 (reference: 1000) */
+    float   thirsty_plant_prob; /* reference: 0.7 */
+    int32_t map_source;         /* PLANTOS_MAPS_* */
+    uint64_t seed;              /* Philox key */
+    double  r_goal, r_mistake, r_invalid, r_water_empty, r_step,
+            r_exploration, r_revisit, r_complete_exploration;
+    int32_t kernel;             /* PLANTOS_KERNEL_* */
+    int32_t reserved[7];
+} plantos_config_t;
+
+typedef struct plantos plantos_t;
+
+/* Fill `cfg` with the reference ctor defaults (plantos_env.py:25-26,76-83,120):
+ * G21 P8 O50 R2 C10, prob 0.7, max_steps 1000, DQN reward set, philox maps, seed 0. */
+int plantos_default_config(plantos_config_t* cfg);
+
+/* Observation length 5*C + 2 + 25 (plantos_env.py:55-57). */
+int plantos_obs_dim(const plantos_config_t* cfg);
+
+/* Host-only: the constant tables the kernels use, evaluated in double precision with
+ * the reference's literal expressions, for cross-checking against another host language:
+ *   lidar_off  int8  [C][R][2]  (int)(r*cos(2*pi*i/C)), (int)(r*sin(..))  plantos_env.py:261-267
+ *   dist_tab   float [R+1]      (float)(r / (double)R)                     :288
+ *   pos_tab    float [G]        (float)(x / (double)G)                     :295-296
+ *   visit_tab  float [11]       (float)(k / 10.0)                          :308
+ *   reward_tab double[2*PLANTOS_RW_COUNT]                                  :164-181
+ * Any pointer may be NULL to skip that table. */
+int plantos_compute_tables(const plantos_config_t* cfg, int8_t* lidar_off, float* dist_tab,
+                           float* pos_tab, float* visit_tab, double* reward_tab);
+
+/* Create a simulator for cfg->num_envs envs on CUDA device `device`.  Validates the
+ * config (replaces the reference's ValueError, plantos_env.py:360-364: the border ring is
+ * always obstacle-free, so 4G-4 >= P+1 is required), allocates persistent state, uploads
+ * the default tables.  Envs hold no valid state until plantos_reset. */
+int plantos_create(const plantos_config_t* cfg, int device, plantos_t** out);
+int plantos_destroy(plantos_t* h);
+
+/* Replace the device tables (layouts as in plantos_compute_tables; host pointers). Synchronous. */
+int plantos_upload_tables(plantos_t* h, const int8_t* lidar_off, const float* dist_tab,
+                          const float* pos_tab, const float* visit_tab, const double* reward_tab);
+
+/* Injected-map mode: give every env a queue of `episodes` recorded maps, consumed one per
+ * reset in order (replaces the procedural generator, plantos_env.py:338-372).  Host pointers:
+ * cells u8 [num_envs][episodes][G*G], rover i16 [num_envs][episodes][2] (x,y).  Resets the
+ * per-env map cursor to 0.  Synchronous. */
+int plantos_push_maps(plantos_t* h, const uint8_t* cells, const int16_t* rover, int episodes);
+
+/* VecEnv.reset(): start a new episode in every env (PlantOSEnv.reset, plantos_env.py:125-158)
+ * and write obs_dev f32 [num_envs][D]. */
+int plantos_reset(plantos_t* h, float* obs_dev, void* stream);
+
+/* VecEnv.step(actions): one PlantOSEnv.step (plantos_env.py:160-183) per env, then SB3's
+ * auto-reset for finished envs.  All pointers are device pointers:
+ *   actions      i64 [N]    0 N, 1 E, 2 S, 3 W, >=4 water (plantos_env.py:166-169)
+ *   obs          f32 [N][D] next observation (post-reset where done)
+ *   reward       f32 [N]
+ *   done         u8  [N]    terminated | truncated
+ *   terminated   u8  [N]    may be NULL
+ *   truncated    u8  [N]    may be NULL   (SB3 "TimeLimit.truncated" = truncated & !terminated)
+ *   terminal_obs f32 [N][D] may be NULL; rows written only where done (SB3 "terminal_observation")
+ */
+int plantos_step(plantos_t* h, const int64_t* actions, float* obs, float* reward,
+                 uint8_t* done, uint8_t* terminated, uint8_t* truncated,
+                 float* terminal_obs, void* stream);
+
+/* Same step with HOST buffers (what a numpy VecEnv consumer sees): copies actions H2D,
+ * runs the step, copies obs / reward / done back D2H on `stream` and waits for it.
+ * Pinned host memory makes the copies asynchronous with respect to the host until the wait. */
+int plantos_step_host(plantos_t* h, const int64_t* actions_host, float* obs_host,
+                      float* reward_host, uint8_t* done_host, void* stream);
+
+/* Per-env scalar state, struct-of-arrays, i32 [PLANTOS_SC_COUNT][N] (device pointer). */
+enum {
+    PLANTOS_SC_X = 0, PLANTOS_SC_Y = 1, PLANTOS_SC_STEP_COUNT = 2, PLANTOS_SC_EXPLORED = 3,
+    PLANTOS_SC_TOTAL_CELLS = 4, PLANTOS_SC_THIRSTY = 5, PLANTOS_SC_COLLISIONS = 6,
+    PLANTOS_SC_COLLIDED = 7, PLANTOS_SC_BONUS_GIVEN = 8, PLANTOS_SC_EPISODE = 9,
+    PLANTOS_SC_WATERED = 10, PLANTOS_SC_COUNT = 11
+};
+/* which: 0 = live state, 1 = snapshot taken at each env's most recent terminal step
+ * (the info dict SB3 returns next to terminal_observation). */
+int plantos_get_scalars(plantos_t* h, int which, int32_t* out_dev, void* stream);
+/* Episode return so far (which=0) / of the last finished episode (which=1), f64 [N]:
+ * sum of the python-float rewards in step order, as SB3 Monitor accumulates it. */
+int plantos_get_returns(plantos_t* h, int which, double* out_dev, void* stream);
+
+/* Full integer state for parity checks (device pointers, any may be NULL):
+ *   cells  u8  [N][G*G] cell codes;  visits i32 [N][G*G] visit_counts (plantos_env.py:146) */
+int plantos_get_state(plantos_t* h, uint8_t* cells_dev, int32_t* visits_dev, void* stream);
+/* Overwrite state (MCTS-style copy, mcts_custom_trainer.py:218-243): cells/visits as above,
+ * scalars i32 [PLANTOS_SC_COUNT][N] (TOTAL_CELLS/THIRSTY are recomputed from cells). */
+int plantos_set_state(plantos_t* h, const uint8_t* cells_dev, const int32_t* visits_dev,
+                      const int32_t* scalars_dev, void* stream);
+
+/* Episode statistics accumulated on device since create / the last clear, f64 [8]:
+ * {episodes, sum return, sum length, sum exploration %, sum collisions, sum plants watered,
+ *  n terminated, n truncated}.  `out_dev` is a device pointer (the payload of the optional
+ * NCCL all-reduce).  Sums are kept in fixed point (1e-6 units) so they do not depend on
+ * the order in which envs finish. */
+int plantos_stats(plantos_t* h, double* out_dev, int clear, void* stream);
+
+/* Sticky device-side error flag (e.g. PLANTOS_ENOMAPS); synchronises `stream`. */
+int plantos_check(plantos_t* h, void* stream);
+
+/* Number of simulator kernels launched by this handle so far. */
+int64_t plantos_launch_count(const plantos_t* h);
+/* Name of the step kernel the handle selected ("generic" / "fast"). */
+const char* plantos_kernel_name(const plantos_t* h);
+/* Bytes of persistent device state per env. */
+int64_t plantos_state_bytes_per_env(const plantos_t* h);
+
+const char* plantos_last_error(void);
+int plantos_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLANTOS_B200_H */

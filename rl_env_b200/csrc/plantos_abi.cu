@@ -1,0 +1,481 @@
+// plantos_abi.cu -- host side of libplantos_b200.so: the C ABI declared in include/plantos.h.
+// No torch / pybind types cross this boundary; build with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/plantos.h"
+#include "plantos_fast.cuh"
+
+using namespace plantos_dev;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return fail(PLANTOS_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+typedef void (*fast_kernel_t)(const Params, const StepIO);
+
+struct FastVariant { int R, C, EPW; fast_kernel_t fn; };
+
+#define FAST_ROW(R_, C_)                                                  \
+    {R_, C_, 4, k_step_fast<R_, C_, 4>}, {R_, C_, 8, k_step_fast<R_, C_, 8>}, \
+    {R_, C_, 16, k_step_fast<R_, C_, 16>}, {R_, C_, 32, k_step_fast<R_, C_, 32>}
+
+const FastVariant kFastVariants[] = {
+    FAST_ROW(6, 16),  // training preset, A2C_training.py:206-212
+    FAST_ROW(2, 10),  // ctor default, plantos_env.py:25-26
+    FAST_ROW(4, 16),  // test_environment.py:24 custom env
+    FAST_ROW(4, 8),
+};
+
+}  // namespace
+
+struct plantos {
+    plantos_config_t cfg;
+    int device;
+    int num_sms;
+    Params p;
+    // owned device buffers
+    void* d_tables;      // one allocation holding every table
+    uint8_t* d_map_cells;
+    int16_t* d_map_rover;
+    // staging for plantos_step_host
+    long long* s_actions;
+    float* s_obs;
+    float* s_reward;
+    uint8_t* s_done;
+    // launch configuration
+    bool use_fast;
+    fast_kernel_t fast_fn;
+    int fast_epw;
+    int generic_grid, generic_smem;
+    int fast_smem;
+    bool did_reset;
+    int64_t launches;
+};
+
+// ------------------------------------------------------------------ host tables
+extern "C" int plantos_default_config(plantos_config_t* cfg) {
+    if (!cfg) return fail(PLANTOS_EINVAL, "cfg is NULL");
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = (int32_t)sizeof(*cfg);
+    cfg->num_envs = 1;
+    cfg->grid_size = 21; cfg->num_plants = 8; cfg->num_obstacles = 50;
+    cfg->lidar_range = 2; cfg->lidar_channels = 10;
+    cfg->max_steps = 1000;
+    cfg->thirsty_plant_prob = 0.7f;
+    cfg->map_source = PLANTOS_MAPS_PHILOX;
+    cfg->seed = 0;
+    cfg->r_goal = 20; cfg->r_mistake = -10; cfg->r_invalid = -5; cfg->r_water_empty = -5;
+    cfg->r_step = -0.1; cfg->r_exploration = 10; cfg->r_revisit = -1; cfg->r_complete_exploration = 50;
+    cfg->kernel = PLANTOS_KERNEL_AUTO;
+    return PLANTOS_OK;
+}
+
+static int validate(const plantos_config_t* c) {
+    if (!c) return fail(PLANTOS_EINVAL, "cfg is NULL");
+    if (c->struct_size != (int32_t)sizeof(plantos_config_t))
+        return fail(PLANTOS_EINVAL, "plantos_config_t.struct_size does not match this library (ABI mismatch)");
+    if (c->num_envs < 1) return fail(PLANTOS_EINVAL, "num_envs must be >= 1");
+    if (c->grid_size < 5 || c->grid_size > 128) return fail(PLANTOS_EINVAL, "grid_size must be in [5, 128]");
+    if (c->lidar_range < 1 || c->lidar_range > 64) return fail(PLANTOS_EINVAL, "lidar_range must be in [1, 64]");
+    if (c->lidar_channels < 1 || c->lidar_channels > 64) return fail(PLANTOS_EINVAL, "lidar_channels must be in [1, 64]");
+    if (c->max_steps < 1 || c->max_steps > 65535) return fail(PLANTOS_EINVAL, "max_steps must be in [1, 65535]");
+    if (c->num_plants < 0 || c->num_obstacles < 0) return fail(PLANTOS_EINVAL, "num_plants / num_obstacles must be >= 0");
+    if (c->num_plants > 255) return fail(PLANTOS_EINVAL, "num_plants must be <= 255");
+    // The reference raises ValueError when fewer than P+1 cells are free (plantos_env.py:360-364).
+    // Obstacle clusters never touch the border ring (centres in [2, G-3], reach 1), so 4G-4
+    // cells are always free: require that bound so a reset can never fail on the device.
+    if (4 * c->grid_size - 4 < c->num_plants + 1)
+        return fail(PLANTOS_EINVAL, "Not enough guaranteed-free positions (4G-4) to place num_plants plants and 1 rover");
+    if (!(c->thirsty_plant_prob >= 0.0f && c->thirsty_plant_prob <= 1.0f))
+        return fail(PLANTOS_EINVAL, "thirsty_plant_prob must be in [0, 1]");
+    if (c->map_source != PLANTOS_MAPS_PHILOX && c->map_source != PLANTOS_MAPS_INJECTED)
+        return fail(PLANTOS_EINVAL, "map_source must be PLANTOS_MAPS_PHILOX or PLANTOS_MAPS_INJECTED");
+    if (c->kernel < PLANTOS_KERNEL_AUTO || c->kernel > PLANTOS_KERNEL_FAST)
+        return fail(PLANTOS_EINVAL, "kernel must be one of PLANTOS_KERNEL_*");
+    return PLANTOS_OK;
+}
+
+extern "C" int plantos_obs_dim(const plantos_config_t* cfg) {
+    if (!cfg) return fail(PLANTOS_EINVAL, "cfg is NULL");
+    return cfg->lidar_channels * 5 + 2 + 25;
+}
+
+extern "C" int plantos_compute_tables(const plantos_config_t* c, int8_t* lidar_off, float* dist_tab,
+                                      float* pos_tab, float* visit_tab, double* reward_tab) {
+    int rc = validate(c);
+    if (rc) return rc;
+    const int C = c->lidar_channels, R = c->lidar_range, G = c->grid_size;
+    if (lidar_off) {
+        for (int i = 0; i < C; ++i) {
+            // angle = (2 * math.pi * i) / C, evaluated left to right in double (plantos_env.py:261)
+            const double angle = (2.0 * M_PI * (double)i) / (double)C;
+            for (int r = 1; r <= R; ++r) {
+                lidar_off[(i * R + (r - 1)) * 2 + 0] = (int8_t)(int)((double)r * std::cos(angle));  // :266
+                lidar_off[(i * R + (r - 1)) * 2 + 1] = (int8_t)(int)((double)r * std::sin(angle));  // :267
+            }
+        }
+    }
+    if (dist_tab) for (int r = 0; r <= R; ++r) dist_tab[r] = (float)((double)r / (double)R);       // :288
+    if (pos_tab) for (int x = 0; x < G; ++x) pos_tab[x] = (float)((double)x / (double)G);            // :295-296
+    if (visit_tab) for (int k = 0; k <= 10; ++k) visit_tab[k] = (float)((double)k / 10.0);           // :308
+    if (reward_tab) {
+        const double x[PLANTOS_RW_COUNT] = {c->r_exploration, c->r_revisit, c->r_invalid,
+                                            c->r_goal, c->r_water_empty, c->r_mistake};
+        for (int k = 0; k < PLANTOS_RW_COUNT; ++k) {
+            double rew = c->r_step;                       // reward = self.R_STEP            (:164)
+            rew += x[k];                                  // reward += handler result        (:167,169)
+            reward_tab[k] = rew;
+            rew += c->r_complete_exploration;             // reward += R_COMPLETE_EXPLORATION (:180)
+            reward_tab[PLANTOS_RW_COUNT + k] = rew;
+        }
+    }
+    return PLANTOS_OK;
+}
+
+// ------------------------------------------------------------------ create / destroy
+static int upload_tables_impl(plantos_t* h, const int8_t* lidar_off, const float* dist_tab, const float* pos_tab,
+                              const float* visit_tab, const double* reward_tab) {
+    const Params& p = h->p;
+    if (lidar_off) CUDA_TRY(cudaMemcpy((void*)p.lidar_off, lidar_off, (size_t)p.C * p.R * 2, cudaMemcpyHostToDevice));
+    if (dist_tab) CUDA_TRY(cudaMemcpy((void*)p.dist_tab, dist_tab, (size_t)(p.R + 1) * 4, cudaMemcpyHostToDevice));
+    if (pos_tab) CUDA_TRY(cudaMemcpy((void*)p.pos_tab, pos_tab, (size_t)p.G * 4, cudaMemcpyHostToDevice));
+    if (visit_tab) CUDA_TRY(cudaMemcpy((void*)p.visit_tab, visit_tab, 11 * 4, cudaMemcpyHostToDevice));
+    if (reward_tab) {
+        float r32[2 * PLANTOS_RW_COUNT];
+        for (int i = 0; i < 2 * PLANTOS_RW_COUNT; ++i) r32[i] = (float)reward_tab[i];
+        CUDA_TRY(cudaMemcpy((void*)p.reward64, reward_tab, sizeof(double) * 2 * PLANTOS_RW_COUNT, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy((void*)p.reward32, r32, sizeof(r32), cudaMemcpyHostToDevice));
+    }
+    return PLANTOS_OK;
+}
+
+static void free_all(plantos_t* h) {
+    if (!h) return;
+    cudaFree(h->p.rec); cudaFree(h->p.term_rec); cudaFree(h->p.types); cudaFree(h->p.visits);
+    cudaFree(h->d_tables); cudaFree(h->p.stats); cudaFree(h->p.err);
+    cudaFree(h->d_map_cells); cudaFree(h->d_map_rover);
+    cudaFree(h->s_actions); cudaFree(h->s_obs); cudaFree(h->s_reward); cudaFree(h->s_done);
+    delete h;
+}
+
+extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t** out) {
+    if (!out) return fail(PLANTOS_EINVAL, "out is NULL");
+    *out = nullptr;
+    int rc = validate(cfg);
+    if (rc) return rc;
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(PLANTOS_EINVAL, "no such CUDA device");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(PLANTOS_ECUDA, std::string("libplantos_b200 is built for sm_100a only; device is ") + prop.name);
+
+    plantos_t* h = new plantos();
+    std::memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    Params& p = h->p;
+    p.N = cfg->num_envs; p.env_base = cfg->env_id_base;
+    p.G = cfg->grid_size; p.P = cfg->num_plants; p.O = cfg->num_obstacles;
+    p.R = cfg->lidar_range; p.C = cfg->lidar_channels; p.D = plantos_obs_dim(cfg);
+    p.W = (p.G + 31) / 32; p.TW = (p.G + 3) / 4; p.VT = p.TW * p.TW;
+    p.max_steps = cfg->max_steps; p.nclusters = cfg->num_obstacles / 3;
+    {
+        double th = std::floor((double)cfg->thirsty_plant_prob * 4294967296.0);
+        if (th < 0) th = 0;
+        if (th > 4294967296.0) th = 4294967296.0;
+        p.thirsty_thresh = (unsigned long long)th;
+    }
+    p.seed_lo = (uint32_t)(cfg->seed & 0xffffffffull); p.seed_hi = (uint32_t)(cfg->seed >> 32);
+    p.map_source = cfg->map_source; p.map_episodes = 0;
+
+    const size_t N = (size_t)p.N;
+#define ALLOC(ptr, bytes)                                                       \
+    do {                                                                        \
+        cudaError_t _e = cudaMalloc((void**)&(ptr), (bytes));                   \
+        if (_e != cudaSuccess) {                                                \
+            free_all(h);                                                        \
+            return fail(PLANTOS_ECUDA, std::string("cudaMalloc(" #ptr "): ") + cudaGetErrorString(_e)); \
+        }                                                                       \
+    } while (0)
+    ALLOC(p.rec, N * 32);
+    ALLOC(p.term_rec, N * 32);
+    ALLOC(p.types, N * p.G * p.W * 8);
+    ALLOC(p.visits, N * p.VT * 32);
+    ALLOC(p.stats, kStatCount * 8);
+    ALLOC(p.err, 4);
+    // tables: rw64 | rw32 | dist | pos | visit | off
+    const size_t tb = 2 * kRwCount * 8 + 2 * kRwCount * 4 + (p.R + 1) * 4 + p.G * 4 + 12 * 4 + (size_t)p.C * p.R * 2 + 64;
+    ALLOC(h->d_tables, tb);
+#undef ALLOC
+    {
+        unsigned char* b = (unsigned char*)h->d_tables;
+        p.reward64 = (const double*)b; b += 2 * kRwCount * 8;
+        p.reward32 = (const float*)b; b += 2 * kRwCount * 4;
+        p.dist_tab = (const float*)b; b += (p.R + 1) * 4;
+        p.pos_tab = (const float*)b; b += p.G * 4;
+        p.visit_tab = (const float*)b; b += 12 * 4;
+        p.lidar_off = (const int8_t*)b;
+    }
+    cudaMemset(p.rec, 0, N * 32);
+    cudaMemset(p.term_rec, 0, N * 32);
+    cudaMemset(p.types, 0, N * p.G * p.W * 8);
+    cudaMemset(p.visits, 0, N * p.VT * 32);
+    cudaMemset(p.stats, 0, kStatCount * 8);
+    cudaMemset(p.err, 0, 4);
+
+    // default tables
+    {
+        std::vector<int8_t> off((size_t)p.C * p.R * 2);
+        std::vector<float> dist(p.R + 1), pos(p.G), visit(11);
+        double rw[2 * PLANTOS_RW_COUNT];
+        plantos_compute_tables(cfg, off.data(), dist.data(), pos.data(), visit.data(), rw);
+        rc = upload_tables_impl(h, off.data(), dist.data(), pos.data(), visit.data(), rw);
+        if (rc) { free_all(h); return rc; }
+    }
+
+    // kernel selection
+    const bool fast_ok = (p.W == 1) && (p.G + p.R <= 32) && (2 * p.R + 1 <= 16) && (p.C <= 16);
+    h->use_fast = false;
+    if (cfg->kernel != PLANTOS_KERNEL_GENERIC && fast_ok) {
+        int epw = 32;
+        const long long fill = (long long)h->num_sms * 16;   // warps wanted in flight
+        while (epw > 4 && (long long)(p.N + epw - 1) / epw < fill) epw >>= 1;
+        if (const char* s = std::getenv("PLANTOS_EPW")) {
+            const int v = std::atoi(s);
+            if (v == 4 || v == 8 || v == 16 || v == 32) epw = v;
+        }
+        for (const FastVariant& v : kFastVariants)
+            if (v.R == p.R && v.C == p.C && v.EPW == epw) { h->use_fast = true; h->fast_fn = v.fn; h->fast_epw = epw; }
+    }
+    if (cfg->kernel == PLANTOS_KERNEL_FAST && !h->use_fast) {
+        free_all(h);
+        return fail(PLANTOS_EINVAL, "PLANTOS_KERNEL_FAST requested but (G, R, C) has no fast-kernel instantiation");
+    }
+    h->generic_smem = tables_bytes(p.G, p.R, p.C) + kGenericWarps * generic_warp_scratch_bytes(p.G, p.W, p.D);
+    h->fast_smem = tables_bytes(p.G, p.R, p.C) + kFastWarps * fast_warp_scratch_bytes(p.G, p.D);
+    cudaError_t e1 = cudaFuncSetAttribute(k_step_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);
+    cudaError_t e2 = cudaFuncSetAttribute(k_reset_all, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        free_all(h);
+        return fail(PLANTOS_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    }
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_generic, kGenericWarps * 32, h->generic_smem);
+    if (occ < 1) occ = 1;
+    const long long want = ((long long)p.N + kGenericWarps - 1) / kGenericWarps;
+    const long long cap = (long long)h->num_sms * occ;
+    h->generic_grid = (int)(want < cap ? want : cap);
+    if (h->use_fast) {
+        cudaError_t e3 = cudaFuncSetAttribute(h->fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fast_smem);
+        if (e3 != cudaSuccess) { free_all(h); return fail(PLANTOS_ECUDA, std::string("cudaFuncSetAttribute(fast): ") + cudaGetErrorString(e3)); }
+    }
+    cudaError_t es = cudaDeviceSynchronize();
+    if (es != cudaSuccess) { free_all(h); return fail(PLANTOS_ECUDA, std::string("create: ") + cudaGetErrorString(es)); }
+    *out = h;
+    return PLANTOS_OK;
+}
+
+extern "C" int plantos_destroy(plantos_t* h) {
+    if (!h) return PLANTOS_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    free_all(h);
+    return PLANTOS_OK;
+}
+
+extern "C" int plantos_upload_tables(plantos_t* h, const int8_t* lidar_off, const float* dist_tab,
+                                     const float* pos_tab, const float* visit_tab, const double* reward_tab) {
+    if (!h) return fail(PLANTOS_EINVAL, "handle is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return upload_tables_impl(h, lidar_off, dist_tab, pos_tab, visit_tab, reward_tab);
+}
+
+extern "C" int plantos_push_maps(plantos_t* h, const uint8_t* cells, const int16_t* rover, int episodes) {
+    if (!h) return fail(PLANTOS_EINVAL, "handle is NULL");
+    if (h->cfg.map_source != PLANTOS_MAPS_INJECTED) return fail(PLANTOS_ESTATE, "handle was not created with PLANTOS_MAPS_INJECTED");
+    if (!cells || !rover || episodes < 1) return fail(PLANTOS_EINVAL, "cells/rover NULL or episodes < 1");
+    Params& p = h->p;
+    const size_t gg = (size_t)p.G * p.G, n = (size_t)p.N * episodes;
+    for (size_t i = 0; i < n; ++i) {
+        const int x = rover[2 * i], y = rover[2 * i + 1];
+        if (x < 0 || x >= p.G || y < 0 || y >= p.G) return fail(PLANTOS_EINVAL, "rover start outside the grid");
+        if (cells[i * gg + (size_t)x * p.G + y] == 1) return fail(PLANTOS_EINVAL, "rover start on an obstacle");
+    }
+    for (size_t i = 0; i < n * gg; ++i)
+        if (cells[i] > 3) return fail(PLANTOS_EINVAL, "cell code > 3");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(h->d_map_cells); cudaFree(h->d_map_rover);
+    h->d_map_cells = nullptr; h->d_map_rover = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&h->d_map_cells, n * gg));
+    CUDA_TRY(cudaMalloc((void**)&h->d_map_rover, n * 2 * sizeof(int16_t)));
+    CUDA_TRY(cudaMemcpy(h->d_map_cells, cells, n * gg, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d_map_rover, rover, n * 2 * sizeof(int16_t), cudaMemcpyHostToDevice));
+    p.map_cells = h->d_map_cells; p.map_rover = h->d_map_rover; p.map_episodes = episodes;
+    // restart every env's map cursor (episode index lives in rec.w of the first uint4)
+    CUDA_TRY(cudaMemset(p.rec, 0, (size_t)p.N * 32));
+    h->did_reset = false;
+    return PLANTOS_OK;
+}
+
+// ------------------------------------------------------------------ reset / step
+extern "C" int plantos_reset(plantos_t* h, float* obs_dev, void* stream) {
+    if (!h || !obs_dev) return fail(PLANTOS_EINVAL, "handle/obs is NULL");
+    if (h->cfg.map_source == PLANTOS_MAPS_INJECTED && h->p.map_episodes == 0)
+        return fail(PLANTOS_ESTATE, "injected-map mode: call plantos_push_maps before plantos_reset");
+    CUDA_TRY(cudaSetDevice(h->device));
+    k_reset_all<<<h->generic_grid, kGenericWarps * 32, h->generic_smem, (cudaStream_t)stream>>>(h->p, obs_dev);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    h->did_reset = true;
+    return PLANTOS_OK;
+}
+
+extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, float* reward, uint8_t* done,
+                            uint8_t* terminated, uint8_t* truncated, float* terminal_obs, void* stream) {
+    if (!h || !actions || !obs || !reward || !done) return fail(PLANTOS_EINVAL, "handle/actions/obs/reward/done is NULL");
+    if (!h->did_reset) return fail(PLANTOS_ESTATE, "plantos_step before plantos_reset");
+    StepIO io;
+    io.actions = (const long long*)actions; io.obs = obs; io.reward = reward; io.done = done;
+    io.terminated = terminated; io.truncated = truncated; io.terminal_obs = terminal_obs;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const bool aligned = (((uintptr_t)obs) & 15u) == 0;
+    if (h->use_fast && aligned) {
+        const int per_block = kFastWarps * h->fast_epw;
+        const int grid = (h->p.N + per_block - 1) / per_block;
+        h->fast_fn<<<grid, kFastWarps * 32, h->fast_smem, (cudaStream_t)stream>>>(h->p, io);
+    } else {
+        if (h->cfg.kernel == PLANTOS_KERNEL_FAST)
+            return fail(PLANTOS_EINVAL, "PLANTOS_KERNEL_FAST needs a 16-byte aligned obs buffer");
+        k_step_generic<<<h->generic_grid, kGenericWarps * 32, h->generic_smem, (cudaStream_t)stream>>>(h->p, io);
+    }
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return PLANTOS_OK;
+}
+
+extern "C" int plantos_step_host(plantos_t* h, const int64_t* actions_host, float* obs_host, float* reward_host,
+                                 uint8_t* done_host, void* stream) {
+    if (!h || !actions_host || !obs_host || !reward_host || !done_host)
+        return fail(PLANTOS_EINVAL, "handle or a host buffer is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t N = (size_t)h->p.N, D = (size_t)h->p.D;
+    if (!h->s_actions) {
+        CUDA_TRY(cudaMalloc((void**)&h->s_actions, N * 8));
+        CUDA_TRY(cudaMalloc((void**)&h->s_obs, N * D * 4));
+        CUDA_TRY(cudaMalloc((void**)&h->s_reward, N * 4));
+        CUDA_TRY(cudaMalloc((void**)&h->s_done, N));
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(h->s_actions, actions_host, N * 8, cudaMemcpyHostToDevice, st));
+    int rc = plantos_step(h, (const int64_t*)h->s_actions, h->s_obs, h->s_reward, h->s_done, nullptr, nullptr, nullptr, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(obs_host, h->s_obs, N * D * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(reward_host, h->s_reward, N * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(done_host, h->s_done, N, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PLANTOS_OK;
+}
+
+// ------------------------------------------------------------------ state access
+extern "C" int plantos_get_scalars(plantos_t* h, int which, int32_t* out_dev, void* stream) {
+    if (!h || !out_dev) return fail(PLANTOS_EINVAL, "handle/out is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    k_get_scalars<<<(h->p.N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->p, which, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return PLANTOS_OK;
+}
+
+extern "C" int plantos_get_returns(plantos_t* h, int which, double* out_dev, void* stream) {
+    if (!h || !out_dev) return fail(PLANTOS_EINVAL, "handle/out is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    k_get_returns<<<(h->p.N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->p, which, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return PLANTOS_OK;
+}
+
+extern "C" int plantos_get_state(plantos_t* h, uint8_t* cells_dev, int32_t* visits_dev, void* stream) {
+    if (!h) return fail(PLANTOS_EINVAL, "handle is NULL");
+    if (!cells_dev && !visits_dev) return PLANTOS_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t total = (size_t)h->p.N * h->p.G * h->p.G;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > (size_t)h->num_sms * 32) blocks = (size_t)h->num_sms * 32;
+    k_get_state<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(h->p, cells_dev, visits_dev);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return PLANTOS_OK;
+}
+
+extern "C" int plantos_set_state(plantos_t* h, const uint8_t* cells_dev, const int32_t* visits_dev,
+                                 const int32_t* scalars_dev, void* stream) {
+    if (!h) return fail(PLANTOS_EINVAL, "handle is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t threads = (size_t)h->p.N * 32;
+    k_set_state<<<(int)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->p, cells_dev, visits_dev, scalars_dev);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    h->did_reset = true;
+    return PLANTOS_OK;
+}
+
+extern "C" int plantos_stats(plantos_t* h, double* out_dev, int clear, void* stream) {
+    if (!h || !out_dev) return fail(PLANTOS_EINVAL, "handle/out is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    k_stats_out<<<1, 32, 0, (cudaStream_t)stream>>>(h->p.stats, out_dev, clear);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return PLANTOS_OK;
+}
+
+extern "C" int plantos_check(plantos_t* h, void* stream) {
+    if (!h) return fail(PLANTOS_EINVAL, "handle is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int err = 0;
+    CUDA_TRY(cudaMemcpyAsync(&err, h->p.err, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    if (err == PLANTOS_ENOMAPS) return fail(PLANTOS_ENOMAPS, "an env was reset more often than maps were pushed for it");
+    if (err != 0) return fail(err, "device-side error flag set");
+    return PLANTOS_OK;
+}
+
+extern "C" int64_t plantos_launch_count(const plantos_t* h) { return h ? h->launches : 0; }
+
+extern "C" const char* plantos_kernel_name(const plantos_t* h) {
+    if (!h) return "";
+    return h->use_fast ? "fast" : "generic";
+}
+
+extern "C" int64_t plantos_state_bytes_per_env(const plantos_t* h) {
+    if (!h) return 0;
+    const Params& p = h->p;
+    return 32 + 32 + (int64_t)p.G * p.W * 8 + (int64_t)p.VT * 32;
+}
+
+extern "C" const char* plantos_last_error(void) { return g_last_error.c_str(); }
+extern "C" int plantos_abi_version(void) { return PLANTOS_ABI_VERSION; }

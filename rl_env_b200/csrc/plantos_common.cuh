@@ -1,0 +1,277 @@
+// plantos_common.cuh -- device-side state layout, tables and helpers shared by the
+// generic (one warp per env) and fast (half-warp per env) PlantOS kernels.
+//
+// Persistent state in HBM, per env (SoA across envs, all little-endian):
+//   rec     32 B   hot scalars, two uint4 (see EnvRec)
+//   types   G*W*8  2-bit cell codes (0 empty 1 obstacle 2 hydrated 3 thirsty), row-major,
+//                  W = ceil(G/32) u64 words per row, cell y of row x at bits [2*(y&31), +2)
+//                  of word x*W + (y>>5).  INVARIANT: columns >= G of the last word hold
+//                  the obstacle code (01) so a shifted row reads "wall" beyond the grid.
+//   visits  VT*32  visit_counts (plantos_env.py:146) as u16 in 4x4-cell tiles of 32 B
+//                  (one DRAM sector): tile (x>>2)*TW + (y>>2), TW = ceil(G/4), element
+//                  (x&3)*4 + (y&3).  A 5x5 window touches exactly 2x2 tiles.  Counts
+//                  saturate at 65535 (a cell gains at most one visit every second step, so
+//                  an episode of <= 65535 steps never reaches it).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace plantos_dev {
+
+constexpr int kEmpty = 0, kObstacle = 1, kHydrated = 2, kThirsty = 3;
+constexpr uint64_t kObstAll = 0x5555555555555555ull;  // obstacle code in every cell of a word
+constexpr int kFlagCollided = 1, kFlagBonus = 2;
+constexpr int kRwCount = 6;  // PLANTOS_RW_COUNT
+constexpr int kStatCount = 8;
+constexpr int kScCount = 11;  // PLANTOS_SC_COUNT
+
+struct Params {
+    int N;
+    long long env_base;
+    int G, P, O, R, C, D;
+    int W;          // u64 words per type row
+    int TW, VT;     // visit tiles per row / per env
+    int max_steps;
+    int nclusters;  // O / 3 (plantos_env.py:341)
+    unsigned long long thirsty_thresh;  // floor(prob * 2^32); draw < thresh => thirsty
+    uint32_t seed_lo, seed_hi;
+    int map_source;    // 0 philox, 1 injected
+    int map_episodes;  // injected maps per env
+    // persistent state
+    uint4* rec;
+    uint64_t* types;
+    uint16_t* visits;
+    uint4* term_rec;   // snapshot of rec at each env's latest terminal step
+    // tables (global memory; staged into shared memory per block)
+    const int8_t* lidar_off;  // [C][R][2]
+    const float* dist_tab;    // [R+1]
+    const float* pos_tab;     // [G]
+    const float* visit_tab;   // [11]
+    const float* reward32;    // [2*kRwCount]
+    const double* reward64;   // [2*kRwCount]
+    // injected maps
+    const uint8_t* map_cells;   // [N][E][G*G]
+    const int16_t* map_rover;   // [N][E][2]
+    // episode statistics (fixed point, see plantos_stats) and sticky error word
+    unsigned long long* stats;
+    int* err;
+};
+
+struct StepIO {
+    const long long* actions;
+    float* obs;
+    float* reward;
+    uint8_t* done;
+    uint8_t* terminated;
+    uint8_t* truncated;
+    float* terminal_obs;
+};
+
+// ---------------------------------------------------------------- env record
+struct EnvRec {
+    int x, y, flags, thirsty;
+    int step, explored;
+    int total_free, collisions;
+    int episode;
+    int watered;
+    double ret;
+};
+
+__device__ __forceinline__ EnvRec unpack_rec(const uint4& a, const uint4& b) {
+    EnvRec r;
+    r.x = a.x & 0xff;
+    r.y = (a.x >> 8) & 0xff;
+    r.flags = (a.x >> 16) & 0xff;
+    r.thirsty = a.x >> 24;
+    r.step = a.y & 0xffff;
+    r.explored = a.y >> 16;
+    r.total_free = a.z & 0xffff;
+    r.collisions = a.z >> 16;
+    r.episode = (int)a.w;
+    r.watered = b.x & 0xffff;
+    r.ret = __hiloint2double((int)b.w, (int)b.z);
+    return r;
+}
+
+__device__ __forceinline__ void pack_rec(const EnvRec& r, uint4& a, uint4& b) {
+    a.x = (uint32_t)r.x | ((uint32_t)r.y << 8) | ((uint32_t)r.flags << 16) | ((uint32_t)r.thirsty << 24);
+    a.y = (uint32_t)r.step | ((uint32_t)r.explored << 16);
+    a.z = (uint32_t)r.total_free | ((uint32_t)r.collisions << 16);
+    a.w = (uint32_t)r.episode;
+    b.x = (uint32_t)r.watered;
+    b.y = 0u;
+    b.z = (uint32_t)__double2loint(r.ret);
+    b.w = (uint32_t)__double2hiint(r.ret);
+}
+
+// ------------------------------------------------------------------- helpers
+__device__ __forceinline__ int cell_of(uint64_t word, int ylow) { return (int)((word >> (2 * ylow)) & 3ull); }
+
+__device__ __forceinline__ int visit_index(int x, int y, int TW) {
+    return (((x >> 2) * TW + (y >> 2)) << 4) + ((x & 3) << 2) + (y & 3);
+}
+
+// valid-column mask (bit0 of each cell) for word w of a row
+__device__ __forceinline__ uint64_t col_mask(int G, int w) {
+    int n = G - w * 32;
+    if (n >= 32) return kObstAll;
+    return kObstAll & ((1ull << (2 * n)) - 1ull);
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------ Philox4x32-10 (counter RNG)
+// Map of env `genv`, episode `ep` is a pure function of (seed, genv, ep): counter =
+// (draw j, ep, genv low 32, (genv >> 32) * 4 + stream), key = seed.  Streams: 0 obstacle
+// clusters, 1 plants, 2 rover.  Mirrored on the host in oracle/philox_mapgen.py.
+__host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
+__device__ __forceinline__ void map_draw(const Params& p, long long genv, int ep, int stream, uint32_t j,
+                                         uint32_t (&out)[4]) {
+    out[0] = j;
+    out[1] = (uint32_t)ep;
+    out[2] = (uint32_t)((unsigned long long)genv & 0xffffffffull);
+    out[3] = (uint32_t)(((unsigned long long)genv >> 32) * 4ull + (unsigned)stream);
+    philox4x32_10(out, p.seed_lo, p.seed_hi);
+}
+
+__device__ __forceinline__ uint32_t bounded(uint32_t w, uint32_t n) { return __umulhi(w, n); }
+
+// ------------------------------------------------- per-block shared-memory tables
+struct Tables {
+    const int8_t* off;    // [C][R][2]
+    const float* dist;    // [R+1]
+    const float* pos;     // [G]
+    const float* visit;   // [11]
+    const float* rw32;    // [12]
+    const double* rw64;   // [12]
+};
+
+__host__ __device__ inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// byte layout of the table block; identical on host (for the launch size) and device
+__host__ __device__ inline int tables_bytes(int G, int R, int C) {
+    int b = 2 * kRwCount * 8;              // rw64
+    b += 2 * kRwCount * 4;                 // rw32
+    b += (R + 1) * 4 + G * 4 + 12 * 4;     // dist, pos, visit(11 padded to 12)
+    b += align_up(C * R * 2, 16);          // offsets
+    return align_up(b, 16);
+}
+
+// Cooperative load by the whole block; ends with __syncthreads().
+__device__ inline Tables load_tables(const Params& p, unsigned char* smem) {
+    double* rw64 = reinterpret_cast<double*>(smem);
+    float* rw32 = reinterpret_cast<float*>(rw64 + 2 * kRwCount);
+    float* dist = rw32 + 2 * kRwCount;
+    float* pos = dist + (p.R + 1);
+    float* visit = pos + p.G;
+    int8_t* off = reinterpret_cast<int8_t*>(visit + 12);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < 2 * kRwCount; i += nt) { rw64[i] = p.reward64[i]; rw32[i] = p.reward32[i]; }
+    for (int i = tid; i <= p.R; i += nt) dist[i] = p.dist_tab[i];
+    for (int i = tid; i < p.G; i += nt) pos[i] = p.pos_tab[i];
+    for (int i = tid; i < 11; i += nt) visit[i] = p.visit_tab[i];
+    for (int i = tid; i < p.C * p.R * 2; i += nt) off[i] = p.lidar_off[i];
+    __syncthreads();
+    Tables t;
+    t.off = off; t.dist = dist; t.pos = pos; t.visit = visit; t.rw32 = rw32; t.rw64 = rw64;
+    return t;
+}
+
+// ------------------------------------------------------------ env transition
+// One PlantOSEnv.step up to (not including) the observation: plantos_env.py:160-222 and the
+// termination/bonus logic of :176-181.  Executed by ONE thread for env e.  `row_word` is the
+// type word holding the cell the action looks at (move target, or the rover's own cell when
+// watering) or kObstAll when the target is out of bounds; `visits_e`/`types_e` point at the
+// env's planes in global memory and receive the read-modify-writes.
+struct StepOut {
+    int ridx;        // index into the reward tables
+    int terminated;  // exploration >= 100 % (plantos_env.py:176,244-246)
+    int truncated;   // step_count >= max_steps (:177)
+    int watered;     // a thirsty plant was hydrated this step
+};
+
+__device__ __forceinline__ void action_target(const EnvRec& r, long long action, int G, int& tx, int& ty, bool& inb) {
+    if (action < 4) {
+        // directions = N, E, S, W on (x, y) (plantos_env.py:186); negative actions index
+        // the list from the end in Python, which is the same two low bits.
+        const int d = (int)(action & 3);
+        tx = r.x + ((d == 2) - (d == 0));
+        ty = r.y + ((d == 1) - (d == 3));
+        inb = ((unsigned)tx < (unsigned)G) && ((unsigned)ty < (unsigned)G);
+    } else {
+        tx = r.x; ty = r.y; inb = true;
+    }
+}
+
+__device__ __forceinline__ StepOut apply_action(EnvRec& r, long long action, int tx, int ty, bool inb,
+                                                uint64_t row_word, uint64_t* word_ptr,
+                                                uint16_t* visits_e, int TW, int max_steps) {
+    StepOut o;
+    o.watered = 0;
+    r.step += 1;                                           // :162
+    const int t = inb ? cell_of(row_word, ty & 31) : kObstacle;
+    if (action < 4) {
+        if (t != kObstacle) {                              // :193-195 (plants are walkable)
+            uint16_t* vp = visits_e + visit_index(tx, ty, TW);
+            const unsigned v = *vp;
+            const bool fresh = (v == 0);                   // :197
+            *vp = (uint16_t)(v < 65535u ? v + 1u : 65535u);  // :203
+            r.x = tx; r.y = ty;                            // :199
+            r.explored += fresh;                           // explored_map>0 count, :198-200,320
+            o.ridx = fresh ? 0 : 1;                        // R_EXPLORATION / R_REVISIT
+        } else {
+            r.flags |= kFlagCollided;                      // :209
+            r.collisions += 1;                             // :210
+            o.ridx = 2;                                    // R_INVALID
+        }
+    } else {
+        if (t == kThirsty) {                               // :217-219
+            *word_ptr = row_word ^ (1ull << (2 * (ty & 31)));  // 3 -> 2
+            r.thirsty -= 1;
+            r.watered += 1;
+            o.watered = 1;
+            o.ridx = 3;                                    // R_GOAL
+        } else if (t == kHydrated) {
+            o.ridx = 5;                                    // documented R_MISTAKE (see plantos.h)
+        } else {
+            o.ridx = 4;                                    // R_WATER_EMPTY, :221-222
+        }
+    }
+    o.terminated = r.explored >= r.total_free;             // exploration_percentage >= 100
+    o.truncated = r.step >= max_steps;
+    if (o.terminated && !(r.flags & kFlagBonus)) {         // :179-181
+        o.ridx += kRwCount;
+        r.flags |= kFlagBonus;
+    }
+    return o;
+}
+
+}  // namespace plantos_dev

@@ -1,0 +1,402 @@
+// plantos_generic.cuh -- one-warp-per-env kernels: any supported (G, P, O, R, C).
+//
+//   k_step_generic   PlantOSEnv.step + SB3 auto-reset            (plantos_env.py:160-183)
+//   k_reset_all      PlantOSEnv.reset for every env              (plantos_env.py:125-158)
+//   k_get_state / k_set_state / k_get_scalars / k_get_returns / k_stats_out
+//
+// The warp-cooperative pieces (reset_env_warp, build_obs_warp) are also the rare-path
+// (auto-reset) code of the fast kernel in plantos_fast.cuh.
+#pragma once
+#include "plantos_common.cuh"
+
+namespace plantos_dev {
+
+constexpr int kGenericWarps = 8;  // warps (= envs in flight) per block
+
+// per-warp scratch: the env's type plane (G*W u64) followed by one observation row
+__host__ __device__ inline int generic_warp_scratch_bytes(int G, int W, int D) {
+    return align_up(G * W * 8, 16) + align_up(D * 4, 16);
+}
+
+// ----------------------------------------------------------------- observation
+// plantos_env.py:251-315.  `plane` (shared memory) must hold the type rows x-R .. x+R that
+// lie inside the grid; visits are read from global memory.  All 32 lanes participate.
+__device__ __forceinline__ void build_obs_warp(const Params& p, const Tables& t, const uint64_t* plane,
+                                               const uint16_t* visits_e, int x, int y, float* obs_s, int lane) {
+    const int G = p.G, W = p.W, R = p.R, C = p.C;
+    for (int i = lane; i < C; i += 32) {                 // one lane per ray
+        int dist = R, kind = kEmpty;                     // :262-263
+        const int8_t* o = t.off + i * R * 2;
+        for (int r = 1; r <= R; ++r) {                   // integer march over the offset table
+            const int cx = x + o[2 * (r - 1)];
+            const int cy = y + o[2 * (r - 1) + 1];
+            int tt;
+            if ((unsigned)cx >= (unsigned)G || (unsigned)cy >= (unsigned)G) tt = kObstacle;  // :271-274
+            else tt = cell_of(plane[cx * W + (cy >> 5)], cy & 31);                           // :277-284
+            if (tt != kEmpty) { dist = r; kind = tt; break; }
+        }
+        float* q = obs_s + 5 * i;                        // :286-292
+        q[0] = t.dist[dist];
+        q[1] = (kind == kEmpty) ? 1.0f : 0.0f;
+        q[2] = (kind == kObstacle) ? 1.0f : 0.0f;
+        q[3] = (kind == kHydrated) ? 1.0f : 0.0f;
+        q[4] = (kind == kThirsty) ? 1.0f : 0.0f;
+    }
+    if (lane == 0) {                                     // :294-296
+        obs_s[5 * C] = t.pos[x];
+        obs_s[5 * C + 1] = t.pos[y];
+    }
+    if (lane < 25) {                                     // :298-313
+        const int gx = x + lane / 5 - 2;
+        const int gy = y + lane % 5 - 2;
+        float v = 1.0f;
+        if ((unsigned)gx < (unsigned)G && (unsigned)gy < (unsigned)G) {
+            const unsigned cnt = visits_e[visit_index(gx, gy, p.TW)];
+            v = t.visit[cnt < 10u ? cnt : 10u];
+        }
+        obs_s[5 * C + 2 + lane] = v;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void store_obs_row(const float* obs_s, float* dst, int D, int lane) {
+    for (int i = lane; i < D; i += 32) dst[i] = obs_s[i];
+}
+
+// ----------------------------------------------------------------------- reset
+// New episode for env e (local index): builds the map in `plane` (shared), writes the type
+// plane and a zeroed visit plane (rover cell = 1, plantos_env.py:146-147) to global memory
+// and returns the fresh record in all lanes.  `episode` selects the injected map / Philox
+// counter and is stored incremented.
+__device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int episode, uint64_t* plane, int lane) {
+    const int G = p.G, W = p.W;
+    const int nwords = G * W;
+    int rx = 0, ry = 0;
+    if (p.map_source == 1) {
+        // recorded map (replaces plantos_env.py:338-372 for equivalence runs)
+        int k = episode;
+        if (k >= p.map_episodes) {
+            if (lane == 0) atomicExch(p.err, -3);  // PLANTOS_ENOMAPS
+            k = k % p.map_episodes;
+        }
+        const size_t mi = (size_t)e * p.map_episodes + k;
+        const uint8_t* mc = p.map_cells + mi * (size_t)(G * G);
+        for (int idx = lane; idx < nwords; idx += 32) {
+            const int row = idx / W, w = idx - row * W;
+            uint64_t word = 0;
+            for (int c = 0; c < 32; ++c) {
+                const int col = w * 32 + c;
+                const uint64_t code = (col < G) ? (uint64_t)(mc[row * G + col] & 3) : (uint64_t)kObstacle;
+                word |= code << (2 * c);
+            }
+            plane[idx] = word;
+        }
+        rx = p.map_rover[mi * 2];
+        ry = p.map_rover[mi * 2 + 1];
+        __syncwarp();
+    } else {
+        // procedural map, same construction as plantos_env.py:338-372 with Philox draws
+        for (int idx = lane; idx < nwords; idx += 32) {
+            const int w = idx % W;
+            plane[idx] = kObstAll & ~col_mask(G, w);     // only the beyond-grid padding
+        }
+        __syncwarp();
+        const long long genv = p.env_base + e;
+        for (int k = lane; k < p.nclusters; k += 32) {   // :343-354, one cluster per lane
+            uint32_t d[4];
+            map_draw(p, genv, episode, 0, (uint32_t)k, d);
+            const int cx = 2 + (int)bounded(d[0], (uint32_t)(G - 4));   // randint(2, G-3)
+            const int cy = 2 + (int)bounded(d[1], (uint32_t)(G - 4));
+            const int size = 2 + (int)(d[2] >> 31);                     // choice([2, 3])
+            for (int dx = 0; dx < size; ++dx)
+                for (int dy = 0; dy < size; ++dy) {
+                    const int ox = cx + dx - 1, oy = cy + dy - 1;       // size // 2 == 1
+                    if ((unsigned)ox < (unsigned)G && (unsigned)oy < (unsigned)G)
+                        atomicOr(reinterpret_cast<unsigned long long*>(&plane[ox * W + (oy >> 5)]),
+                                 1ull << (2 * (oy & 31)));
+                }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            // plants: uniform sample without replacement from the free cells (:366) by
+            // rejection, thirsty with probability thirsty_plant_prob (:368)
+            uint32_t j = 0;
+            const uint32_t ncell = (uint32_t)(G * G);
+            for (int placed = 0; placed < p.P && j < (1u << 20); ++j) {
+                uint32_t d[4];
+                map_draw(p, genv, episode, 1, j, d);
+                const int cell = (int)bounded(d[0], ncell);
+                const int cx = cell / G, cy = cell - cx * G;
+                uint64_t& word = plane[cx * W + (cy >> 5)];
+                if (cell_of(word, cy & 31) == kEmpty) {
+                    const uint64_t code = ((unsigned long long)d[1] < p.thirsty_thresh) ? kThirsty : kHydrated;
+                    word |= code << (2 * (cy & 31));
+                    ++placed;
+                }
+            }
+            // rover: uniform over free cells that hold no plant (:372)
+            for (j = 0; j < (1u << 20); ++j) {
+                uint32_t d[4];
+                map_draw(p, genv, episode, 2, j, d);
+                const int cell = (int)bounded(d[0], ncell);
+                const int cx = cell / G, cy = cell - cx * G;
+                if (cell_of(plane[cx * W + (cy >> 5)], cy & 31) == kEmpty) { rx = cx; ry = cy; break; }
+            }
+        }
+        rx = __shfl_sync(0xffffffffu, rx, 0);
+        ry = __shfl_sync(0xffffffffu, ry, 0);
+        __syncwarp();
+    }
+    // counts + write-out
+    int n_obst = 0, n_thirsty = 0;
+    uint64_t* types_e = p.types + (size_t)e * nwords;
+    for (int idx = lane; idx < nwords; idx += 32) {
+        const uint64_t word = plane[idx];
+        const uint64_t m = col_mask(G, idx % W);
+        n_obst += __popcll(word & ~(word >> 1) & m);
+        n_thirsty += __popcll(word & (word >> 1) & m);
+        types_e[idx] = word;
+    }
+    n_obst = warp_sum_i(n_obst);
+    n_thirsty = warp_sum_i(n_thirsty);
+    uint4* vt = reinterpret_cast<uint4*>(p.visits + (size_t)e * p.VT * 16);
+    const int rtile = (rx >> 2) * p.TW + (ry >> 2);
+    const int rwithin = ((rx & 3) << 2) + (ry & 3);
+    for (int tile = lane; tile < p.VT; tile += 32) {
+        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (tile == rtile) w[rwithin >> 1] = 1u << (16 * (rwithin & 1));
+        vt[2 * tile] = make_uint4(w[0], w[1], w[2], w[3]);
+        vt[2 * tile + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+    __syncwarp();
+    EnvRec r;
+    r.x = rx; r.y = ry; r.flags = 0; r.thirsty = n_thirsty;
+    r.step = 0; r.explored = 1;                          // :130-133, :236
+    r.total_free = G * G - n_obst; r.collisions = 0;
+    r.episode = episode + 1; r.watered = 0; r.ret = 0.0;
+    return r;
+}
+
+// episode statistics of finished envs -> fixed-point accumulators (one atomic per warp)
+__device__ __forceinline__ void accumulate_stats(const Params& p, bool done, const EnvRec& r, int terminated,
+                                                 int truncated, int lane) {
+    if (__ballot_sync(0xffffffffu, done) == 0u) return;
+    long long v[kStatCount];
+    v[0] = done ? 1 : 0;
+    v[1] = done ? __double2ll_rn(r.ret * 1e6) : 0;
+    v[2] = done ? r.step : 0;
+    v[3] = done ? __double2ll_rn(((double)r.explored / (double)r.total_free) * 100.0 * 1e6) : 0;
+    v[4] = done ? r.collisions : 0;
+    v[5] = done ? r.watered : 0;
+    v[6] = (done && terminated) ? 1 : 0;
+    v[7] = (done && truncated) ? 1 : 0;
+#pragma unroll
+    for (int i = 0; i < kStatCount; ++i) {
+        const long long s = warp_sum_ll(v[i]);
+        if (lane == 0 && s != 0) atomicAdd(&p.stats[i], (unsigned long long)s);
+    }
+}
+
+// --------------------------------------------------------------- step (generic)
+__global__ void __launch_bounds__(kGenericWarps * 32)
+k_step_generic(const Params p, const StepIO io) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Tables t = load_tables(p, smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwords = p.G * p.W;
+    unsigned char* scratch = smem + tables_bytes(p.G, p.R, p.C) + warp * generic_warp_scratch_bytes(p.G, p.W, p.D);
+    uint64_t* plane = reinterpret_cast<uint64_t*>(scratch);
+    float* obs_s = reinterpret_cast<float*>(scratch + align_up(nwords * 8, 16));
+
+    for (int e = blockIdx.x * kGenericWarps + warp; e < p.N; e += gridDim.x * kGenericWarps) {
+        uint4 ra = make_uint4(0, 0, 0, 0), rb = ra;
+        long long action = 0;
+        if (lane == 0) {
+            ra = p.rec[2 * (size_t)e];
+            rb = p.rec[2 * (size_t)e + 1];
+            action = io.actions[e];
+        }
+        const unsigned posw = __shfl_sync(0xffffffffu, ra.x, 0);
+        int x = posw & 0xff, y = (posw >> 8) & 0xff;
+        uint64_t* types_e = p.types + (size_t)e * nwords;
+        uint16_t* visits_e = p.visits + (size_t)e * p.VT * 16;
+
+        // stage the rows the step can look at: x-R-1 .. x+R+1 (move of one row + LIDAR reach)
+        const int lo = max(0, x - p.R - 1), hi = min(p.G - 1, x + p.R + 1);
+        for (int idx = lo * p.W + lane; idx < (hi + 1) * p.W; idx += 32) plane[idx] = types_e[idx];
+        __syncwarp();
+
+        int flagw = 0;
+        EnvRec r;
+        if (lane == 0) {
+            r = unpack_rec(ra, rb);
+            int tx, ty; bool inb;
+            action_target(r, action, p.G, tx, ty, inb);
+            const int widx = inb ? tx * p.W + (ty >> 5) : 0;
+            const uint64_t word = inb ? plane[widx] : kObstAll;
+            uint64_t newword = word;
+            const StepOut o = apply_action(r, action, tx, ty, inb, word, &newword, visits_e, p.TW, p.max_steps);
+            if (o.watered) { plane[widx] = newword; types_e[widx] = newword; }
+            r.ret += t.rw64[o.ridx];
+            io.reward[e] = t.rw32[o.ridx];
+            const int done = o.terminated | o.truncated;
+            io.done[e] = (uint8_t)done;
+            if (io.terminated) io.terminated[e] = (uint8_t)o.terminated;
+            if (io.truncated) io.truncated[e] = (uint8_t)o.truncated;
+            flagw = r.x | (r.y << 8) | (done << 16) | (o.terminated << 17) | (o.truncated << 18);
+        }
+        __syncwarp();
+        flagw = __shfl_sync(0xffffffffu, flagw, 0);
+        x = flagw & 0xff; y = (flagw >> 8) & 0xff;
+        const bool done = (flagw >> 16) & 1;
+
+        build_obs_warp(p, t, plane, visits_e, x, y, obs_s, lane);
+        float* obs_row = io.obs + (size_t)e * p.D;
+        if (!done) {
+            store_obs_row(obs_s, obs_row, p.D, lane);
+            if (lane == 0) pack_rec(r, ra, rb);
+        } else {
+            // SB3 auto-reset: terminal observation + info snapshot, then a fresh episode
+            if (io.terminal_obs) store_obs_row(obs_s, io.terminal_obs + (size_t)e * p.D, p.D, lane);
+            int episode = 0;
+            if (lane == 0) {
+                pack_rec(r, ra, rb);
+                p.term_rec[2 * (size_t)e] = ra;
+                p.term_rec[2 * (size_t)e + 1] = rb;
+                episode = r.episode;
+            }
+            accumulate_stats(p, lane == 0, r, (flagw >> 17) & 1, (flagw >> 18) & 1, lane);
+            episode = __shfl_sync(0xffffffffu, episode, 0);
+            __syncwarp();
+            const EnvRec nr = reset_env_warp(p, e, episode, plane, lane);
+            build_obs_warp(p, t, plane, visits_e, nr.x, nr.y, obs_s, lane);
+            store_obs_row(obs_s, obs_row, p.D, lane);
+            if (lane == 0) pack_rec(nr, ra, rb);
+        }
+        if (lane == 0) {
+            p.rec[2 * (size_t)e] = ra;
+            p.rec[2 * (size_t)e + 1] = rb;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ reset (all)
+__global__ void __launch_bounds__(kGenericWarps * 32)
+k_reset_all(const Params p, float* obs) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Tables t = load_tables(p, smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwords = p.G * p.W;
+    unsigned char* scratch = smem + tables_bytes(p.G, p.R, p.C) + warp * generic_warp_scratch_bytes(p.G, p.W, p.D);
+    uint64_t* plane = reinterpret_cast<uint64_t*>(scratch);
+    float* obs_s = reinterpret_cast<float*>(scratch + align_up(nwords * 8, 16));
+    for (int e = blockIdx.x * kGenericWarps + warp; e < p.N; e += gridDim.x * kGenericWarps) {
+        int episode = 0;
+        if (lane == 0) episode = (int)p.rec[2 * (size_t)e].w;
+        episode = __shfl_sync(0xffffffffu, episode, 0);
+        const EnvRec nr = reset_env_warp(p, e, episode, plane, lane);
+        const uint16_t* visits_e = p.visits + (size_t)e * p.VT * 16;
+        build_obs_warp(p, t, plane, visits_e, nr.x, nr.y, obs_s, lane);
+        store_obs_row(obs_s, obs + (size_t)e * p.D, p.D, lane);
+        if (lane == 0) {
+            uint4 ra, rb;
+            pack_rec(nr, ra, rb);
+            p.rec[2 * (size_t)e] = ra;
+            p.rec[2 * (size_t)e + 1] = rb;
+        }
+        __syncwarp();
+    }
+}
+
+// --------------------------------------------------------------- state access
+__global__ void k_get_state(const Params p, uint8_t* cells, int32_t* visits) {
+    const int gg = p.G * p.G;
+    const size_t total = (size_t)p.N * gg;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int e = (int)(i / gg), c = (int)(i - (size_t)e * gg);
+        const int x = c / p.G, y = c - x * p.G;
+        if (cells) cells[i] = (uint8_t)cell_of(p.types[(size_t)e * p.G * p.W + x * p.W + (y >> 5)], y & 31);
+        if (visits) visits[i] = (int32_t)p.visits[(size_t)e * p.VT * 16 + visit_index(x, y, p.TW)];
+    }
+}
+
+// warp per env; recomputes total_cells / thirsty from the cells
+__global__ void k_set_state(const Params p, const uint8_t* cells, const int32_t* visits, const int32_t* sc) {
+    const int lane = threadIdx.x & 31;
+    const int e = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    if (e >= p.N) return;
+    const int G = p.G, W = p.W, nwords = G * W, gg = G * G;
+    uint4 ra = p.rec[2 * (size_t)e], rb = p.rec[2 * (size_t)e + 1];
+    EnvRec r = unpack_rec(ra, rb);
+    uint64_t* types_e = p.types + (size_t)e * nwords;
+    if (cells) {
+        int n_obst = 0, n_thirsty = 0;
+        for (int idx = lane; idx < nwords; idx += 32) {
+            const int row = idx / W, w = idx - row * W;
+            uint64_t word = 0;
+            for (int c = 0; c < 32; ++c) {
+                const int col = w * 32 + c;
+                const uint64_t code = (col < G) ? (uint64_t)(cells[(size_t)e * gg + row * G + col] & 3) : (uint64_t)kObstacle;
+                word |= code << (2 * c);
+            }
+            types_e[idx] = word;
+            const uint64_t m = col_mask(G, w);
+            n_obst += __popcll(word & ~(word >> 1) & m);
+            n_thirsty += __popcll(word & (word >> 1) & m);
+        }
+        r.total_free = gg - warp_sum_i(n_obst);
+        r.thirsty = warp_sum_i(n_thirsty);
+    }
+    if (visits) {
+        uint16_t* ve = p.visits + (size_t)e * p.VT * 16;
+        for (int i = lane; i < p.VT * 16; i += 32) {
+            const int tile = i >> 4, within = i & 15;
+            const int x = (tile / p.TW) * 4 + (within >> 2), y = (tile % p.TW) * 4 + (within & 3);
+            int v = 0;
+            if (x < G && y < G) v = visits[(size_t)e * gg + x * G + y];
+            ve[i] = (uint16_t)(v < 0 ? 0 : (v > 65535 ? 65535 : v));
+        }
+    }
+    if (sc) {
+        const size_t n = p.N;
+        r.x = sc[0 * n + e]; r.y = sc[1 * n + e]; r.step = sc[2 * n + e]; r.explored = sc[3 * n + e];
+        r.collisions = sc[6 * n + e];
+        r.flags = (sc[7 * n + e] ? kFlagCollided : 0) | (sc[8 * n + e] ? kFlagBonus : 0);
+        r.episode = sc[9 * n + e]; r.watered = sc[10 * n + e];
+    }
+    if (lane == 0) {
+        pack_rec(r, ra, rb);
+        p.rec[2 * (size_t)e] = ra;
+        p.rec[2 * (size_t)e + 1] = rb;
+    }
+}
+
+__global__ void k_get_scalars(const Params p, int which, int32_t* out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.N) return;
+    const uint4* src = which ? p.term_rec : p.rec;
+    const EnvRec r = unpack_rec(src[2 * (size_t)e], src[2 * (size_t)e + 1]);
+    const size_t n = p.N;
+    out[0 * n + e] = r.x; out[1 * n + e] = r.y; out[2 * n + e] = r.step; out[3 * n + e] = r.explored;
+    out[4 * n + e] = r.total_free; out[5 * n + e] = r.thirsty; out[6 * n + e] = r.collisions;
+    out[7 * n + e] = (r.flags & kFlagCollided) ? 1 : 0; out[8 * n + e] = (r.flags & kFlagBonus) ? 1 : 0;
+    out[9 * n + e] = r.episode; out[10 * n + e] = r.watered;
+}
+
+__global__ void k_get_returns(const Params p, int which, double* out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.N) return;
+    const uint4* src = which ? p.term_rec : p.rec;
+    out[e] = unpack_rec(src[2 * (size_t)e], src[2 * (size_t)e + 1]).ret;
+}
+
+__global__ void k_stats_out(unsigned long long* acc, double* out, int clear) {
+    const int i = threadIdx.x;
+    if (i >= kStatCount) return;
+    const long long v = (long long)acc[i];
+    out[i] = (i == 1 || i == 3) ? (double)v * 1e-6 : (double)v;
+    if (clear) acc[i] = 0ull;
+}
+
+}  // namespace plantos_dev

@@ -1,0 +1,421 @@
+"""PlantOSVecEnv -- the SB3-style `VecEnv` face of the B200 simulator.
+
+Drop-in for `DummyVecEnv([lambda: Monitor(PlantOSEnv(**kw))] * n)` as the reference's
+trainers build it (A2C_training.py:116-125,216-218; trainingCode.py:109,130,216):
+`reset()`, `step_async(actions)`, `step_wait()`, `step()`, `close()`, `num_envs`,
+`observation_space`, `action_space`, `get_attr`/`set_attr`/`env_method`/`env_is_wrapped`/
+`seed`.  Differences a caller sees: arrays are CUDA-resident torch tensors that the next
+step overwrites, and `infos` is a lazy sequence (dicts are built on access) unless
+`full_infos=True`.
+
+Everything is computed by libplantos_b200.so (include/plantos.h) -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import tables
+
+try:  # real spaces when gymnasium is installed (it is not in the build image)
+    from gymnasium import spaces as _spaces  # type: ignore
+except Exception:  # pragma: no cover - exercised in the build image
+    _spaces = None
+
+
+class _Discrete:
+    def __init__(self, n: int):
+        self.n = int(n)
+        self.shape = ()
+        self.dtype = np.dtype(np.int64)
+
+    def contains(self, x) -> bool:
+        return isinstance(x, (int, np.integer)) and 0 <= int(x) < self.n
+
+    def sample(self) -> int:
+        return int(np.random.randint(self.n))
+
+
+class _Box:
+    def __init__(self, low, high, shape, dtype):
+        self.shape = tuple(shape)
+        self.dtype = np.dtype(dtype)
+        self.low = np.full(self.shape, low, dtype=self.dtype)
+        self.high = np.full(self.shape, high, dtype=self.dtype)
+
+
+PRESETS: Dict[str, Dict[str, int]] = {
+    # ctor defaults, plantos_env.py:25-26 (D = 77)
+    "default": dict(grid_size=21, num_plants=8, num_obstacles=50, lidar_range=2, lidar_channels=10),
+    # A2C_training.py:206-212 / trainingCode.py:120-126 (D = 107)
+    "training": dict(grid_size=25, num_plants=10, num_obstacles=12, lidar_range=6, lidar_channels=16),
+    # large-map stress configuration of BASELINE.json configs[4]
+    "xl": dict(grid_size=64, num_plants=64, num_obstacles=600, lidar_range=32, lidar_channels=16),
+}
+
+_KERNELS = {"auto": nat.KERNEL_AUTO, "generic": nat.KERNEL_GENERIC, "fast": nat.KERNEL_FAST}
+
+
+class LazyInfos(Sequence):
+    """`infos` of one step: behaves like SB3's list of dicts, built on access.
+
+    Keys per env: the 12 of PlantOSEnv._get_info (plantos_env.py:323-336); for finished
+    envs additionally `terminal_observation`, `TimeLimit.truncated` and Monitor's
+    `episode = {r, l, t}`.  The scalar snapshot is pulled from the device on first access,
+    so read it before the next `step_async`.
+    """
+
+    def __init__(self, env: "PlantOSVecEnv"):
+        self._env = env
+        self._snap: Optional[Dict[str, np.ndarray]] = None
+
+    def __len__(self) -> int:
+        return self._env.num_envs
+
+    def snapshot(self) -> Dict[str, np.ndarray]:
+        if self._snap is None:
+            self._snap = self._env._info_snapshot()
+        return self._snap
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        n = len(self)
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError(i)
+        s = self.snapshot()
+        env = self._env
+        done = bool(s["done"][i])
+        src = s["term"] if done else s["live"]
+        explored, total = int(src["explored_cells"][i]), int(src["total_cells"][i])
+        thirsty = int(src["thirsty_plants"][i])
+        info: Dict[str, Any] = {
+            "rover_position": (int(src["x"][i]), int(src["y"][i])),
+            "thirsty_plants": thirsty,
+            "hydrated_plants": env.num_plants - thirsty,
+            "total_plants": env.num_plants,
+            "step_count": int(src["step_count"][i]),
+            "explored_cells": explored,
+            "total_cells": total,
+            "exploration_percentage": (explored / total) * 100,
+            "lidar_range": env.lidar_range,
+            "lidar_channels": env.lidar_channels,
+            "collided_with_wall": bool(src["collided_with_wall"][i]),
+            "total_collisions": int(src["total_collisions"][i]),
+            "TimeLimit.truncated": bool(s["truncated"][i]) and not bool(s["terminated"][i]),
+        }
+        if done:
+            info["episode"] = {"r": round(float(s["term_return"][i]), 6),
+                               "l": int(src["step_count"][i]),
+                               "t": round(time.time() - env._t_start, 6)}
+            if env._terminal_obs is not None:
+                info["terminal_observation"] = env._terminal_obs[i]
+        return info
+
+
+class PlantOSVecEnv:
+    """N PlantOS envs on one B200, one kernel launch per `step`."""
+
+    def __init__(self, num_envs: int, device: Any = "cuda:0", *,
+                 grid_size: int = 21, num_plants: int = 8, num_obstacles: int = 50,
+                 lidar_range: int = 2, lidar_channels: int = 10, thirsty_plant_prob: float = 0.7,
+                 max_steps: int = 1000, seed: int = 0, map_source: str = "philox",
+                 env_id_base: int = 0, kernel: str = "auto",
+                 rewards: Optional[Dict[str, float]] = None,
+                 track_terminal_obs: bool = True, full_infos: Optional[bool] = None):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("PlantOSVecEnv runs on a CUDA device only (no CPU path)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("PlantOSVecEnv needs a CUDA device; torch.cuda.is_available() is False")
+        if map_source not in ("philox", "injected"):
+            raise ValueError("map_source must be 'philox' or 'injected'")
+        self._lib = nat.load()
+        self.num_envs = int(num_envs)
+        self.grid_size, self.num_plants, self.num_obstacles = int(grid_size), int(num_plants), int(num_obstacles)
+        self.lidar_range, self.lidar_channels = int(lidar_range), int(lidar_channels)
+        self.thirsty_plant_prob = float(thirsty_plant_prob)
+        self.max_steps = int(max_steps)
+        self.rewards = dict(tables.DEFAULT_REWARDS)
+        if rewards:
+            self.rewards.update(rewards)
+        self.obs_dim = 5 * self.lidar_channels + 2 + 25
+        self.map_source = map_source
+        self.full_infos = (self.num_envs <= 64) if full_infos is None else bool(full_infos)
+
+        cfg = nat.Config()
+        nat.check(self._lib.plantos_default_config(C.byref(cfg)))
+        cfg.num_envs = self.num_envs
+        cfg.env_id_base = int(env_id_base)
+        cfg.grid_size, cfg.num_plants, cfg.num_obstacles = self.grid_size, self.num_plants, self.num_obstacles
+        cfg.lidar_range, cfg.lidar_channels = self.lidar_range, self.lidar_channels
+        cfg.max_steps = self.max_steps
+        cfg.thirsty_plant_prob = self.thirsty_plant_prob
+        cfg.map_source = nat.MAPS_INJECTED if map_source == "injected" else nat.MAPS_PHILOX
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        for key, val in self.rewards.items():
+            setattr(cfg, key, float(val))
+        cfg.kernel = _KERNELS[kernel]
+        self._cfg = cfg
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", dev_index)
+        handle = C.c_void_p()
+        nat.check(self._lib.plantos_create(C.byref(cfg), dev_index, C.byref(handle)))
+        self._h = handle
+
+        # tables evaluated by the Python interpreter, exactly as the reference evaluates them
+        off = np.ascontiguousarray(tables.lidar_offsets(self.lidar_channels, self.lidar_range))
+        dist = tables.distance_table(self.lidar_range)
+        pos = tables.position_table(self.grid_size)
+        vis = tables.visit_table()
+        rw = tables.reward_table(self.rewards)
+        nat.check(self._lib.plantos_upload_tables(
+            self._h, off.ctypes.data, dist.ctypes.data, pos.ctypes.data, vis.ctypes.data, rw.ctypes.data))
+
+        n, d, dev = self.num_envs, self.obs_dim, self.device
+        self._obs = torch.empty((n, d), dtype=torch.float32, device=dev)
+        self._rewards = torch.empty(n, dtype=torch.float32, device=dev)
+        self._dones = torch.zeros(n, dtype=torch.bool, device=dev)
+        self._terminated = torch.zeros(n, dtype=torch.bool, device=dev)
+        self._truncated = torch.zeros(n, dtype=torch.bool, device=dev)
+        self._terminal_obs = torch.zeros((n, d), dtype=torch.float32, device=dev) if track_terminal_obs else None
+        self._actions: Optional[torch.Tensor] = None
+        self._scalars = torch.empty((nat.SC_COUNT, n), dtype=torch.int32, device=dev)
+        self._stats = torch.zeros(len(nat.STAT_NAMES), dtype=torch.float64, device=dev)
+        self._host: Optional[Dict[str, torch.Tensor]] = None
+        self._t_start = time.time()
+        self._waiting = False
+
+        if _spaces is not None:
+            self.action_space = _spaces.Discrete(5)                                   # plantos_env.py:41
+            self.observation_space = _spaces.Box(low=0, high=1.0, shape=(d,), dtype=np.float32)  # :59-63
+        else:
+            self.action_space = _Discrete(5)
+            self.observation_space = _Box(0, 1.0, (d,), np.float32)
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    @property
+    def kernel_name(self) -> str:
+        return self._lib.plantos_kernel_name(self._h).decode()
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.plantos_launch_count(self._h))
+
+    @property
+    def state_bytes_per_env(self) -> int:
+        return int(self._lib.plantos_state_bytes_per_env(self._h))
+
+    def check(self) -> None:
+        """Raise if a device-side error was flagged (synchronises the stream)."""
+        nat.check(self._lib.plantos_check(self._h, self._stream()))
+
+    # --------------------------------------------------------------------- maps
+    def push_maps(self, cells: np.ndarray, rover: np.ndarray) -> None:
+        """Injected-map mode: `cells` u8 [N, E, G, G] cell codes, `rover` [N, E, 2] starts;
+        env i consumes map (i, k) at its k-th reset."""
+        n, g = self.num_envs, self.grid_size
+        cells = np.ascontiguousarray(cells, dtype=np.uint8)
+        rover = np.ascontiguousarray(rover, dtype=np.int16)
+        if cells.ndim != 4 or cells.shape[0] != n or cells.shape[2:] != (g, g):
+            raise ValueError(f"cells must be [N={n}, E, {g}, {g}], got {cells.shape}")
+        e = cells.shape[1]
+        if rover.shape != (n, e, 2):
+            raise ValueError(f"rover must be [{n}, {e}, 2], got {rover.shape}")
+        nat.check(self._lib.plantos_push_maps(self._h, cells.ctypes.data, rover.ctypes.data, e))
+
+    # ------------------------------------------------------------- VecEnv surface
+    def reset(self) -> torch.Tensor:
+        nat.check(self._lib.plantos_reset(self._h, self._obs.data_ptr(), self._stream()))
+        self._dones.zero_()
+        self._terminated.zero_()
+        self._truncated.zero_()
+        self._waiting = False
+        return self._obs
+
+    def step_async(self, actions) -> None:
+        if not isinstance(actions, torch.Tensor):
+            actions = torch.as_tensor(np.asarray(actions), dtype=torch.int64)
+        if actions.dtype != torch.int64 or actions.device != self.device or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.int64, non_blocking=True).contiguous()
+        if actions.numel() != self.num_envs:
+            raise ValueError(f"expected {self.num_envs} actions, got {actions.numel()}")
+        self._actions = actions  # keep alive until the launch has consumed it
+        tobs = self._terminal_obs.data_ptr() if self._terminal_obs is not None else None
+        nat.check(self._lib.plantos_step(
+            self._h, actions.data_ptr(), self._obs.data_ptr(), self._rewards.data_ptr(),
+            self._dones.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr(),
+            tobs, self._stream()))
+        self._waiting = True
+
+    def step_wait(self):
+        if not self._waiting:
+            raise RuntimeError("step_wait() without step_async()")
+        self._waiting = False
+        infos = LazyInfos(self)
+        if self.full_infos:
+            infos = [infos[i] for i in range(self.num_envs)]
+        return self._obs, self._rewards, self._dones, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.plantos_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def seed(self, seed: Optional[int] = None) -> List[Optional[int]]:
+        # PlantOSEnv.reset(seed=) never reaches the map generator (plantos_env.py:127 vs :344);
+        # maps here come from the Philox key given at construction.
+        return [None] * self.num_envs
+
+    def get_attr(self, attr_name: str, indices=None) -> List[Any]:
+        return [getattr(self, attr_name)] * len(self._indices(indices))
+
+    def set_attr(self, attr_name: str, value: Any, indices=None) -> None:
+        raise NotImplementedError("env attributes are fixed at construction (they are baked into the device config)")
+
+    def env_method(self, method_name: str, *args, indices=None, **kwargs) -> List[Any]:
+        raise NotImplementedError(f"env_method({method_name!r}) is not available on the batched simulator")
+
+    def env_is_wrapped(self, wrapper_class, indices=None) -> List[bool]:
+        return [False] * len(self._indices(indices))
+
+    def _indices(self, indices) -> List[int]:
+        if indices is None:
+            return list(range(self.num_envs))
+        if isinstance(indices, int):
+            return [indices]
+        return list(indices)
+
+    # -------------------------------------------------- extra tensors of the last step
+    @property
+    def terminated(self) -> torch.Tensor:
+        return self._terminated
+
+    @property
+    def truncated(self) -> torch.Tensor:
+        return self._truncated
+
+    @property
+    def terminal_observation(self) -> Optional[torch.Tensor]:
+        """[N, D]; row i is valid where the last `dones[i]` was True."""
+        return self._terminal_obs
+
+    # --------------------------------------------------------------- host-buffer step
+    def step_host(self, actions: np.ndarray):
+        """numpy in / numpy out, like an SB3 numpy VecEnv: H2D actions, step, D2H results.
+        Uses pinned host buffers owned by this object; returns views of them."""
+        if self._host is None:
+            n, d = self.num_envs, self.obs_dim
+            self._host = {
+                "actions": torch.empty(n, dtype=torch.int64).pin_memory(),
+                "obs": torch.empty((n, d), dtype=torch.float32).pin_memory(),
+                "rewards": torch.empty(n, dtype=torch.float32).pin_memory(),
+                "dones": torch.empty(n, dtype=torch.bool).pin_memory(),
+            }
+        hb = self._host
+        hb["actions"].numpy()[:] = np.asarray(actions, dtype=np.int64).reshape(-1)
+        nat.check(self._lib.plantos_step_host(
+            self._h, hb["actions"].data_ptr(), hb["obs"].data_ptr(), hb["rewards"].data_ptr(),
+            hb["dones"].data_ptr(), self._stream()))
+        return hb["obs"].numpy(), hb["rewards"].numpy(), hb["dones"].numpy()
+
+    # ------------------------------------------------------------------- state / info
+    def scalars(self, terminal: bool = False) -> Dict[str, torch.Tensor]:
+        """Per-env integer state as int32 tensors (names: _native.SC_NAMES)."""
+        nat.check(self._lib.plantos_get_scalars(self._h, int(terminal), self._scalars.data_ptr(), self._stream()))
+        out = self._scalars.clone()
+        return {name: out[k] for k, name in enumerate(nat.SC_NAMES)}
+
+    def returns(self, terminal: bool = False) -> torch.Tensor:
+        out = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
+        nat.check(self._lib.plantos_get_returns(self._h, int(terminal), out.data_ptr(), self._stream()))
+        return out
+
+    def get_state(self) -> Dict[str, torch.Tensor]:
+        """cells u8 [N,G,G], visits i32 [N,G,G] and the scalar dict."""
+        n, g = self.num_envs, self.grid_size
+        cells = torch.empty((n, g, g), dtype=torch.uint8, device=self.device)
+        visits = torch.empty((n, g, g), dtype=torch.int32, device=self.device)
+        nat.check(self._lib.plantos_get_state(self._h, cells.data_ptr(), visits.data_ptr(), self._stream()))
+        state = {"cells": cells, "visits": visits}
+        state.update(self.scalars())
+        return state
+
+    def set_state(self, cells: Optional[torch.Tensor] = None, visits: Optional[torch.Tensor] = None,
+                  scalars: Optional[Dict[str, torch.Tensor]] = None) -> None:
+        def dev(t, dtype):
+            return None if t is None else torch.as_tensor(t).to(device=self.device, dtype=dtype).contiguous()
+        cells_t, visits_t = dev(cells, torch.uint8), dev(visits, torch.int32)
+        sc_t = None
+        if scalars is not None:
+            cur = self.scalars()
+            cur.update({k: torch.as_tensor(v).to(self.device, torch.int32) for k, v in scalars.items()})
+            sc_t = torch.stack([cur[name] for name in nat.SC_NAMES]).contiguous()
+        nat.check(self._lib.plantos_set_state(
+            self._h, cells_t.data_ptr() if cells_t is not None else None,
+            visits_t.data_ptr() if visits_t is not None else None,
+            sc_t.data_ptr() if sc_t is not None else None, self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()  # inputs may be temporaries
+
+    def _info_snapshot(self) -> Dict[str, Any]:
+        live = {k: v.cpu().numpy() for k, v in self.scalars(False).items()}
+        done = self._dones.cpu().numpy()
+        snap: Dict[str, Any] = {"live": live, "done": done,
+                                "terminated": self._terminated.cpu().numpy(),
+                                "truncated": self._truncated.cpu().numpy()}
+        if done.any():
+            snap["term"] = {k: v.cpu().numpy() for k, v in self.scalars(True).items()}
+            snap["term_return"] = self.returns(True).cpu().numpy()
+        return snap
+
+    # --------------------------------------------------------------- episode statistics
+    def episode_stats(self, clear: bool = False, all_reduce: bool = True) -> Dict[str, float]:
+        """Sums over finished episodes since construction / the last clear.  With
+        torch.distributed initialised the 8-vector is summed over ranks (NCCL on the GPU
+        ranks) -- the only inter-GPU traffic of the simulator."""
+        nat.check(self._lib.plantos_stats(self._h, self._stats.data_ptr(), int(clear), self._stream()))
+        vec = self._stats
+        if all_reduce:
+            vec = all_reduce_stats(vec)
+        vals = vec.cpu().tolist()
+        return dict(zip(nat.STAT_NAMES, vals))
+
+
+def all_reduce_stats(vec: torch.Tensor) -> torch.Tensor:
+    """Sum a rank-local statistics vector over the default process group (no-op if there is
+    none).  Works on NCCL (CUDA tensor) and gloo (CPU tensor) alike."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        vec = vec.clone()
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+    return vec
+
+
+def shard_range(total_envs: int, rank: int, world_size: int):
+    """Contiguous block of global env ids owned by `rank`: [start, start + count)."""
+    if not 0 <= rank < world_size:
+        raise ValueError("rank out of range")
+    base, rem = divmod(int(total_envs), int(world_size))
+    count = base + (1 if rank < rem else 0)
+    start = rank * base + min(rank, rem)
+    return start, count
