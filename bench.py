@@ -1,0 +1,377 @@
+#!/usr/bin/env python3
+"""bench.py -- env-steps/s of the PlantOS env-step hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one VecEnv.step over all envs (one fused kernel launch per GPU: transition +
+LIDAR observation + auto-reset).  Workload (BASELINE.json configs[3], the one the metric is
+quoted on): training preset G25/P10/O12/R6/C16 (D=107), 131 072 envs per GPU -- 1 048 576
+envs on 8 GPUs -- weak scaling, Philox maps, i.i.d. uniform actions.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events, max over
+ranks); `e2e` = the same metric through plantos_step_host with pinned HOST buffers (H2D
+actions, D2H obs/reward/done inside the timed region); `roofline` = algorithmic bytes
+(441 B per env-step at D=107) over the measured step time against the measured
+HBM copy peak; `cpu_baseline` = the oracle port of the reference on this box's host cores.
+`--impl reference` times that CPU implementation alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 131072
+PRESET = dict(grid_size=25, num_plants=10, num_obstacles=12, lidar_range=6, lidar_channels=16)
+OBS_DIM = 5 * PRESET["lidar_channels"] + 27
+B_ALG = 4 * OBS_DIM + 4 + 1 + 8          # obs f32[D] + reward f32 + done u8 + action i64
+ACTION_RING = 16
+OBS_RING = 5                              # rollout-buffer depth (A2C n_steps=5, A2C_training.py:229-247)
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def workload_name(n_gpus: int) -> str:
+    return (f"PlantOS training preset G25/P10/O12/R6/C16 (D=107), {ENVS_PER_GPU} envs/GPU x {n_gpus} GPU "
+            f"= {ENVS_PER_GPU * n_gpus} envs, fused step+LIDAR obs+auto-reset, random actions")
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------ CPU baseline (oracle port)
+def _cpu_worker(conn, n_envs, seed, literal_trig):
+    import random
+    import numpy as np
+    from oracle.plantos_oracle import OracleVecEnv
+    random.seed(seed)
+    rng = np.random.default_rng(seed)
+    env = OracleVecEnv(n_envs, literal_trig=literal_trig, **PRESET)
+    env.reset()
+    conn.send("ready")
+    while True:
+        msg = conn.recv()
+        if msg is None:
+            break
+        for _ in range(msg):  # msg = number of VecEnv steps to run
+            env.step(rng.integers(0, 5, size=n_envs))
+        conn.send(msg * n_envs)
+    conn.close()
+
+
+class CpuPool:
+    """One process per host core, each stepping its own slice of envs through the oracle's
+    DummyVecEnv+Monitor restatement (SubprocVecEnv's work without its pipe traffic: an
+    upper bound on what SB3's SubprocVecEnv could reach on these cores)."""
+
+    def __init__(self, envs_per_worker: int, workers: int | None = None):
+        self.workers = workers or (os.cpu_count() or 1)
+        self.envs_per_worker = envs_per_worker
+        ctx = mp.get_context("fork")
+        self.conns, self.procs = [], []
+        for w in range(self.workers):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_cpu_worker, args=(b, envs_per_worker, 1000 + w, True), daemon=True)
+            p.start()
+            self.conns.append(a)
+            self.procs.append(p)
+        for c in self.conns:
+            assert c.recv() == "ready"
+
+    @property
+    def num_envs(self) -> int:
+        return self.workers * self.envs_per_worker
+
+    def run(self, vec_steps: int) -> int:
+        for c in self.conns:
+            c.send(vec_steps)
+        return sum(c.recv() for c in self.conns)
+
+    def close(self):
+        for c in self.conns:
+            try:
+                c.send(None)
+            except Exception:
+                pass
+        for p in self.procs:
+            p.join(timeout=5)
+
+
+def cpu_baseline(seconds: float = 12.0):
+    pool = CpuPool(envs_per_worker=8)
+    pool.run(20)  # warm-up
+    t0 = time.perf_counter()
+    steps = 0
+    chunk = 100
+    while time.perf_counter() - t0 < seconds:
+        steps += pool.run(chunk)
+    dt = time.perf_counter() - t0
+    cores = pool.workers
+    n_envs = pool.num_envs
+    pool.close()
+    return {"value": steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} env-steps in {dt:.1f} s: {n_envs} envs (8 per process, {cores} processes, "
+                      f"no IPC on the step path) of the same preset, oracle/plantos_oracle.py"}
+
+
+def run_reference(args, rank: int):
+    """`--impl reference`: the reference's CPU implementation (oracle port) on all host cores."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # calibrate, then size the per-step sample so the K timed steps are ~20 s of CPU work
+    # (at least 8 envs per core) and bound the whole run to ~90 s
+    pool = CpuPool(envs_per_worker=8, workers=cores)
+    pool.run(5)
+    t0 = time.perf_counter()
+    done = pool.run(25)
+    rate = done / (time.perf_counter() - t0)
+    pool.close()
+    per_worker = int(min(256, max(8, rate * 20 / (max(1, args.steps) * cores))))
+    pool = CpuPool(envs_per_worker=per_worker, workers=cores)
+    n_envs = pool.num_envs
+    budget_steps = max(1, int(rate * 90 / n_envs))
+    total = args.steps + args.warmup
+    reps = 1
+    steps, warmup = args.steps, args.warmup
+    if total > budget_steps:  # each bench "step" = one VecEnv step of the sample; cap their number
+        scale = budget_steps / total
+        steps, warmup = max(1, int(args.steps * scale)), max(1, int(args.warmup * scale))
+    pool.run(warmup)
+    t0 = time.perf_counter()
+    n = pool.run(steps * reps)
+    dt = time.perf_counter() - t0
+    pool.close()
+    value = n / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "python float64 / int", "data": "synthetic",
+        "config": {"workload": workload_name(args.gpus), "sample_envs": n_envs,
+                   "note": "CPU port of plantos_env.py (oracle/plantos_oracle.py), one process per host core; "
+                           "each step is one VecEnv step over the sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} env-steps in {dt:.1f} s over {n_envs} envs"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._h = None
+
+    def sample(self):
+        if self._h is None:
+            return
+        nv = self._nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+            except Exception:
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                     0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
+            for bit, name in names.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            self.sample()
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        self.sample()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"], "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------ ours
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+    from rl_env_b200 import make_sharded
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs_per_gpu
+    env = make_sharded(n * world, rank, world, local_device=local_rank, seed=0, kernel=args.kernel,
+                       obs_ring=OBS_RING, track_terminal_obs=not args.no_terminal_obs, full_infos=False, **PRESET)
+    assert env.num_envs == n and env.obs_dim == OBS_DIM
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    actions = [torch.randint(0, 5, (n,), device=dev, dtype=torch.int64, generator=gen) for _ in range(ACTION_RING)]
+    env.reset()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_steps(k, start):
+        for i in range(start, start + k):
+            env.step_async(actions[i % ACTION_RING])
+            env.step_wait()
+            if world > 1 and args.stats_every and (i + 1) % args.stats_every == 0:
+                env.episode_stats_tensor(all_reduce=True)   # NCCL all-reduce of 8 doubles, no host sync
+
+    run_steps(args.warmup, 0)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.sample()
+    sampler.start()
+    launches0 = env.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_steps(args.steps, args.warmup)
+    e1.record()
+    barrier()
+    sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = env.launch_count - launches0
+    env.check()
+
+    # isolated duration of the step kernel: event pair around single launches
+    iso = []
+    for i in range(min(200, max(20, args.steps))):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        env.step_async(actions[i % ACTION_RING])
+        b.record()
+        env.step_wait()
+        iso.append((a, b))
+    torch.cuda.synchronize()
+    iso_us = sorted(a.elapsed_time(b) * 1e3 for a, b in iso)
+    iso_med_us = iso_us[len(iso_us) // 2]
+
+    # end to end through the host-buffer entry point (plantos_step_host)
+    import numpy as np
+    host_actions = [a.cpu().numpy() for a in actions[:4]]
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    for i in range(3):
+        env.step_host(host_actions[i % 4])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        env.step_host(host_actions[i % 4])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    stats = env.episode_stats_tensor(all_reduce=True).cpu().tolist()
+    t_ms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t_ms.tolist()
+    kernel_name = env.kernel_name
+    state_bytes = env.state_bytes_per_env
+    env.close()
+
+    if rank == 0:
+        total_envs = n * world
+        value = total_envs * args.steps / (ms * 1e-3)
+        peak, peak_src = measured_peak_gbs()
+        step_s = ms * 1e-3 / args.steps
+        achieved = n * B_ALG / step_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "int (2-bit cells, u16 visits) + f32 table-driven obs/reward", "data": "synthetic",
+            "config": {"workload": workload_name(world), "envs_per_gpu": n, "obs_dim": OBS_DIM,
+                       "kernel": kernel_name, "maps": "philox seed 0", "state_bytes_per_env": state_bytes,
+                       "l2": f"inputs larger than L2: per-GPU state {n * state_bytes / 1e6:.0f} MB + obs ring "
+                             f"{OBS_RING}x{n * OBS_DIM * 4 / 1e6:.0f} MB vs 126 MB L2; no explicit flush",
+                       "stats_allreduce_every": args.stats_every if world > 1 else 0},
+            "e2e": {"value": total_envs * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * (4 * OBS_DIM + 4 + 1),
+                    "steps": e2e_steps, "api": "plantos_step_host (pinned host buffers), per GPU"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "alg_bytes_per_env_step": B_ALG, "kernel": f"k_step_{kernel_name}",
+                         "avg_launch_us": step_s * 1e6, "isolated_launch_us_median": iso_med_us},
+            "clocks": sampler.summary(),
+            "episode_stats": dict(zip(("episodes", "return_sum", "length_sum", "exploration_pct_sum",
+                                       "collisions_sum", "watered_sum", "terminated", "truncated"), stats)),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fast"])
+    ap.add_argument("--stats-every", type=int, default=100)
+    ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-terminal-obs", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        print(f"note: --gpus {args.gpus} without torchrun; launch with torch.distributed.run "
+              f"--nproc-per-node {args.gpus}. Running 1 GPU.", file=sys.stderr)
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

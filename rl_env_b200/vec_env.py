@@ -129,7 +129,8 @@ class PlantOSVecEnv:
                  max_steps: int = 1000, seed: int = 0, map_source: str = "philox",
                  env_id_base: int = 0, kernel: str = "auto",
                  rewards: Optional[Dict[str, float]] = None,
-                 track_terminal_obs: bool = True, full_infos: Optional[bool] = None):
+                 track_terminal_obs: bool = True, full_infos: Optional[bool] = None,
+                 obs_ring: int = 1):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("PlantOSVecEnv runs on a CUDA device only (no CPU path)")
@@ -180,7 +181,12 @@ class PlantOSVecEnv:
             self._h, off.ctypes.data, dist.ctypes.data, pos.ctypes.data, vis.ctypes.data, rw.ctypes.data))
 
         n, d, dev = self.num_envs, self.obs_dim, self.device
-        self._obs = torch.empty((n, d), dtype=torch.float32, device=dev)
+        # obs_ring > 1 rotates the observation output through that many buffers (one per step),
+        # the way a rollout buffer [n_steps, N, D] is filled: step t's tensor stays valid for
+        # obs_ring - 1 further steps instead of being overwritten by the next one.
+        self._obs_ring = [torch.empty((n, d), dtype=torch.float32, device=dev) for _ in range(max(1, int(obs_ring)))]
+        self._ring_pos = 0
+        self._obs = self._obs_ring[0]
         self._rewards = torch.empty(n, dtype=torch.float32, device=dev)
         self._dones = torch.zeros(n, dtype=torch.bool, device=dev)
         self._terminated = torch.zeros(n, dtype=torch.bool, device=dev)
@@ -251,6 +257,9 @@ class PlantOSVecEnv:
         if actions.numel() != self.num_envs:
             raise ValueError(f"expected {self.num_envs} actions, got {actions.numel()}")
         self._actions = actions  # keep alive until the launch has consumed it
+        if len(self._obs_ring) > 1:
+            self._ring_pos = (self._ring_pos + 1) % len(self._obs_ring)
+            self._obs = self._obs_ring[self._ring_pos]
         tobs = self._terminal_obs.data_ptr() if self._terminal_obs is not None else None
         nat.check(self._lib.plantos_step(
             self._h, actions.data_ptr(), self._obs.data_ptr(), self._rewards.data_ptr(),
@@ -393,12 +402,14 @@ class PlantOSVecEnv:
         """Sums over finished episodes since construction / the last clear.  With
         torch.distributed initialised the 8-vector is summed over ranks (NCCL on the GPU
         ranks) -- the only inter-GPU traffic of the simulator."""
-        nat.check(self._lib.plantos_stats(self._h, self._stats.data_ptr(), int(clear), self._stream()))
-        vec = self._stats
-        if all_reduce:
-            vec = all_reduce_stats(vec)
-        vals = vec.cpu().tolist()
+        vals = self.episode_stats_tensor(clear=clear, all_reduce=all_reduce).cpu().tolist()
         return dict(zip(nat.STAT_NAMES, vals))
+
+    def episode_stats_tensor(self, clear: bool = False, all_reduce: bool = True) -> torch.Tensor:
+        """Same 8-vector as a float64 CUDA tensor, enqueued without a host sync (the kernel
+        and the collective are stream-ordered), for callers that poll it off the step path."""
+        nat.check(self._lib.plantos_stats(self._h, self._stats.data_ptr(), int(clear), self._stream()))
+        return all_reduce_stats(self._stats) if all_reduce else self._stats
 
 
 def all_reduce_stats(vec: torch.Tensor) -> torch.Tensor:

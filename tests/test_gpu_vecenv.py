@@ -1,0 +1,92 @@
+"""The SB3-facing surface: infos, Monitor episode records, episode statistics, spaces."""
+import numpy as np
+import pytest
+
+from replay import PyOracleBackend, fixture_kwargs, load_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+def test_infos_match_dummyvecenv_monitor():
+    """Step the restated DummyVecEnv+Monitor (oracle) and PlantOSVecEnv side by side on the
+    tiny fixture (terminations + truncations) and compare the info dicts key by key."""
+    from rl_env_b200 import PlantOSVecEnv
+    fx = load_fixture("replay_tiny_4env")
+    ora = PyOracleBackend(fx).env
+    env = PlantOSVecEnv(4, map_source="injected", max_steps=int(fx["cfg_max_steps"]), **fixture_kwargs(fx))
+    env.push_maps(fx["maps_cells"], fx["maps_rover"])
+    assert env.full_infos
+    assert env.observation_space.shape == (fx["obs"].shape[2],) and env.action_space.n == 5
+    o_obs, g_obs = ora.reset(), env.reset().cpu().numpy()
+    assert np.array_equal(o_obs, g_obs)
+    seen_done = 0
+    for t in range(700):
+        o_obs, o_rew, o_done, o_infos = ora.step(fx["actions"][t])
+        g_obs, g_rew, g_done, g_infos = env.step(fx["actions"][t])
+        assert np.array_equal(g_obs.cpu().numpy(), o_obs)
+        assert np.array_equal(g_rew.cpu().numpy(), o_rew)
+        assert np.array_equal(g_done.cpu().numpy(), o_done)
+        assert isinstance(g_infos, list) and len(g_infos) == 4
+        for i in range(4):
+            gi, oi = g_infos[i], o_infos[i]
+            for key in ("rover_position", "thirsty_plants", "hydrated_plants", "total_plants", "step_count",
+                        "explored_cells", "total_cells", "exploration_percentage", "lidar_range",
+                        "lidar_channels", "collided_with_wall", "total_collisions", "TimeLimit.truncated"):
+                assert gi[key] == oi[key], (t, i, key, gi[key], oi[key])
+            assert ("episode" in gi) == ("episode" in oi) == bool(o_done[i])
+            if o_done[i]:
+                seen_done += 1
+                assert gi["episode"]["r"] == oi["episode"]["r"] and gi["episode"]["l"] == oi["episode"]["l"]
+                assert np.array_equal(gi["terminal_observation"].cpu().numpy(), oi["terminal_observation"])
+    assert seen_done >= 3
+    stats = env.episode_stats(all_reduce=False)
+    k = fx["term_t"] < 700
+    assert stats["episodes"] == k.sum()
+    assert abs(stats["return_sum"] - fx["ep_r"][k].sum()) < 1e-6
+    assert stats["length_sum"] == fx["ep_l"][k].sum()
+    assert stats["terminated"] == fx["terminated"][:700].sum()
+    assert stats["truncated"] == fx["truncated"][:700].sum()
+    env.close()
+
+
+def test_lazy_infos_and_state_roundtrip():
+    from rl_env_b200 import LazyInfos, PlantOSVecEnv
+    env = PlantOSVecEnv(256, seed=2, grid_size=25, num_plants=10, num_obstacles=12, lidar_range=6, lidar_channels=16)
+    env.reset()
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        obs, rew, done, infos = env.step(rng.integers(0, 5, 256))
+    assert isinstance(infos, LazyInfos) and len(infos) == 256
+    info = infos[17]
+    assert info["step_count"] == 20 and info["total_plants"] == 10
+    # get_state -> set_state into a second simulator reproduces the trajectory (MCTS-style copy,
+    # mcts_custom_trainer.py:218-243)
+    st = env.get_state()
+    twin = PlantOSVecEnv(256, seed=99, grid_size=25, num_plants=10, num_obstacles=12, lidar_range=6, lidar_channels=16)
+    twin.reset()
+    twin.set_state(st["cells"], st["visits"], {k: st[k] for k in
+                   ("x", "y", "step_count", "explored_cells", "total_collisions", "collided_with_wall",
+                    "completion_bonus_given", "episode", "watered")})
+    for _ in range(30):
+        a = rng.integers(0, 5, 256)
+        o1, r1, d1, _ = env.step(a)
+        o2, r2, d2, _ = twin.step(a)
+        assert np.array_equal(o1.cpu().numpy(), o2.cpu().numpy())
+        assert np.array_equal(r1.cpu().numpy(), r2.cpu().numpy())
+    env.close(); twin.close()
+
+
+def test_step_host_matches_device_step():
+    from rl_env_b200 import PlantOSVecEnv
+    kw = dict(grid_size=21, num_plants=8, num_obstacles=50, lidar_range=2, lidar_channels=10)
+    a = PlantOSVecEnv(513, seed=5, **kw)
+    b = PlantOSVecEnv(513, seed=5, **kw)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(1)
+    for _ in range(25):
+        act = rng.integers(0, 5, 513)
+        o1, r1, d1, _ = a.step(act)
+        o2, r2, d2 = b.step_host(act)
+        assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
+        assert np.array_equal(d1.cpu().numpy(), d2)
+    a.close(); b.close()

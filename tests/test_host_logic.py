@@ -1,0 +1,57 @@
+"""Host-side logic that needs no GPU: sharding arithmetic, the Philox mirror, presets."""
+import random
+
+import numpy as np
+import pytest
+
+from rl_env_b200 import PRESETS, shard_range
+
+
+def test_shard_range_partitions_exactly():
+    for total in (1, 7, 8, 1000, 1048576):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+            for (s0, c0), (s1, _) in zip(spans, spans[1:]):
+                assert s0 + c0 == s1
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+    assert shard_range(1048576, 3, 8) == (393216, 131072)
+    with pytest.raises(ValueError):
+        shard_range(8, 8, 8)
+
+
+def test_presets_are_the_reference_configs():
+    assert PRESETS["default"] == dict(grid_size=21, num_plants=8, num_obstacles=50, lidar_range=2, lidar_channels=10)
+    assert PRESETS["training"] == dict(grid_size=25, num_plants=10, num_obstacles=12, lidar_range=6, lidar_channels=16)
+
+
+def test_philox_known_answers():
+    from oracle.philox_mapgen import philox4x32_10
+    # Random123 kat_vectors, philox4x32 10 rounds
+    assert philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)
+    assert philox4x32_10((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2) == (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)
+    assert philox4x32_10((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0)) == \
+        (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)
+
+
+def test_philox_mirror_builds_valid_maps_like_the_reference_generator():
+    """Construction invariants of plantos_env.py:338-372 hold for the Philox generator."""
+    from oracle.philox_mapgen import generate_map
+    from oracle.plantos_oracle import PlantOSOracle
+    kw = PRESETS["training"]
+    counts = []
+    for env_id in range(300):
+        cells, rover = generate_map(1, env_id, 0, kw["grid_size"], kw["num_plants"], kw["num_obstacles"])
+        assert (cells >= 2).sum() == kw["num_plants"]
+        assert cells[rover] == 0
+        assert not (cells[0] == 1).any() and not (cells[-1] == 1).any()
+        assert not (cells[:, 0] == 1).any() and not (cells[:, -1] == 1).any()
+        counts.append((cells == 1).sum())
+    random.seed(0)
+    ref = PlantOSOracle(**kw)
+    ref_counts = []
+    for _ in range(300):
+        ref.generate_map()
+        ref_counts.append(len(ref.obstacles))
+    assert abs(np.mean(counts) - np.mean(ref_counts)) < 1.5   # SURVEY: mean 25.5 for this preset
+    assert min(counts) >= 4 and max(counts) <= 36

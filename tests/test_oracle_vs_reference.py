@@ -1,0 +1,86 @@
+"""Pin the oracle port against the UNMODIFIED reference, run side by side (build container
+only: the reference checkout is not shipped to the GPU box, where this module is skipped and
+the committed golden vectors take over)."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle.ref_shim import reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference checkout not mounted")
+
+
+@pytest.mark.parametrize("preset,seed,steps", [("T", 0, 1500), ("T", 3, 1200), ("DFLT", 1, 1500), ("XL", 0, 150)])
+def test_port_equals_reference_step_by_step(preset, seed, steps):
+    from oracle.plantos_oracle import PRESETS, PlantOSOracle
+    from oracle.ref_shim import ReferenceEnv
+    kw = PRESETS[preset]
+    ref, ora = ReferenceEnv(**kw), PlantOSOracle(**kw)
+    random.seed(seed)
+    o1, i1 = ref.reset()
+    random.seed(seed)
+    o2, i2 = ora.reset()
+    assert np.array_equal(o1.view(np.uint32), o2.view(np.uint32)) and o1.dtype == o2.dtype == np.float32
+    assert ref.env.obstacles == ora.obstacles and list(ref.env.plants.items()) == list(ora.plants.items())
+    assert ref.env.rover_pos == ora.rover_pos and set(i1) == set(i2)
+    rng = np.random.default_rng(seed)
+    for t in range(steps):
+        a = int(rng.integers(5))
+        r1, r2 = ref.step(a), ora.step(a)
+        assert np.array_equal(r1[0].view(np.uint32), r2[0].view(np.uint32)), t
+        assert r1[1] == r2[1] and r1[2] == r2[2] and r1[3] == r2[3], t
+        assert r1[4] == r2[4], t
+        assert np.array_equal(ref.env.visit_counts, ora.visit_counts)
+        assert np.array_equal(ref.env.explored_map, ora.explored_map)
+        if r1[2] or r1[3]:
+            state = random.getstate()
+            ref.reset()
+            random.setstate(state)
+            ora.reset()
+            assert ref.env.obstacles == ora.obstacles and list(ref.env.plants.items()) == list(ora.plants.items())
+            assert ref.env.rover_pos == ora.rover_pos
+    assert ref.mistake_steps == ora.mistake_steps
+
+
+def test_reference_bug_is_what_the_policy_says():
+    """plantos_env.py:213-222: watering a hydrated plant raises TypeError after step_count was
+    incremented and with nothing else changed; the shim substitutes the documented -10."""
+    from oracle.ref_shim import ReferenceEnv, load_reference
+    mod = load_reference()
+    env = mod.PlantOSEnv(grid_size=7, num_plants=3, num_obstacles=0)
+    random.seed(0)
+    env.reset()
+    pos = next(iter(env.plants))
+    env.plants[pos] = False
+    env.rover_pos = pos
+    before = (env.step_count, dict(env.plants), env.visit_counts.copy())
+    with pytest.raises(TypeError):
+        env.step(4)
+    assert env.step_count == before[0] + 1 and env.plants == before[1]
+    assert np.array_equal(env.visit_counts, before[2])
+    shim = ReferenceEnv(grid_size=7, num_plants=3, num_obstacles=0)
+    random.seed(0)
+    shim.reset()
+    shim.env.plants[pos] = False
+    shim.env.rover_pos = pos
+    _, reward, _, _, _ = shim.step(4)
+    assert reward == -0.1 + -10 and shim.mistake_steps == 1
+
+
+def test_golden_fixtures_are_reproducible():
+    """Regenerating a fixture from the reference gives the committed bytes' content."""
+    import importlib.util, os, tempfile
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    with tempfile.TemporaryDirectory() as tmp:
+        mg.OUT = tmp
+        name, n, steps, seed, kw, ms = mg.FIXTURES[3]
+        mg.record(name, n, steps, seed, kw, max_steps=ms)
+        new = np.load(os.path.join(tmp, name + ".npz"))
+        old = np.load(os.path.join(here, "golden", name + ".npz"))
+        assert set(new.files) == set(old.files)
+        for k in old.files:
+            assert np.array_equal(new[k], old[k]), k
