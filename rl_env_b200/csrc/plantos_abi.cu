@@ -199,7 +199,10 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     p.N = cfg->num_envs; p.env_base = cfg->env_id_base;
     p.G = cfg->grid_size; p.P = cfg->num_plants; p.O = cfg->num_obstacles;
     p.R = cfg->lidar_range; p.C = cfg->lidar_channels; p.D = plantos_obs_dim(cfg);
-    p.W = (p.G + 31) / 32; p.TW = (p.G + 3) / 4; p.VT = p.TW * p.TW;
+    p.W = (p.G + 31) / 32;
+    p.TS = (p.G + 2 * p.R) * p.W;                       // wall-padded type plane, u64 words per env
+    p.VS = p.G + 4;                                     // bordered visit plane
+    p.VE = ((p.VS * p.VS + 7) / 8) * 8;                 // u16 elements per env, 16-byte multiple
     p.max_steps = cfg->max_steps; p.nclusters = cfg->num_obstacles / 3;
     {
         double th = std::floor((double)cfg->thirsty_plant_prob * 4294967296.0);
@@ -221,8 +224,8 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     } while (0)
     ALLOC(p.rec, N * 32);
     ALLOC(p.term_rec, N * 32);
-    ALLOC(p.types, N * p.G * p.W * 8);
-    ALLOC(p.visits, N * p.VT * 32);
+    ALLOC(p.types, N * p.TS * 8);
+    ALLOC(p.visits, N * p.VE * 2);
     ALLOC(p.stats, kStatCount * 8);
     ALLOC(p.err, 4);
     // tables: rw64 | rw32 | dist | pos | visit | off
@@ -240,8 +243,8 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     }
     cudaMemset(p.rec, 0, N * 32);
     cudaMemset(p.term_rec, 0, N * 32);
-    cudaMemset(p.types, 0, N * p.G * p.W * 8);
-    cudaMemset(p.visits, 0, N * p.VT * 32);
+    cudaMemset(p.types, 0x55, N * p.TS * 8);          // every cell = obstacle: the wall padding
+    cudaMemset(p.visits, 0xFF, N * p.VE * 2);         // every count = 0xFFFF: the window border
     cudaMemset(p.stats, 0, kStatCount * 8);
     cudaMemset(p.err, 0, 4);
 
@@ -474,7 +477,7 @@ extern "C" const char* plantos_kernel_name(const plantos_t* h) {
 extern "C" int64_t plantos_state_bytes_per_env(const plantos_t* h) {
     if (!h) return 0;
     const Params& p = h->p;
-    return 32 + 32 + (int64_t)p.G * p.W * 8 + (int64_t)p.VT * 32;
+    return 32 + 32 + (int64_t)p.TS * 8 + (int64_t)p.VE * 2;
 }
 
 extern "C" const char* plantos_last_error(void) { return g_last_error.c_str(); }

@@ -3,15 +3,17 @@
 //
 // Persistent state in HBM, per env (SoA across envs, all little-endian):
 //   rec     32 B   hot scalars, two uint4 (see EnvRec)
-//   types   G*W*8  2-bit cell codes (0 empty 1 obstacle 2 hydrated 3 thirsty), row-major,
+//   types   (G+2R)*W*8  2-bit cell codes (0 empty 1 obstacle 2 hydrated 3 thirsty), row-major,
 //                  W = ceil(G/32) u64 words per row, cell y of row x at bits [2*(y&31), +2)
-//                  of word x*W + (y>>5).  INVARIANT: columns >= G of the last word hold
-//                  the obstacle code (01) so a shifted row reads "wall" beyond the grid.
-//   visits  VT*32  visit_counts (plantos_env.py:146) as u16 in 4x4-cell tiles of 32 B
-//                  (one DRAM sector): tile (x>>2)*TW + (y>>2), TW = ceil(G/4), element
-//                  (x&3)*4 + (y&3).  A 5x5 window touches exactly 2x2 tiles.  Counts
-//                  saturate at 65535 (a cell gains at most one visit every second step, so
-//                  an episode of <= 65535 steps never reaches it).
+//                  of word (x+R)*W + (y>>5).  The plane is WALL-PADDED so that the LIDAR never
+//                  needs a bounds check: R all-obstacle rows above and below the grid, and the
+//                  columns >= G of the last word of every row hold the obstacle code (01).
+//   visits  (G+4)^2*2    visit_counts (plantos_env.py:146) as u16, row-major with a 2-cell
+//                  border on every side: cell (x,y) at (x+2)*(G+4) + (y+2).  Border cells hold
+//                  0xFFFF, which min(v,10)/10 maps to the 1.0 the reference writes for
+//                  out-of-bounds window cells (plantos_env.py:310-311), so the 5x5 window is 25
+//                  unconditional loads at lane-constant offsets.  Counts saturate at 65534 (a
+//                  cell gains at most one visit every second step; max_steps <= 65535).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -30,7 +32,8 @@ struct Params {
     long long env_base;
     int G, P, O, R, C, D;
     int W;          // u64 words per type row
-    int TW, VT;     // visit tiles per row / per env
+    int TS;         // u64 words per env in the type plane: (G + 2R) * W
+    int VS, VE;     // visit row stride (G + 4) and u16 elements per env (padded to 8)
     int max_steps;
     int nclusters;  // O / 3 (plantos_env.py:341)
     unsigned long long thirsty_thresh;  // floor(prob * 2^32); draw < thresh => thirsty
@@ -107,9 +110,7 @@ __device__ __forceinline__ void pack_rec(const EnvRec& r, uint4& a, uint4& b) {
 // ------------------------------------------------------------------- helpers
 __device__ __forceinline__ int cell_of(uint64_t word, int ylow) { return (int)((word >> (2 * ylow)) & 3ull); }
 
-__device__ __forceinline__ int visit_index(int x, int y, int TW) {
-    return (((x >> 2) * TW + (y >> 2)) << 4) + ((x & 3) << 2) + (y & 3);
-}
+__device__ __forceinline__ int visit_index(int x, int y, int VS) { return (x + 2) * VS + (y + 2); }
 
 // valid-column mask (bit0 of each cell) for word w of a row
 __device__ __forceinline__ uint64_t col_mask(int G, int w) {
@@ -172,6 +173,7 @@ struct Tables {
     const float* visit;   // [11]
     const float* rw32;    // [12]
     const double* rw64;   // [12]
+    const float* onehot;  // [4][4] identity rows: the one-hot entity encoding (plantos_env.py:290-292)
 };
 
 __host__ __device__ inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
@@ -179,6 +181,7 @@ __host__ __device__ inline int align_up(int v, int a) { return (v + a - 1) / a *
 // byte layout of the table block; identical on host (for the launch size) and device
 __host__ __device__ inline int tables_bytes(int G, int R, int C) {
     int b = 2 * kRwCount * 8;              // rw64
+    b += 16 * 4;                           // onehot (16-byte aligned: 96 B in)
     b += 2 * kRwCount * 4;                 // rw32
     b += (R + 1) * 4 + G * 4 + 12 * 4;     // dist, pos, visit(11 padded to 12)
     b += align_up(C * R * 2, 16);          // offsets
@@ -188,20 +191,22 @@ __host__ __device__ inline int tables_bytes(int G, int R, int C) {
 // Cooperative load by the whole block; ends with __syncthreads().
 __device__ inline Tables load_tables(const Params& p, unsigned char* smem) {
     double* rw64 = reinterpret_cast<double*>(smem);
-    float* rw32 = reinterpret_cast<float*>(rw64 + 2 * kRwCount);
+    float* onehot = reinterpret_cast<float*>(rw64 + 2 * kRwCount);
+    float* rw32 = onehot + 16;
     float* dist = rw32 + 2 * kRwCount;
     float* pos = dist + (p.R + 1);
     float* visit = pos + p.G;
     int8_t* off = reinterpret_cast<int8_t*>(visit + 12);
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < 2 * kRwCount; i += nt) { rw64[i] = p.reward64[i]; rw32[i] = p.reward32[i]; }
+    for (int i = tid; i < 16; i += nt) onehot[i] = ((i >> 2) == (i & 3)) ? 1.0f : 0.0f;
     for (int i = tid; i <= p.R; i += nt) dist[i] = p.dist_tab[i];
     for (int i = tid; i < p.G; i += nt) pos[i] = p.pos_tab[i];
     for (int i = tid; i < 11; i += nt) visit[i] = p.visit_tab[i];
     for (int i = tid; i < p.C * p.R * 2; i += nt) off[i] = p.lidar_off[i];
     __syncthreads();
     Tables t;
-    t.off = off; t.dist = dist; t.pos = pos; t.visit = visit; t.rw32 = rw32; t.rw64 = rw64;
+    t.off = off; t.dist = dist; t.pos = pos; t.visit = visit; t.rw32 = rw32; t.rw64 = rw64; t.onehot = onehot;
     return t;
 }
 
@@ -233,17 +238,17 @@ __device__ __forceinline__ void action_target(const EnvRec& r, long long action,
 
 __device__ __forceinline__ StepOut apply_action(EnvRec& r, long long action, int tx, int ty, bool inb,
                                                 uint64_t row_word, uint64_t* word_ptr,
-                                                uint16_t* visits_e, int TW, int max_steps) {
+                                                uint16_t* visits_e, int VS, int max_steps) {
     StepOut o;
     o.watered = 0;
     r.step += 1;                                           // :162
     const int t = inb ? cell_of(row_word, ty & 31) : kObstacle;
     if (action < 4) {
         if (t != kObstacle) {                              // :193-195 (plants are walkable)
-            uint16_t* vp = visits_e + visit_index(tx, ty, TW);
+            uint16_t* vp = visits_e + visit_index(tx, ty, VS);
             const unsigned v = *vp;
             const bool fresh = (v == 0);                   // :197
-            *vp = (uint16_t)(v < 65535u ? v + 1u : 65535u);  // :203
+            *vp = (uint16_t)(v < 65534u ? v + 1u : 65534u);  // :203
             r.x = tx; r.y = ty;                            // :199
             r.explored += fresh;                           // explored_map>0 count, :198-200,320
             o.ridx = fresh ? 0 : 1;                        // R_EXPLORATION / R_REVISIT

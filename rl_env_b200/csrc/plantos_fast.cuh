@@ -9,15 +9,19 @@
 //            load, action, target-cell lookup, visit-count read-modify-write, watering,
 //            reward / done / record stores.  Outputs are coalesced across the tile.
 //   phase B  one HALF-WARP per env, two envs per iteration -- the observation
-//            (plantos_env.py:251-315): 2R+1 lanes each fetch one 8-byte type row and turn
-//            it into a rover-centred window word (wall-padded by shifts, no per-cell
-//            bounds checks); one lane per ray marches the integer offset table with
-//            warp shuffles as the row lookup; 25 visit cells over 16 lanes in two rounds.
-//            Rows go to a 4-env shared-memory tile whose 16*D bytes are 16-byte aligned in
-//            the [N, D] fp32 buffer, flushed with st.global.v4.  Loads of iteration i+1 are
-//            issued before the arithmetic of iteration i.
+//            (plantos_env.py:251-315): 2R+1 lanes each fetch one 8-byte row of the wall-padded
+//            type plane and shift it into a rover-centred window word (no bounds checks
+//            anywhere); one lane per ray marches the integer offset table, with a warp
+//            shuffle as the row lookup; the 25 visit cells are two unconditional u16 loads
+//            per lane from the bordered visit plane.  Rows are assembled in a 4-env
+//            shared-memory tile whose 16*D bytes are 16-byte aligned in the [N, D] fp32
+//            buffer and leave with streaming 128-bit stores (st.global.cs.v4) so that the
+//            write-once observation stream does not evict the env state from L2.  The loop
+//            is unrolled by two with ping-pong prefetch registers: the loads of iteration
+//            i+1 are in flight during the arithmetic of iteration i.
 //   phase C  whole warp, rare   -- SB3 auto-reset of finished envs (terminal observation,
 //            Philox / injected map, fresh observation) via the generic warp routines.
+// A ragged last tile (N % EPW != 0) is stepped env by env with step_env_warp.
 #pragma once
 #include "plantos_generic.cuh"
 
@@ -26,8 +30,14 @@ namespace plantos_dev {
 constexpr int kFastWarps = 4;
 
 __host__ __device__ inline int fast_warp_scratch_bytes(int G, int D) {
-    return 16 * D + align_up(G * 8, 16);   // 4-env obs tile + type plane for phase C
+    return 16 * D + align_up(G * 8, 16);   // 4-env obs tile + type plane for phase C / tail
 }
+
+struct Prefetch {
+    uint64_t row;       // this lane's type row of the env's window
+    unsigned v0, v1;    // this lane's two visit-window cells
+    unsigned pw;        // x | y << 8 of the env
+};
 
 template <int R, int C, int EPW>
 __global__ void __launch_bounds__(kFastWarps * 32, 8)
@@ -41,43 +51,34 @@ k_step_fast(const Params p, const StepIO io) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Tables t = load_tables(p, smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int G = p.G, TW = p.TW;
+    const int G = p.G, VS = p.VS, VE = p.VE, TS = p.TS;
     const int e0 = (blockIdx.x * kFastWarps + warp) * EPW;
     if (e0 >= p.N) return;
     unsigned char* scratch = smem + tables_bytes(G, R, C) + warp * fast_warp_scratch_bytes(G, D);
     float* tile = reinterpret_cast<float*>(scratch);
     uint64_t* plane = reinterpret_cast<uint64_t*>(scratch + 16 * D);
 
-    // ---- per-lane constants: this lane's ray and visit cells
-    const int sub = lane & 15, half = lane >> 4, hbase = lane & 16;
-    int srcl[R], shf[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        int dx = 0, dy = 0;
-        if (sub < C) { dx = t.off[(sub * R + r) * 2]; dy = t.off[(sub * R + r) * 2 + 1]; }
-        srcl[r] = hbase + dx + R;      // lane holding window row x+dx
-        shf[r] = 2 * (dy + R);         // bit offset of column y+dy inside the window word
+    if (p.N - e0 < EPW) {   // ragged last tile
+        for (int e = e0; e < p.N; ++e) step_env_warp(p, t, io, e, plane, tile, lane);
+        return;
     }
-    const int lx0 = sub / 5 - 2, ly0 = sub % 5 - 2;
-    const int lx1 = (sub + 16) / 5 - 2, ly1 = (sub + 16) % 5 - 2;
 
     // ---- phase A: transition, one lane per env
-    const int nvalid = min(EPW, p.N - e0);
-    const bool act = lane < nvalid;
-    const int e = e0 + lane;
+    const bool act = lane < EPW;
     EnvRec r = {};
     int done = 0, term = 0, trunc = 0;
     unsigned posw = 0;
     if (act) {
+        const int e = e0 + lane;
         uint4 ra = p.rec[2 * (size_t)e], rb = p.rec[2 * (size_t)e + 1];
-        const long long action = io.actions[e];
+        const long long action = __ldcs(io.actions + e);
         r = unpack_rec(ra, rb);
         int tx, ty; bool inb;
         action_target(r, action, G, tx, ty, inb);
-        uint64_t* wp = p.types + (size_t)e * G + (inb ? tx : r.x);
+        uint64_t* wp = p.types + (size_t)e * TS + R + (inb ? tx : r.x);
         const uint64_t word = inb ? *wp : kObstAll;
-        uint16_t* visits_e = p.visits + (size_t)e * p.VT * 16;
-        const StepOut o = apply_action(r, action, tx, ty, inb, word, wp, visits_e, TW, p.max_steps);
+        uint16_t* visits_e = p.visits + (size_t)e * VE;
+        const StepOut o = apply_action(r, action, tx, ty, inb, word, wp, visits_e, VS, p.max_steps);
         r.ret += t.rw64[o.ridx];
         io.reward[e] = t.rw32[o.ridx];
         term = o.terminated; trunc = o.truncated; done = term | trunc;
@@ -97,44 +98,48 @@ k_step_fast(const Params p, const StepIO io) {
     __syncwarp();   // phase A's plane updates are visible to the other lanes' loads below
 
     // ---- phase B: observations, half-warp per env
-    const int niter = (nvalid + 1) >> 1;
+    const int sub = lane & 15, half = lane >> 4, hbase = lane & 16;
+    int srcl[R], shf[R];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+        int dx = 0, dy = 0;
+        if (sub < C) { dx = t.off[(sub * R + rr) * 2]; dy = t.off[(sub * R + rr) * 2 + 1]; }
+        srcl[rr] = hbase + dx + R;     // lane holding window row x+dx
+        shf[rr] = 2 * (dy + R);        // bit offset of column y+dy inside the window word
+    }
+    // lane-constant bases: padded type row (x - R + sub) + R = x + sub; visit cells
+    // (x + q/5 - 2, y + q%5 - 2) -> padded (x + q/5) * VS + (y + q%5) for q = sub, sub + 16
+    // (byte pointers + unsigned 32-bit byte offsets keep the per-iteration address math to one
+    // multiply-add and one wide add per load)
+    const char* trow = reinterpret_cast<const char*>(p.types + (size_t)e0 * TS + sub);
+    const char* vc0 = reinterpret_cast<const char*>(p.visits + (size_t)e0 * VE + (sub / 5) * VS + sub % 5);
+    const char* vc1 = reinterpret_cast<const char*>(p.visits + (size_t)e0 * VE + ((sub + 16) / 5) * VS + (sub + 16) % 5);
+    const unsigned TS8 = 8u * TS, VE2 = 2u * VE, VS2 = 2u * VS;
+    const bool has_row = sub < NROW, has_ray = sub < C, has_v1 = sub < 9;
+    float* const rowA = tile + half * D;          // env 2*it + half of an even iteration
+    float* const rowB = tile + (2 + half) * D;    // ... of an odd iteration
+    const float4* onehot = reinterpret_cast<const float4*>(t.onehot);
     constexpr uint64_t LOWPAD = kObstAll & ((1ull << (2 * R)) - 1ull);
 
-    // software pipeline registers: loads for the next iteration
-    uint64_t n_row; unsigned n_v0, n_v1; int n_x, n_y; bool n_valid;
-    auto issue_loads = [&](int it) {
+    auto issue = [&](int it, Prefetch& n) {
         const int j = 2 * it + half;
-        n_valid = j < nvalid;
-        const unsigned pw = __shfl_sync(FULL, posw, j & 31);
-        n_x = pw & 0xff; n_y = (pw >> 8) & 0xff;
-        const size_t ej = (size_t)(e0 + j);
-        n_row = kObstAll;
-        const int gx = n_x - R + sub;
-        if (n_valid && sub < NROW && (unsigned)gx < (unsigned)G) n_row = p.types[ej * G + gx];
-        n_v0 = 0xffffffffu; n_v1 = 0xffffffffu;
-        const uint16_t* ve = p.visits + ej * p.VT * 16;
-        const int ax = n_x + lx0, ay = n_y + ly0;
-        if (n_valid && (unsigned)ax < (unsigned)G && (unsigned)ay < (unsigned)G) n_v0 = ve[visit_index(ax, ay, TW)];
-        const int bx = n_x + lx1, by = n_y + ly1;
-        if (n_valid && sub < 9 && (unsigned)bx < (unsigned)G && (unsigned)by < (unsigned)G)
-            n_v1 = ve[visit_index(bx, by, TW)];
+        n.pw = __shfl_sync(FULL, posw, j);
+        const unsigned x = n.pw & 0xff, y = n.pw >> 8;
+        n.row = kObstAll;
+        if (has_row) n.row = *reinterpret_cast<const uint64_t*>(trow + ((unsigned)j * TS8 + 8u * x));
+        const unsigned vo = (unsigned)j * VE2 + (unsigned)x * VS2 + 2u * y;
+        n.v0 = *reinterpret_cast<const uint16_t*>(vc0 + vo);
+        n.v1 = 0;
+        if (has_v1) n.v1 = *reinterpret_cast<const uint16_t*>(vc1 + vo);
     };
 
-    issue_loads(0);
-    for (int it = 0; it < niter; ++it) {
-        const uint64_t c_row = n_row;
-        const unsigned c_v0 = n_v0, c_v1 = n_v1;
-        const int x = n_x, y = n_y;
-        const bool valid = n_valid;
-        if (it + 1 < niter) issue_loads(it + 1);   // warp-uniform condition
-
+    auto compute = [&](const Prefetch& c, float* row) {
+        const int x = c.pw & 0xff, y = c.pw >> 8;
         // rover-centred window word: cells y-R .. y+R of this lane's row, walls outside
         const int s = 2 * y;
-        const uint64_t ext = (c_row << (2 * R)) | LOWPAD;
-        const uint64_t w64 = (ext >> s) | ((kObstAll << 1) << (63 - s));
-        const unsigned w = (unsigned)w64;
-
-        // LIDAR march (plantos_env.py:260-284): sample r looks at window row srcl[r], bits shf[r]
+        const uint64_t ext = (c.row << (2 * R)) | LOWPAD;
+        const unsigned w = (unsigned)((ext >> s) | ((kObstAll << 1) << (63 - s)));
+        // LIDAR march (plantos_env.py:260-284): sample rr looks at window row srcl[rr], bits shf[rr]
         unsigned acc = 0;
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) {
@@ -142,40 +147,39 @@ k_step_fast(const Params p, const StepIO io) {
             acc += ((wr >> shf[rr]) & 3u) << (2 * rr);
         }
         const unsigned m = (acc | (acc >> 1)) & 0x55555555u;
-        int dist = R, kind = kEmpty;
-        if (m) {
-            const int b = __ffs(m) - 1;
-            dist = (b >> 1) + 1;
-            kind = (acc >> b) & 3;
-        }
-        const int g = ((it & 1) << 1) + half;
-        float* row = tile + g * D;
-        if (valid && sub < C) {
+        const int b = __ffs(m) - 1;                       // -1 when nothing was hit
+        const int dist = m ? (b >> 1) + 1 : R;
+        const int kind = m ? (acc >> b) & 3 : kEmpty;
+        if (has_ray) {                                    // :286-292
             float* q = row + 5 * sub;
+            const float4 oh = onehot[kind];
             q[0] = t.dist[dist];
-            q[1] = (kind == kEmpty) ? 1.0f : 0.0f;
-            q[2] = (kind == kObstacle) ? 1.0f : 0.0f;
-            q[3] = (kind == kHydrated) ? 1.0f : 0.0f;
-            q[4] = (kind == kThirsty) ? 1.0f : 0.0f;
+            q[1] = oh.x; q[2] = oh.y; q[3] = oh.z; q[4] = oh.w;
         }
-        if (valid && sub < 2) row[5 * C + sub] = t.pos[sub ? y : x];
-        if (valid) {
-            row[5 * C + 2 + sub] = (c_v0 == 0xffffffffu) ? 1.0f : t.visit[c_v0 < 10u ? c_v0 : 10u];
-            if (sub < 9) row[5 * C + 18 + sub] = (c_v1 == 0xffffffffu) ? 1.0f : t.visit[c_v1 < 10u ? c_v1 : 10u];
-        }
+        if (sub < 2) row[5 * C + sub] = t.pos[sub ? y : x];                       // :294-296
+        row[5 * C + 2 + sub] = t.visit[c.v0 < 10u ? c.v0 : 10u];                  // :298-313
+        if (has_v1) row[5 * C + 18 + sub] = t.visit[c.v1 < 10u ? c.v1 : 10u];
+    };
 
-        if ((it & 1) || it == niter - 1) {
-            // flush a group of <= 4 env rows: 16-byte aligned because e0 and g0 are multiples of 4
-            __syncwarp();
-            const int g0 = (it >> 1) << 2;
-            const int nfl = min(4, nvalid - g0) * D;
-            float* dst = io.obs + (size_t)(e0 + g0) * D;
-            const float4* src4 = reinterpret_cast<const float4*>(tile);
-            float4* dst4 = reinterpret_cast<float4*>(dst);
-            for (int k = lane; k < (nfl >> 2); k += 32) dst4[k] = src4[k];
-            for (int k = (nfl & ~3) + lane; k < nfl; k += 32) dst[k] = tile[k];
-            __syncwarp();
+    float4* const obs4 = reinterpret_cast<float4*>(io.obs) + (size_t)(e0 >> 2) * D;
+    const float4* src4 = reinterpret_cast<const float4*>(tile);
+    Prefetch pa, pb;
+    issue(0, pa);
+#pragma unroll 1
+    for (int it = 0; it < EPW / 2; it += 2) {
+        issue(it + 1, pb);
+        compute(pa, rowA);
+        if (it + 2 < EPW / 2) issue(it + 2, pa);
+        compute(pb, rowB);
+        // flush four env rows = D float4, 16-byte aligned because e0 and 2*it are multiples of 4
+        __syncwarp();
+        float4* dst4 = obs4 + (size_t)(it >> 1) * D;
+#pragma unroll
+        for (int k = 0; k < (D + 31) / 32; ++k) {
+            const int idx = k * 32 + lane;
+            if (idx < D) __stcs(dst4 + idx, src4[idx]);
         }
+        __syncwarp();
     }
 
     // ---- phase C: auto-reset of finished envs (rare; warp-cooperative generic code)
@@ -186,8 +190,8 @@ k_step_fast(const Params p, const StepIO io) {
         const int ej = e0 + j;
         const int episode = __shfl_sync(FULL, r.episode, j);
         const int px = __shfl_sync(FULL, r.x, j), py = __shfl_sync(FULL, r.y, j);
-        const uint64_t* types_e = p.types + (size_t)ej * G;
-        const uint16_t* visits_e = p.visits + (size_t)ej * p.VT * 16;
+        const uint64_t* types_e = p.types + (size_t)ej * TS + R;
+        const uint16_t* visits_e = p.visits + (size_t)ej * VE;
         if (io.terminal_obs) {
             for (int idx = lane; idx < G; idx += 32) plane[idx] = types_e[idx];
             __syncwarp();

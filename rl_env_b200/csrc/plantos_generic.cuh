@@ -4,8 +4,8 @@
 //   k_reset_all      PlantOSEnv.reset for every env              (plantos_env.py:125-158)
 //   k_get_state / k_set_state / k_get_scalars / k_get_returns / k_stats_out
 //
-// The warp-cooperative pieces (reset_env_warp, build_obs_warp) are also the rare-path
-// (auto-reset) code of the fast kernel in plantos_fast.cuh.
+// The warp-cooperative pieces (step_env_warp, reset_env_warp, build_obs_warp) are also the
+// rare-path code of the fast kernel in plantos_fast.cuh (auto-reset, ragged last tile).
 #pragma once
 #include "plantos_common.cuh"
 
@@ -13,14 +13,14 @@ namespace plantos_dev {
 
 constexpr int kGenericWarps = 8;  // warps (= envs in flight) per block
 
-// per-warp scratch: the env's type plane (G*W u64) followed by one observation row
+// per-warp scratch: the env's (unpadded) type plane, G*W u64, followed by one observation row
 __host__ __device__ inline int generic_warp_scratch_bytes(int G, int W, int D) {
     return align_up(G * W * 8, 16) + align_up(D * 4, 16);
 }
 
 // ----------------------------------------------------------------- observation
-// plantos_env.py:251-315.  `plane` (shared memory) must hold the type rows x-R .. x+R that
-// lie inside the grid; visits are read from global memory.  All 32 lanes participate.
+// plantos_env.py:251-315.  `plane` (shared memory, indexed by grid row) must hold the type
+// rows x-R .. x+R that lie inside the grid; visits are read from global memory.
 __device__ __forceinline__ void build_obs_warp(const Params& p, const Tables& t, const uint64_t* plane,
                                                const uint16_t* visits_e, int x, int y, float* obs_s, int lane) {
     const int G = p.G, W = p.W, R = p.R, C = p.C;
@@ -46,15 +46,9 @@ __device__ __forceinline__ void build_obs_warp(const Params& p, const Tables& t,
         obs_s[5 * C] = t.pos[x];
         obs_s[5 * C + 1] = t.pos[y];
     }
-    if (lane < 25) {                                     // :298-313
-        const int gx = x + lane / 5 - 2;
-        const int gy = y + lane % 5 - 2;
-        float v = 1.0f;
-        if ((unsigned)gx < (unsigned)G && (unsigned)gy < (unsigned)G) {
-            const unsigned cnt = visits_e[visit_index(gx, gy, p.TW)];
-            v = t.visit[cnt < 10u ? cnt : 10u];
-        }
-        obs_s[5 * C + 2 + lane] = v;
+    if (lane < 25) {                                     // :298-313; the 0xFFFF border reads as 1.0
+        const unsigned cnt = visits_e[visit_index(x + lane / 5 - 2, y + lane % 5 - 2, p.VS)];
+        obs_s[5 * C + 2 + lane] = t.visit[cnt < 10u ? cnt : 10u];
     }
     __syncwarp();
 }
@@ -65,9 +59,9 @@ __device__ __forceinline__ void store_obs_row(const float* obs_s, float* dst, in
 
 // ----------------------------------------------------------------------- reset
 // New episode for env e (local index): builds the map in `plane` (shared), writes the type
-// plane and a zeroed visit plane (rover cell = 1, plantos_env.py:146-147) to global memory
-// and returns the fresh record in all lanes.  `episode` selects the injected map / Philox
-// counter and is stored incremented.
+// rows and a fresh visit plane (zeros, rover cell = 1, plantos_env.py:146-147; 0xFFFF border)
+// to global memory and returns the fresh record in all lanes.  `episode` selects the
+// injected map / Philox counter and is stored incremented.
 __device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int episode, uint64_t* plane, int lane) {
     const int G = p.G, W = p.W;
     const int nwords = G * W;
@@ -147,9 +141,9 @@ __device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int epi
         ry = __shfl_sync(0xffffffffu, ry, 0);
         __syncwarp();
     }
-    // counts + write-out
+    // counts + write-out of the G grid rows (the wall rows above/below were set at create)
     int n_obst = 0, n_thirsty = 0;
-    uint64_t* types_e = p.types + (size_t)e * nwords;
+    uint64_t* types_e = p.types + (size_t)e * p.TS + (size_t)p.R * W;
     for (int idx = lane; idx < nwords; idx += 32) {
         const uint64_t word = plane[idx];
         const uint64_t m = col_mask(G, idx % W);
@@ -159,14 +153,20 @@ __device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int epi
     }
     n_obst = warp_sum_i(n_obst);
     n_thirsty = warp_sum_i(n_thirsty);
-    uint4* vt = reinterpret_cast<uint4*>(p.visits + (size_t)e * p.VT * 16);
-    const int rtile = (rx >> 2) * p.TW + (ry >> 2);
-    const int rwithin = ((rx & 3) << 2) + (ry & 3);
-    for (int tile = lane; tile < p.VT; tile += 32) {
-        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (tile == rtile) w[rwithin >> 1] = 1u << (16 * (rwithin & 1));
-        vt[2 * tile] = make_uint4(w[0], w[1], w[2], w[3]);
-        vt[2 * tile + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+    // visit plane: pairs of u16 as u32 words (VE is even and the plane is 4-byte aligned)
+    uint32_t* vw = reinterpret_cast<uint32_t*>(p.visits + (size_t)e * p.VE);
+    const int VS = p.VS, rcell = visit_index(rx, ry, VS);
+    for (int wi = lane; wi < p.VE / 2; wi += 32) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int el = 2 * wi + hf;
+            const int vx = el / VS - 2, vy = el % VS - 2;
+            uint32_t v = 0xffffu;                                   // border / tail padding
+            if ((unsigned)vx < (unsigned)G && (unsigned)vy < (unsigned)G) v = (el == rcell) ? 1u : 0u;
+            word |= v << (16 * hf);
+        }
+        vw[wi] = word;
     }
     __syncwarp();
     EnvRec r;
@@ -197,88 +197,90 @@ __device__ __forceinline__ void accumulate_stats(const Params& p, bool done, con
     }
 }
 
-// --------------------------------------------------------------- step (generic)
+// -------------------------------------------------- one env, one warp (any config)
+__device__ __forceinline__ void step_env_warp(const Params& p, const Tables& t, const StepIO& io, int e,
+                                              uint64_t* plane, float* obs_s, int lane) {
+    uint4 ra = make_uint4(0, 0, 0, 0), rb = ra;
+    long long action = 0;
+    if (lane == 0) {
+        ra = p.rec[2 * (size_t)e];
+        rb = p.rec[2 * (size_t)e + 1];
+        action = io.actions[e];
+    }
+    const unsigned posw = __shfl_sync(0xffffffffu, ra.x, 0);
+    int x = posw & 0xff, y = (posw >> 8) & 0xff;
+    uint64_t* types_e = p.types + (size_t)e * p.TS + (size_t)p.R * p.W;   // grid row 0
+    uint16_t* visits_e = p.visits + (size_t)e * p.VE;
+
+    // stage the rows the step can look at: x-R-1 .. x+R+1 (move of one row + LIDAR reach)
+    const int lo = max(0, x - p.R - 1), hi = min(p.G - 1, x + p.R + 1);
+    for (int idx = lo * p.W + lane; idx < (hi + 1) * p.W; idx += 32) plane[idx] = types_e[idx];
+    __syncwarp();
+
+    int flagw = 0;
+    EnvRec r = {};
+    if (lane == 0) {
+        r = unpack_rec(ra, rb);
+        int tx, ty; bool inb;
+        action_target(r, action, p.G, tx, ty, inb);
+        const int widx = inb ? tx * p.W + (ty >> 5) : 0;
+        const uint64_t word = inb ? plane[widx] : kObstAll;
+        uint64_t newword = word;
+        const StepOut o = apply_action(r, action, tx, ty, inb, word, &newword, visits_e, p.VS, p.max_steps);
+        if (o.watered) { plane[widx] = newword; types_e[widx] = newword; }
+        r.ret += t.rw64[o.ridx];
+        io.reward[e] = t.rw32[o.ridx];
+        const int done = o.terminated | o.truncated;
+        io.done[e] = (uint8_t)done;
+        if (io.terminated) io.terminated[e] = (uint8_t)o.terminated;
+        if (io.truncated) io.truncated[e] = (uint8_t)o.truncated;
+        flagw = r.x | (r.y << 8) | (done << 16) | (o.terminated << 17) | (o.truncated << 18);
+    }
+    __syncwarp();
+    flagw = __shfl_sync(0xffffffffu, flagw, 0);
+    x = flagw & 0xff; y = (flagw >> 8) & 0xff;
+    const bool done = (flagw >> 16) & 1;
+
+    build_obs_warp(p, t, plane, visits_e, x, y, obs_s, lane);
+    float* obs_row = io.obs + (size_t)e * p.D;
+    if (!done) {
+        store_obs_row(obs_s, obs_row, p.D, lane);
+        if (lane == 0) pack_rec(r, ra, rb);
+    } else {
+        // SB3 auto-reset: terminal observation + info snapshot, then a fresh episode
+        if (io.terminal_obs) store_obs_row(obs_s, io.terminal_obs + (size_t)e * p.D, p.D, lane);
+        int episode = 0;
+        if (lane == 0) {
+            pack_rec(r, ra, rb);
+            p.term_rec[2 * (size_t)e] = ra;
+            p.term_rec[2 * (size_t)e + 1] = rb;
+            episode = r.episode;
+        }
+        accumulate_stats(p, lane == 0, r, (flagw >> 17) & 1, (flagw >> 18) & 1, lane);
+        episode = __shfl_sync(0xffffffffu, episode, 0);
+        __syncwarp();
+        const EnvRec nr = reset_env_warp(p, e, episode, plane, lane);
+        build_obs_warp(p, t, plane, visits_e, nr.x, nr.y, obs_s, lane);
+        store_obs_row(obs_s, obs_row, p.D, lane);
+        if (lane == 0) pack_rec(nr, ra, rb);
+    }
+    if (lane == 0) {
+        p.rec[2 * (size_t)e] = ra;
+        p.rec[2 * (size_t)e + 1] = rb;
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(kGenericWarps * 32)
 k_step_generic(const Params p, const StepIO io) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Tables t = load_tables(p, smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nwords = p.G * p.W;
     unsigned char* scratch = smem + tables_bytes(p.G, p.R, p.C) + warp * generic_warp_scratch_bytes(p.G, p.W, p.D);
     uint64_t* plane = reinterpret_cast<uint64_t*>(scratch);
-    float* obs_s = reinterpret_cast<float*>(scratch + align_up(nwords * 8, 16));
-
-    for (int e = blockIdx.x * kGenericWarps + warp; e < p.N; e += gridDim.x * kGenericWarps) {
-        uint4 ra = make_uint4(0, 0, 0, 0), rb = ra;
-        long long action = 0;
-        if (lane == 0) {
-            ra = p.rec[2 * (size_t)e];
-            rb = p.rec[2 * (size_t)e + 1];
-            action = io.actions[e];
-        }
-        const unsigned posw = __shfl_sync(0xffffffffu, ra.x, 0);
-        int x = posw & 0xff, y = (posw >> 8) & 0xff;
-        uint64_t* types_e = p.types + (size_t)e * nwords;
-        uint16_t* visits_e = p.visits + (size_t)e * p.VT * 16;
-
-        // stage the rows the step can look at: x-R-1 .. x+R+1 (move of one row + LIDAR reach)
-        const int lo = max(0, x - p.R - 1), hi = min(p.G - 1, x + p.R + 1);
-        for (int idx = lo * p.W + lane; idx < (hi + 1) * p.W; idx += 32) plane[idx] = types_e[idx];
-        __syncwarp();
-
-        int flagw = 0;
-        EnvRec r;
-        if (lane == 0) {
-            r = unpack_rec(ra, rb);
-            int tx, ty; bool inb;
-            action_target(r, action, p.G, tx, ty, inb);
-            const int widx = inb ? tx * p.W + (ty >> 5) : 0;
-            const uint64_t word = inb ? plane[widx] : kObstAll;
-            uint64_t newword = word;
-            const StepOut o = apply_action(r, action, tx, ty, inb, word, &newword, visits_e, p.TW, p.max_steps);
-            if (o.watered) { plane[widx] = newword; types_e[widx] = newword; }
-            r.ret += t.rw64[o.ridx];
-            io.reward[e] = t.rw32[o.ridx];
-            const int done = o.terminated | o.truncated;
-            io.done[e] = (uint8_t)done;
-            if (io.terminated) io.terminated[e] = (uint8_t)o.terminated;
-            if (io.truncated) io.truncated[e] = (uint8_t)o.truncated;
-            flagw = r.x | (r.y << 8) | (done << 16) | (o.terminated << 17) | (o.truncated << 18);
-        }
-        __syncwarp();
-        flagw = __shfl_sync(0xffffffffu, flagw, 0);
-        x = flagw & 0xff; y = (flagw >> 8) & 0xff;
-        const bool done = (flagw >> 16) & 1;
-
-        build_obs_warp(p, t, plane, visits_e, x, y, obs_s, lane);
-        float* obs_row = io.obs + (size_t)e * p.D;
-        if (!done) {
-            store_obs_row(obs_s, obs_row, p.D, lane);
-            if (lane == 0) pack_rec(r, ra, rb);
-        } else {
-            // SB3 auto-reset: terminal observation + info snapshot, then a fresh episode
-            if (io.terminal_obs) store_obs_row(obs_s, io.terminal_obs + (size_t)e * p.D, p.D, lane);
-            int episode = 0;
-            if (lane == 0) {
-                pack_rec(r, ra, rb);
-                p.term_rec[2 * (size_t)e] = ra;
-                p.term_rec[2 * (size_t)e + 1] = rb;
-                episode = r.episode;
-            }
-            accumulate_stats(p, lane == 0, r, (flagw >> 17) & 1, (flagw >> 18) & 1, lane);
-            episode = __shfl_sync(0xffffffffu, episode, 0);
-            __syncwarp();
-            const EnvRec nr = reset_env_warp(p, e, episode, plane, lane);
-            build_obs_warp(p, t, plane, visits_e, nr.x, nr.y, obs_s, lane);
-            store_obs_row(obs_s, obs_row, p.D, lane);
-            if (lane == 0) pack_rec(nr, ra, rb);
-        }
-        if (lane == 0) {
-            p.rec[2 * (size_t)e] = ra;
-            p.rec[2 * (size_t)e + 1] = rb;
-        }
-        __syncwarp();
-    }
+    float* obs_s = reinterpret_cast<float*>(scratch + align_up(p.G * p.W * 8, 16));
+    for (int e = blockIdx.x * kGenericWarps + warp; e < p.N; e += gridDim.x * kGenericWarps)
+        step_env_warp(p, t, io, e, plane, obs_s, lane);
 }
 
 // ------------------------------------------------------------------ reset (all)
@@ -287,16 +289,15 @@ k_reset_all(const Params p, float* obs) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Tables t = load_tables(p, smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nwords = p.G * p.W;
     unsigned char* scratch = smem + tables_bytes(p.G, p.R, p.C) + warp * generic_warp_scratch_bytes(p.G, p.W, p.D);
     uint64_t* plane = reinterpret_cast<uint64_t*>(scratch);
-    float* obs_s = reinterpret_cast<float*>(scratch + align_up(nwords * 8, 16));
+    float* obs_s = reinterpret_cast<float*>(scratch + align_up(p.G * p.W * 8, 16));
     for (int e = blockIdx.x * kGenericWarps + warp; e < p.N; e += gridDim.x * kGenericWarps) {
         int episode = 0;
         if (lane == 0) episode = (int)p.rec[2 * (size_t)e].w;
         episode = __shfl_sync(0xffffffffu, episode, 0);
         const EnvRec nr = reset_env_warp(p, e, episode, plane, lane);
-        const uint16_t* visits_e = p.visits + (size_t)e * p.VT * 16;
+        const uint16_t* visits_e = p.visits + (size_t)e * p.VE;
         build_obs_warp(p, t, plane, visits_e, nr.x, nr.y, obs_s, lane);
         store_obs_row(obs_s, obs + (size_t)e * p.D, p.D, lane);
         if (lane == 0) {
@@ -316,8 +317,8 @@ __global__ void k_get_state(const Params p, uint8_t* cells, int32_t* visits) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int e = (int)(i / gg), c = (int)(i - (size_t)e * gg);
         const int x = c / p.G, y = c - x * p.G;
-        if (cells) cells[i] = (uint8_t)cell_of(p.types[(size_t)e * p.G * p.W + x * p.W + (y >> 5)], y & 31);
-        if (visits) visits[i] = (int32_t)p.visits[(size_t)e * p.VT * 16 + visit_index(x, y, p.TW)];
+        if (cells) cells[i] = (uint8_t)cell_of(p.types[(size_t)e * p.TS + (size_t)(x + p.R) * p.W + (y >> 5)], y & 31);
+        if (visits) visits[i] = (int32_t)p.visits[(size_t)e * p.VE + visit_index(x, y, p.VS)];
     }
 }
 
@@ -329,7 +330,7 @@ __global__ void k_set_state(const Params p, const uint8_t* cells, const int32_t*
     const int G = p.G, W = p.W, nwords = G * W, gg = G * G;
     uint4 ra = p.rec[2 * (size_t)e], rb = p.rec[2 * (size_t)e + 1];
     EnvRec r = unpack_rec(ra, rb);
-    uint64_t* types_e = p.types + (size_t)e * nwords;
+    uint64_t* types_e = p.types + (size_t)e * p.TS + (size_t)p.R * W;
     if (cells) {
         int n_obst = 0, n_thirsty = 0;
         for (int idx = lane; idx < nwords; idx += 32) {
@@ -349,13 +350,11 @@ __global__ void k_set_state(const Params p, const uint8_t* cells, const int32_t*
         r.thirsty = warp_sum_i(n_thirsty);
     }
     if (visits) {
-        uint16_t* ve = p.visits + (size_t)e * p.VT * 16;
-        for (int i = lane; i < p.VT * 16; i += 32) {
-            const int tile = i >> 4, within = i & 15;
-            const int x = (tile / p.TW) * 4 + (within >> 2), y = (tile % p.TW) * 4 + (within & 3);
-            int v = 0;
-            if (x < G && y < G) v = visits[(size_t)e * gg + x * G + y];
-            ve[i] = (uint16_t)(v < 0 ? 0 : (v > 65535 ? 65535 : v));
+        uint16_t* ve = p.visits + (size_t)e * p.VE;
+        for (int c = lane; c < gg; c += 32) {
+            const int x = c / G, y = c - x * G;
+            const int v = visits[(size_t)e * gg + c];
+            ve[visit_index(x, y, p.VS)] = (uint16_t)(v < 0 ? 0 : (v > 65534 ? 65534 : v));
         }
     }
     if (sc) {
