@@ -16,7 +16,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
-LIB_PATH = os.path.join(CSRC, "libplantos_b200.so")
+# PLANTOS_LIB points the loader at an alternative build (kernel-variant experiments)
+LIB_PATH = os.environ.get("PLANTOS_LIB") or os.path.join(CSRC, "libplantos_b200.so")
 SOURCES = ["plantos_abi.cu"]
 HEADERS = ["plantos_common.cuh", "plantos_generic.cuh", "plantos_fast.cuh",
            os.path.join(ROOT, "include", "plantos.h")]

@@ -31,11 +31,12 @@ int fail(int code, const std::string& msg) {
 
 typedef void (*fast_kernel_t)(const Params, const StepIO);
 
-struct FastVariant { int R, C, EPW; fast_kernel_t fn; };
+struct FastVariant { int R, C, EPW, keep; fast_kernel_t fn; };
 
-#define FAST_ROW(R_, C_)                                                  \
-    {R_, C_, 4, k_step_fast<R_, C_, 4>}, {R_, C_, 8, k_step_fast<R_, C_, 8>}, \
-    {R_, C_, 16, k_step_fast<R_, C_, 16>}, {R_, C_, 32, k_step_fast<R_, C_, 32>}
+#define FAST_ROW1(R_, C_, K_)                                                              \
+    {R_, C_, 4, K_, k_step_fast<R_, C_, 4, K_>}, {R_, C_, 8, K_, k_step_fast<R_, C_, 8, K_>},   \
+    {R_, C_, 16, K_, k_step_fast<R_, C_, 16, K_>}, {R_, C_, 32, K_, k_step_fast<R_, C_, 32, K_>}
+#define FAST_ROW(R_, C_) FAST_ROW1(R_, C_, 0), FAST_ROW1(R_, C_, 1)
 
 const FastVariant kFastVariants[] = {
     FAST_ROW(6, 16),  // training preset, A2C_training.py:206-212
@@ -169,7 +170,7 @@ static int upload_tables_impl(plantos_t* h, const int8_t* lidar_off, const float
 
 static void free_all(plantos_t* h) {
     if (!h) return;
-    cudaFree(h->p.rec); cudaFree(h->p.term_rec); cudaFree(h->p.types); cudaFree(h->p.visits);
+    cudaFree(h->p.rec); cudaFree(h->p.term_rec); cudaFree(h->p.types); cudaFree(h->p.vis4); cudaFree(h->p.visov);
     cudaFree(h->d_tables); cudaFree(h->p.stats); cudaFree(h->p.err);
     cudaFree(h->d_map_cells); cudaFree(h->d_map_rover);
     cudaFree(h->s_actions); cudaFree(h->s_obs); cudaFree(h->s_reward); cudaFree(h->s_done);
@@ -201,8 +202,8 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     p.R = cfg->lidar_range; p.C = cfg->lidar_channels; p.D = plantos_obs_dim(cfg);
     p.W = (p.G + 31) / 32;
     p.TS = (p.G + 2 * p.R) * p.W;                       // wall-padded type plane, u64 words per env
-    p.VS = p.G + 4;                                     // bordered visit plane
-    p.VE = ((p.VS * p.VS + 7) / 8) * 8;                 // u16 elements per env, 16-byte multiple
+    p.VW = ((p.G + 4 + 7) / 8 + 3) / 4 * 4;              // u32 words per visit-nibble row (16-byte rows)
+    p.VE = (p.G + 4) * p.VW;                            // u32 words per env, bordered nibble plane
     p.max_steps = cfg->max_steps; p.nclusters = cfg->num_obstacles / 3;
     {
         double th = std::floor((double)cfg->thirsty_plant_prob * 4294967296.0);
@@ -212,6 +213,8 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     }
     p.seed_lo = (uint32_t)(cfg->seed & 0xffffffffull); p.seed_hi = (uint32_t)(cfg->seed >> 32);
     p.map_source = cfg->map_source; p.map_episodes = 0;
+    p.dbg = 0;
+    if (const char* s = std::getenv("PLANTOS_DEBUG_SKIP")) p.dbg = std::atoi(s);
 
     const size_t N = (size_t)p.N;
 #define ALLOC(ptr, bytes)                                                       \
@@ -225,7 +228,8 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     ALLOC(p.rec, N * 32);
     ALLOC(p.term_rec, N * 32);
     ALLOC(p.types, N * p.TS * 8);
-    ALLOC(p.visits, N * p.VE * 2);
+    ALLOC(p.vis4, N * p.VE * 4);
+    ALLOC(p.visov, N * p.G * p.G * 2);
     ALLOC(p.stats, kStatCount * 8);
     ALLOC(p.err, 4);
     // tables: rw64 | rw32 | dist | pos | visit | off
@@ -244,7 +248,8 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     cudaMemset(p.rec, 0, N * 32);
     cudaMemset(p.term_rec, 0, N * 32);
     cudaMemset(p.types, 0x55, N * p.TS * 8);          // every cell = obstacle: the wall padding
-    cudaMemset(p.visits, 0xFF, N * p.VE * 2);         // every count = 0xFFFF: the window border
+    cudaMemset(p.vis4, 0xFF, N * p.VE * 4);           // every nibble = 15: the window border
+    cudaMemset(p.visov, 0, N * p.G * p.G * 2);
     cudaMemset(p.stats, 0, kStatCount * 8);
     cudaMemset(p.err, 0, 4);
 
@@ -259,7 +264,7 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     }
 
     // kernel selection
-    const bool fast_ok = (p.W == 1) && (p.G + p.R <= 32) && (2 * p.R + 1 <= 16) && (p.C <= 16);
+    const bool fast_ok = (p.W == 1) && (p.VW == 4) && (p.G + p.R <= 32) && (2 * p.R + 1 <= 16) && (p.C <= 16);
     h->use_fast = false;
     if (cfg->kernel != PLANTOS_KERNEL_GENERIC && fast_ok) {
         int epw = 32;
@@ -269,8 +274,20 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
             const int v = std::atoi(s);
             if (v == 4 || v == 8 || v == 16 || v == 32) epw = v;
         }
+        // L2 policy: keep the env state resident (evict_last) when its per-step working set
+        // (~5 lines of 128 B per env) can fit next to the streaming outputs
+        int keep = ((double)p.N * 5 * 128 < 0.8 * (double)prop.l2CacheSize) ? 1 : 0;
+        if (const char* s = std::getenv("PLANTOS_L2_KEEP")) keep = std::atoi(s) ? 1 : 0;
+        p.l2_keep = keep;
+        if (keep) {
+            // evict_last lines only persist inside the persisting-L2 set-aside, which is 0 by
+            // default: claim the device maximum (82.9 MB of the 132.6 MB L2 on B200)
+            size_t want = (size_t)prop.persistingL2CacheMaxSize;
+            if (const char* s = std::getenv("PLANTOS_L2_PERSIST_MB")) want = (size_t)std::atoi(s) << 20;
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+        }
         for (const FastVariant& v : kFastVariants)
-            if (v.R == p.R && v.C == p.C && v.EPW == epw) { h->use_fast = true; h->fast_fn = v.fn; h->fast_epw = epw; }
+            if (v.R == p.R && v.C == p.C && v.EPW == epw && v.keep == keep) { h->use_fast = true; h->fast_fn = v.fn; h->fast_epw = epw; }
     }
     if (cfg->kernel == PLANTOS_KERNEL_FAST && !h->use_fast) {
         free_all(h);
@@ -477,7 +494,7 @@ extern "C" const char* plantos_kernel_name(const plantos_t* h) {
 extern "C" int64_t plantos_state_bytes_per_env(const plantos_t* h) {
     if (!h) return 0;
     const Params& p = h->p;
-    return 32 + 32 + (int64_t)p.TS * 8 + (int64_t)p.VE * 2;
+    return 32 + 32 + (int64_t)p.TS * 8 + (int64_t)p.VE * 4 + (int64_t)p.G * p.G * 2;
 }
 
 extern "C" const char* plantos_last_error(void) { return g_last_error.c_str(); }

@@ -8,12 +8,16 @@
 //                  of word (x+R)*W + (y>>5).  The plane is WALL-PADDED so that the LIDAR never
 //                  needs a bounds check: R all-obstacle rows above and below the grid, and the
 //                  columns >= G of the last word of every row hold the obstacle code (01).
-//   visits  (G+4)^2*2    visit_counts (plantos_env.py:146) as u16, row-major with a 2-cell
-//                  border on every side: cell (x,y) at (x+2)*(G+4) + (y+2).  Border cells hold
-//                  0xFFFF, which min(v,10)/10 maps to the 1.0 the reference writes for
-//                  out-of-bounds window cells (plantos_env.py:310-311), so the 5x5 window is 25
-//                  unconditional loads at lane-constant offsets.  Counts saturate at 65534 (a
-//                  cell gains at most one visit every second step; max_steps <= 65535).
+//   vis4    (G+4)*VW*4  visit_counts (plantos_env.py:146) as saturating 4-BIT counters, 8 per
+//                  u32 word, rows of VW words (a multiple of 4, i.e. 16-byte rows), with a
+//                  2-cell border on every side: cell (x,y) is nibble (y+2) of row (x+2).
+//                  Border nibbles hold 15.  The observation only needs min(v,10)/10
+//                  (plantos_env.py:308) and 15 maps to the 1.0 the reference writes for
+//                  out-of-bounds window cells (:310-311), so the 5x5 window is FIVE CONSECUTIVE
+//                  16-byte rows (80 contiguous bytes when G <= 28) read without bounds checks.
+//   visov   G*G*2  exact u16 count of the cells whose nibble has saturated (v >= 15); never
+//                  read or written for the others, so it stays out of cache and DRAM traffic.
+//                  visit_counts[x,y] = nibble < 15 ? nibble : visov[x*G+y]  (exact up to 65535).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -33,17 +37,21 @@ struct Params {
     int G, P, O, R, C, D;
     int W;          // u64 words per type row
     int TS;         // u64 words per env in the type plane: (G + 2R) * W
-    int VS, VE;     // visit row stride (G + 4) and u16 elements per env (padded to 8)
+    int VW;         // u32 words per nibble row (multiple of 4)
+    int VE;         // u32 words per env in the nibble plane: (G + 4) * VW
     int max_steps;
     int nclusters;  // O / 3 (plantos_env.py:341)
     unsigned long long thirsty_thresh;  // floor(prob * 2^32); draw < thresh => thirsty
     uint32_t seed_lo, seed_hi;
+    int dbg;           // perf-debug mask (PLANTOS_DEBUG_SKIP): 1 no obs stores, 2 no visit loads, 4 no row loads
+    int l2_keep;       // 1: tag state accesses L2::evict_last (fast kernel)
     int map_source;    // 0 philox, 1 injected
     int map_episodes;  // injected maps per env
     // persistent state
     uint4* rec;
     uint64_t* types;
-    uint16_t* visits;
+    uint32_t* vis4;
+    uint16_t* visov;
     uint4* term_rec;   // snapshot of rec at each env's latest terminal step
     // tables (global memory; staged into shared memory per block)
     const int8_t* lidar_off;  // [C][R][2]
@@ -110,7 +118,9 @@ __device__ __forceinline__ void pack_rec(const EnvRec& r, uint4& a, uint4& b) {
 // ------------------------------------------------------------------- helpers
 __device__ __forceinline__ int cell_of(uint64_t word, int ylow) { return (int)((word >> (2 * ylow)) & 3ull); }
 
-__device__ __forceinline__ int visit_index(int x, int y, int VS) { return (x + 2) * VS + (y + 2); }
+// nibble plane addressing of grid cell (x, y): u32 word index inside the env, and bit shift
+__device__ __forceinline__ int nib_word(int x, int y, int VW) { return (x + 2) * VW + ((y + 2) >> 3); }
+__device__ __forceinline__ int nib_shift(int y) { return 4 * ((y + 2) & 7); }
 
 // valid-column mask (bit0 of each cell) for word w of a row
 __device__ __forceinline__ uint64_t col_mask(int G, int w) {
@@ -170,7 +180,7 @@ struct Tables {
     const int8_t* off;    // [C][R][2]
     const float* dist;    // [R+1]
     const float* pos;     // [G]
-    const float* visit;   // [11]
+    const float* visit;   // [16]: min(k,10)/10 for every nibble value k
     const float* rw32;    // [12]
     const double* rw64;   // [12]
     const float* onehot;  // [4][4] identity rows: the one-hot entity encoding (plantos_env.py:290-292)
@@ -183,7 +193,7 @@ __host__ __device__ inline int tables_bytes(int G, int R, int C) {
     int b = 2 * kRwCount * 8;              // rw64
     b += 16 * 4;                           // onehot (16-byte aligned: 96 B in)
     b += 2 * kRwCount * 4;                 // rw32
-    b += (R + 1) * 4 + G * 4 + 12 * 4;     // dist, pos, visit(11 padded to 12)
+    b += (R + 1) * 4 + G * 4 + 16 * 4;     // dist, pos, visit
     b += align_up(C * R * 2, 16);          // offsets
     return align_up(b, 16);
 }
@@ -196,13 +206,13 @@ __device__ inline Tables load_tables(const Params& p, unsigned char* smem) {
     float* dist = rw32 + 2 * kRwCount;
     float* pos = dist + (p.R + 1);
     float* visit = pos + p.G;
-    int8_t* off = reinterpret_cast<int8_t*>(visit + 12);
+    int8_t* off = reinterpret_cast<int8_t*>(visit + 16);
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < 2 * kRwCount; i += nt) { rw64[i] = p.reward64[i]; rw32[i] = p.reward32[i]; }
     for (int i = tid; i < 16; i += nt) onehot[i] = ((i >> 2) == (i & 3)) ? 1.0f : 0.0f;
     for (int i = tid; i <= p.R; i += nt) dist[i] = p.dist_tab[i];
     for (int i = tid; i < p.G; i += nt) pos[i] = p.pos_tab[i];
-    for (int i = tid; i < 11; i += nt) visit[i] = p.visit_tab[i];
+    for (int i = tid; i < 16; i += nt) visit[i] = p.visit_tab[i < 10 ? i : 10];   // min(v, 10) / 10.0
     for (int i = tid; i < p.C * p.R * 2; i += nt) off[i] = p.lidar_off[i];
     __syncthreads();
     Tables t;
@@ -210,12 +220,60 @@ __device__ inline Tables load_tables(const Params& p, unsigned char* smem) {
     return t;
 }
 
+// ------------------------------------------------------------ L2 residency hints
+// The env state (records, type rows, visit nibbles) is re-read every step while observations,
+// rewards and flags are written once and never read back by the simulator.  On B200 the
+// state's per-step working set (a few 128-byte lines per env) fits the 126 MB L2 only if the
+// write-once streams do not push it out, so state accesses can carry an L2::evict_last policy
+// (observation stores carry evict-first, see plantos_fast.cuh).
+struct PlainMem {
+    __device__ __forceinline__ uint64_t ld64(const uint64_t* q) const { return *q; }
+    __device__ __forceinline__ uint32_t ld32(const uint32_t* q) const { return *q; }
+    __device__ __forceinline__ uint4 ld128(const uint4* q) const { return *q; }
+    __device__ __forceinline__ void st64(uint64_t* q, uint64_t v) const { *q = v; }
+    __device__ __forceinline__ void st32(uint32_t* q, uint32_t v) const { *q = v; }
+    __device__ __forceinline__ void st128(uint4* q, const uint4& v) const { *q = v; }
+};
+
+struct KeepMem {   // every access tagged L2::evict_last
+    uint64_t pol;
+    __device__ __forceinline__ KeepMem() {
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    }
+    __device__ __forceinline__ uint64_t ld64(const uint64_t* q) const {
+        uint64_t v;
+        asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(q), "l"(pol) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ uint32_t ld32(const uint32_t* q) const {
+        uint32_t v;
+        asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(q), "l"(pol) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ uint4 ld128(const uint4* q) const {
+        uint4 v;
+        asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(q), "l"(pol) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void st64(uint64_t* q, uint64_t v) const {
+        asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" :: "l"(q), "l"(v), "l"(pol) : "memory");
+    }
+    __device__ __forceinline__ void st32(uint32_t* q, uint32_t v) const {
+        asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(q), "r"(v), "l"(pol) : "memory");
+    }
+    __device__ __forceinline__ void st128(uint4* q, const uint4& v) const {
+        asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;"
+                     :: "l"(q), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+    }
+};
+
 // ------------------------------------------------------------ env transition
 // One PlantOSEnv.step up to (not including) the observation: plantos_env.py:160-222 and the
 // termination/bonus logic of :176-181.  Executed by ONE thread for env e.  `row_word` is the
 // type word holding the cell the action looks at (move target, or the rover's own cell when
-// watering) or kObstAll when the target is out of bounds; `visits_e`/`types_e` point at the
-// env's planes in global memory and receive the read-modify-writes.
+// watering) or kObstAll when the target is out of bounds; `word_ptr` is where it lives (for
+// the watering write); `vis_e` / `visov_e` are the env's nibble and overflow planes.
 struct StepOut {
     int ridx;        // index into the reward tables
     int terminated;  // exploration >= 100 % (plantos_env.py:176,244-246)
@@ -236,19 +294,29 @@ __device__ __forceinline__ void action_target(const EnvRec& r, long long action,
     }
 }
 
+template <class Mem>
 __device__ __forceinline__ StepOut apply_action(EnvRec& r, long long action, int tx, int ty, bool inb,
                                                 uint64_t row_word, uint64_t* word_ptr,
-                                                uint16_t* visits_e, int VS, int max_steps) {
+                                                uint32_t* vis_e, uint16_t* visov_e, int G, int VW,
+                                                int max_steps, const Mem& mem) {
     StepOut o;
     o.watered = 0;
     r.step += 1;                                           // :162
     const int t = inb ? cell_of(row_word, ty & 31) : kObstacle;
     if (action < 4) {
         if (t != kObstacle) {                              // :193-195 (plants are walkable)
-            uint16_t* vp = visits_e + visit_index(tx, ty, VS);
-            const unsigned v = *vp;
-            const bool fresh = (v == 0);                   // :197
-            *vp = (uint16_t)(v < 65534u ? v + 1u : 65534u);  // :203
+            uint32_t* vp = vis_e + nib_word(tx, ty, VW);
+            const int sh = nib_shift(ty);
+            const uint32_t w = mem.ld32(vp);
+            const unsigned nib = (w >> sh) & 15u;
+            const bool fresh = (nib == 0);                 // :197
+            if (nib < 15u) {                               // :203, count still lives in the nibble
+                mem.st32(vp, w + (1u << sh));
+                if (nib == 14u) visov_e[tx * G + ty] = 15;
+            } else {                                       // saturated: exact count in visov
+                const unsigned v = visov_e[tx * G + ty];
+                if (v < 65535u) visov_e[tx * G + ty] = (uint16_t)(v + 1u);
+            }
             r.x = tx; r.y = ty;                            // :199
             r.explored += fresh;                           // explored_map>0 count, :198-200,320
             o.ridx = fresh ? 0 : 1;                        // R_EXPLORATION / R_REVISIT
@@ -259,7 +327,7 @@ __device__ __forceinline__ StepOut apply_action(EnvRec& r, long long action, int
         }
     } else {
         if (t == kThirsty) {                               // :217-219
-            *word_ptr = row_word ^ (1ull << (2 * (ty & 31)));  // 3 -> 2
+            mem.st64(word_ptr, row_word ^ (1ull << (2 * (ty & 31))));  // 3 -> 2
             r.thirsty -= 1;
             r.watered += 1;
             o.watered = 1;

@@ -1,32 +1,38 @@
 // plantos_fast.cuh -- the sm_100a hot kernel for the reference presets.
 //
-// Requirements (checked on the host): W == 1 (G <= 32), G + R <= 32, 2R+1 <= 16, C <= 16.
-// Both the training preset (G25 R6 C16, D=107; A2C_training.py:206-212) and the ctor default
-// (G21 R2 C10, D=77; plantos_env.py:25-26) qualify; everything else runs k_step_generic.
+// Requirements (checked on the host): W == 1 and VW == 4 (G <= 28), G + R <= 32, 2R+1 <= 16,
+// C <= 16.  Both the training preset (G25 R6 C16, D=107; A2C_training.py:206-212) and the ctor
+// default (G21 R2 C10, D=77; plantos_env.py:25-26) qualify; everything else runs
+// k_step_generic.
 //
 // Work split inside one warp, which owns a tile of EPW consecutive envs:
 //   phase A  one LANE per env   -- the scalar transition (plantos_env.py:160-222): record
-//            load, action, target-cell lookup, visit-count read-modify-write, watering,
+//            load, action, target-cell lookup, visit-nibble read-modify-write, watering,
 //            reward / done / record stores.  Outputs are coalesced across the tile.
 //   phase B  one HALF-WARP per env, two envs per iteration -- the observation
 //            (plantos_env.py:251-315): 2R+1 lanes each fetch one 8-byte row of the wall-padded
 //            type plane and shift it into a rover-centred window word (no bounds checks
 //            anywhere); one lane per ray marches the integer offset table, with a warp
-//            shuffle as the row lookup; the 25 visit cells are two unconditional u16 loads
-//            per lane from the bordered visit plane.  Rows are assembled in a 4-env
+//            shuffle as the row lookup; five lanes fetch the five 16-byte visit-nibble rows
+//            of the 5x5 window (80 contiguous bytes) and cut the 20-bit slice the window
+//            needs, which the 25 cell lanes read by shuffle.  Rows are assembled in a 4-env
 //            shared-memory tile whose 16*D bytes are 16-byte aligned in the [N, D] fp32
-//            buffer and leave with streaming 128-bit stores (st.global.cs.v4) so that the
-//            write-once observation stream does not evict the env state from L2.  The loop
-//            is unrolled by two with ping-pong prefetch registers: the loads of iteration
-//            i+1 are in flight during the arithmetic of iteration i.
+//            buffer and leave with streaming 128-bit stores (st.global.cs.v4, evict-first)
+//            so that the write-once observation stream does not evict the env state from L2.
+//            The loop is unrolled by two with ping-pong prefetch registers: the loads of
+//            iteration i+1 are in flight during the arithmetic of iteration i.
 //   phase C  whole warp, rare   -- SB3 auto-reset of finished envs (terminal observation,
 //            Philox / injected map, fresh observation) via the generic warp routines.
 // A ragged last tile (N % EPW != 0) is stepped env by env with step_env_warp.
 #pragma once
+#include <type_traits>
 #include "plantos_generic.cuh"
 
 namespace plantos_dev {
 
+#ifndef PLANTOS_FAST_MINBLOCKS
+#define PLANTOS_FAST_MINBLOCKS 8
+#endif
 constexpr int kFastWarps = 4;
 
 __host__ __device__ inline int fast_warp_scratch_bytes(int G, int D) {
@@ -35,23 +41,25 @@ __host__ __device__ inline int fast_warp_scratch_bytes(int G, int D) {
 
 struct Prefetch {
     uint64_t row;       // this lane's type row of the env's window
-    unsigned v0, v1;    // this lane's two visit-window cells
+    unsigned vlo, vhi;  // the two nibble words of this lane's visit row that hold the window
     unsigned pw;        // x | y << 8 of the env
 };
 
-template <int R, int C, int EPW>
-__global__ void __launch_bounds__(kFastWarps * 32, 8)
+template <int R, int C, int EPW, bool KEEP>
+__global__ void __launch_bounds__(kFastWarps * 32, PLANTOS_FAST_MINBLOCKS)
 k_step_fast(const Params p, const StepIO io) {
     constexpr int D = 5 * C + 27;
     constexpr int NROW = 2 * R + 1;
+    constexpr int VW = 4;                 // nibble words per visit row (G + 4 <= 32)
     constexpr unsigned FULL = 0xffffffffu;
     static_assert(NROW <= 16 && C <= 16, "fast kernel shape limits");
     static_assert(EPW % 4 == 0 && EPW <= 32, "tile must be whole 4-env groups");
 
     extern __shared__ __align__(16) unsigned char smem[];
     const Tables t = load_tables(p, smem);
+    typename std::conditional<KEEP, KeepMem, PlainMem>::type const mem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int G = p.G, VS = p.VS, VE = p.VE, TS = p.TS;
+    const int G = p.G, VE = p.VE, TS = p.TS;
     const int e0 = (blockIdx.x * kFastWarps + warp) * EPW;
     if (e0 >= p.N) return;
     unsigned char* scratch = smem + tables_bytes(G, R, C) + warp * fast_warp_scratch_bytes(G, D);
@@ -70,15 +78,15 @@ k_step_fast(const Params p, const StepIO io) {
     unsigned posw = 0;
     if (act) {
         const int e = e0 + lane;
-        uint4 ra = p.rec[2 * (size_t)e], rb = p.rec[2 * (size_t)e + 1];
+        uint4 ra = mem.ld128(p.rec + 2 * (size_t)e), rb = mem.ld128(p.rec + 2 * (size_t)e + 1);
         const long long action = __ldcs(io.actions + e);
         r = unpack_rec(ra, rb);
         int tx, ty; bool inb;
         action_target(r, action, G, tx, ty, inb);
         uint64_t* wp = p.types + (size_t)e * TS + R + (inb ? tx : r.x);
-        const uint64_t word = inb ? *wp : kObstAll;
-        uint16_t* visits_e = p.visits + (size_t)e * VE;
-        const StepOut o = apply_action(r, action, tx, ty, inb, word, wp, visits_e, VS, p.max_steps);
+        const uint64_t word = inb ? mem.ld64(wp) : kObstAll;
+        const StepOut o = apply_action(r, action, tx, ty, inb, word, wp, p.vis4 + (size_t)e * VE,
+                                       p.visov + (size_t)e * G * G, G, VW, p.max_steps, mem);
         r.ret += t.rw64[o.ridx];
         io.reward[e] = t.rw32[o.ridx];
         term = o.terminated; trunc = o.truncated; done = term | trunc;
@@ -86,8 +94,8 @@ k_step_fast(const Params p, const StepIO io) {
         if (io.terminated) io.terminated[e] = (uint8_t)term;
         if (io.truncated) io.truncated[e] = (uint8_t)trunc;
         pack_rec(r, ra, rb);
-        p.rec[2 * (size_t)e] = ra;
-        p.rec[2 * (size_t)e + 1] = rb;
+        mem.st128(p.rec + 2 * (size_t)e, ra);
+        mem.st128(p.rec + 2 * (size_t)e + 1, rb);
         if (done) {
             p.term_rec[2 * (size_t)e] = ra;
             p.term_rec[2 * (size_t)e + 1] = rb;
@@ -107,15 +115,16 @@ k_step_fast(const Params p, const StepIO io) {
         srcl[rr] = hbase + dx + R;     // lane holding window row x+dx
         shf[rr] = 2 * (dy + R);        // bit offset of column y+dy inside the window word
     }
-    // lane-constant bases: padded type row (x - R + sub) + R = x + sub; visit cells
-    // (x + q/5 - 2, y + q%5 - 2) -> padded (x + q/5) * VS + (y + q%5) for q = sub, sub + 16
-    // (byte pointers + unsigned 32-bit byte offsets keep the per-iteration address math to one
-    // multiply-add and one wide add per load)
+    // lane-constant bases (byte pointers + unsigned 32-bit byte offsets keep the per-iteration
+    // address math short): padded type row (x - R + sub) + R = x + sub; visit-nibble row
+    // (x - 2 + sub) + 2 = x + sub for sub < 5, 16 bytes each
     const char* trow = reinterpret_cast<const char*>(p.types + (size_t)e0 * TS + sub);
-    const char* vc0 = reinterpret_cast<const char*>(p.visits + (size_t)e0 * VE + (sub / 5) * VS + sub % 5);
-    const char* vc1 = reinterpret_cast<const char*>(p.visits + (size_t)e0 * VE + ((sub + 16) / 5) * VS + (sub + 16) % 5);
-    const unsigned TS8 = 8u * TS, VE2 = 2u * VE, VS2 = 2u * VS;
-    const bool has_row = sub < NROW, has_ray = sub < C, has_v1 = sub < 9;
+    const char* vrow = reinterpret_cast<const char*>(p.vis4 + (size_t)e0 * VE + (size_t)sub * VW);
+    const unsigned TS8 = 8u * TS, VE4 = 4u * VE;
+    const bool has_row = sub < NROW, has_ray = sub < C, has_vrow = sub < 5, has_v1 = sub < 9;
+    // the two window cells this lane converts: q = sub and q = sub + 16 -> (row lane, nibble shift)
+    const int vsrc0 = hbase + sub / 5, vsh0 = 4 * (sub % 5);
+    const int vsrc1 = hbase + (sub + 16) / 5, vsh1 = 4 * ((sub + 16) % 5);
     float* const rowA = tile + half * D;          // env 2*it + half of an even iteration
     float* const rowB = tile + (2 + half) * D;    // ... of an odd iteration
     const float4* onehot = reinterpret_cast<const float4*>(t.onehot);
@@ -126,11 +135,16 @@ k_step_fast(const Params p, const StepIO io) {
         n.pw = __shfl_sync(FULL, posw, j);
         const unsigned x = n.pw & 0xff, y = n.pw >> 8;
         n.row = kObstAll;
-        if (has_row) n.row = *reinterpret_cast<const uint64_t*>(trow + ((unsigned)j * TS8 + 8u * x));
-        const unsigned vo = (unsigned)j * VE2 + (unsigned)x * VS2 + 2u * y;
-        n.v0 = *reinterpret_cast<const uint16_t*>(vc0 + vo);
-        n.v1 = 0;
-        if (has_v1) n.v1 = *reinterpret_cast<const uint16_t*>(vc1 + vo);
+        if (has_row && !(p.dbg & 4))
+            n.row = mem.ld64(reinterpret_cast<const uint64_t*>(trow + ((unsigned)j * TS8 + 8u * x)));
+        n.vlo = 0; n.vhi = 0;
+        if (has_vrow && !(p.dbg & 2)) {
+            // window nibbles y .. y+4 of this row start in word y>>3 and may spill into the next
+            const unsigned w0 = y >> 3, w1 = w0 < 3u ? w0 + 1u : 3u;
+            const char* base = vrow + ((unsigned)j * VE4 + 16u * x);
+            n.vlo = mem.ld32(reinterpret_cast<const uint32_t*>(base + 4u * w0));
+            n.vhi = mem.ld32(reinterpret_cast<const uint32_t*>(base + 4u * w1));
+        }
     };
 
     auto compute = [&](const Prefetch& c, float* row) {
@@ -139,6 +153,9 @@ k_step_fast(const Params p, const StepIO io) {
         const int s = 2 * y;
         const uint64_t ext = (c.row << (2 * R)) | LOWPAD;
         const unsigned w = (unsigned)((ext >> s) | ((kObstAll << 1) << (63 - s)));
+        // this lane's visit row: the 5 nibbles y .. y+4 (20 bits; when they sit entirely in
+        // word 3 the funnel's high half is unused)
+        const unsigned vslice = __funnelshift_r(c.vlo, c.vhi, 4 * (y & 7));
         // LIDAR march (plantos_env.py:260-284): sample rr looks at window row srcl[rr], bits shf[rr]
         unsigned acc = 0;
 #pragma unroll
@@ -146,6 +163,8 @@ k_step_fast(const Params p, const StepIO io) {
             const unsigned wr = __shfl_sync(FULL, w, srcl[rr]);
             acc += ((wr >> shf[rr]) & 3u) << (2 * rr);
         }
+        const unsigned s0 = __shfl_sync(FULL, vslice, vsrc0);
+        const unsigned s1 = __shfl_sync(FULL, vslice, vsrc1);
         const unsigned m = (acc | (acc >> 1)) & 0x55555555u;
         const int b = __ffs(m) - 1;                       // -1 when nothing was hit
         const int dist = m ? (b >> 1) + 1 : R;
@@ -157,29 +176,34 @@ k_step_fast(const Params p, const StepIO io) {
             q[1] = oh.x; q[2] = oh.y; q[3] = oh.z; q[4] = oh.w;
         }
         if (sub < 2) row[5 * C + sub] = t.pos[sub ? y : x];                       // :294-296
-        row[5 * C + 2 + sub] = t.visit[c.v0 < 10u ? c.v0 : 10u];                  // :298-313
-        if (has_v1) row[5 * C + 18 + sub] = t.visit[c.v1 < 10u ? c.v1 : 10u];
+        row[5 * C + 2 + sub] = t.visit[(s0 >> vsh0) & 15u];                       // :298-313
+        if (has_v1) row[5 * C + 18 + sub] = t.visit[(s1 >> vsh1) & 15u];
     };
 
     float4* const obs4 = reinterpret_cast<float4*>(io.obs) + (size_t)(e0 >> 2) * D;
     const float4* src4 = reinterpret_cast<const float4*>(tile);
-    Prefetch pa, pb;
-    issue(0, pa);
-#pragma unroll 1
-    for (int it = 0; it < EPW / 2; it += 2) {
-        issue(it + 1, pb);
-        compute(pa, rowA);
-        if (it + 2 < EPW / 2) issue(it + 2, pa);
-        compute(pb, rowB);
-        // flush four env rows = D float4, 16-byte aligned because e0 and 2*it are multiples of 4
+    auto flush = [&](int group) {
+        // four env rows = D float4, 16-byte aligned because e0 and the group start are multiples of 4
         __syncwarp();
-        float4* dst4 = obs4 + (size_t)(it >> 1) * D;
+        float4* dst4 = obs4 + (size_t)group * D;
 #pragma unroll
         for (int k = 0; k < (D + 31) / 32; ++k) {
             const int idx = k * 32 + lane;
-            if (idx < D) __stcs(dst4 + idx, src4[idx]);
+            if (idx < D && !(p.dbg & 1)) __stcs(dst4 + idx, src4[idx]);
         }
         __syncwarp();
+    };
+
+    constexpr int NIT = EPW / 2;
+    Prefetch pa, pb;
+    issue(0, pa);
+#pragma unroll 1
+    for (int it = 0; it < NIT; it += 2) {
+        issue(it + 1, pb);
+        compute(pa, rowA);
+        if (it + 2 < NIT) issue(it + 2, pa);
+        compute(pb, rowB);
+        flush(it >> 1);
     }
 
     // ---- phase C: auto-reset of finished envs (rare; warp-cooperative generic code)
@@ -191,16 +215,16 @@ k_step_fast(const Params p, const StepIO io) {
         const int episode = __shfl_sync(FULL, r.episode, j);
         const int px = __shfl_sync(FULL, r.x, j), py = __shfl_sync(FULL, r.y, j);
         const uint64_t* types_e = p.types + (size_t)ej * TS + R;
-        const uint16_t* visits_e = p.visits + (size_t)ej * VE;
+        const uint32_t* vis_e = p.vis4 + (size_t)ej * VE;
         if (io.terminal_obs) {
             for (int idx = lane; idx < G; idx += 32) plane[idx] = types_e[idx];
             __syncwarp();
-            build_obs_warp(p, t, plane, visits_e, px, py, tile, lane);
+            build_obs_warp(p, t, plane, vis_e, px, py, tile, lane);
             store_obs_row(tile, io.terminal_obs + (size_t)ej * D, D, lane);
             __syncwarp();
         }
         const EnvRec nr = reset_env_warp(p, ej, episode, plane, lane);
-        build_obs_warp(p, t, plane, visits_e, nr.x, nr.y, tile, lane);
+        build_obs_warp(p, t, plane, vis_e, nr.x, nr.y, tile, lane);
         store_obs_row(tile, io.obs + (size_t)ej * D, D, lane);
         if (lane == 0) {
             uint4 ra, rb;

@@ -20,9 +20,9 @@ __host__ __device__ inline int generic_warp_scratch_bytes(int G, int W, int D) {
 
 // ----------------------------------------------------------------- observation
 // plantos_env.py:251-315.  `plane` (shared memory, indexed by grid row) must hold the type
-// rows x-R .. x+R that lie inside the grid; visits are read from global memory.
+// rows x-R .. x+R that lie inside the grid; visit nibbles are read from global memory.
 __device__ __forceinline__ void build_obs_warp(const Params& p, const Tables& t, const uint64_t* plane,
-                                               const uint16_t* visits_e, int x, int y, float* obs_s, int lane) {
+                                               const uint32_t* vis_e, int x, int y, float* obs_s, int lane) {
     const int G = p.G, W = p.W, R = p.R, C = p.C;
     for (int i = lane; i < C; i += 32) {                 // one lane per ray
         int dist = R, kind = kEmpty;                     // :262-263
@@ -46,9 +46,10 @@ __device__ __forceinline__ void build_obs_warp(const Params& p, const Tables& t,
         obs_s[5 * C] = t.pos[x];
         obs_s[5 * C + 1] = t.pos[y];
     }
-    if (lane < 25) {                                     // :298-313; the 0xFFFF border reads as 1.0
-        const unsigned cnt = visits_e[visit_index(x + lane / 5 - 2, y + lane % 5 - 2, p.VS)];
-        obs_s[5 * C + 2 + lane] = t.visit[cnt < 10u ? cnt : 10u];
+    if (lane < 25) {                                     // :298-313; border nibbles (15) read as 1.0
+        const int gx = x + lane / 5 - 2, gy = y + lane % 5 - 2;
+        const unsigned nib = (vis_e[nib_word(gx, gy, p.VW)] >> nib_shift(gy)) & 15u;
+        obs_s[5 * C + 2 + lane] = t.visit[nib];
     }
     __syncwarp();
 }
@@ -59,8 +60,8 @@ __device__ __forceinline__ void store_obs_row(const float* obs_s, float* dst, in
 
 // ----------------------------------------------------------------------- reset
 // New episode for env e (local index): builds the map in `plane` (shared), writes the type
-// rows and a fresh visit plane (zeros, rover cell = 1, plantos_env.py:146-147; 0xFFFF border)
-// to global memory and returns the fresh record in all lanes.  `episode` selects the
+// rows and a fresh visit-nibble plane (zeros, rover cell = 1, plantos_env.py:146-147; border
+// 15) to global memory and returns the fresh record in all lanes.  `episode` selects the
 // injected map / Philox counter and is stored incremented.
 __device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int episode, uint64_t* plane, int lane) {
     const int G = p.G, W = p.W;
@@ -153,20 +154,20 @@ __device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int epi
     }
     n_obst = warp_sum_i(n_obst);
     n_thirsty = warp_sum_i(n_thirsty);
-    // visit plane: pairs of u16 as u32 words (VE is even and the plane is 4-byte aligned)
-    uint32_t* vw = reinterpret_cast<uint32_t*>(p.visits + (size_t)e * p.VE);
-    const int VS = p.VS, rcell = visit_index(rx, ry, VS);
-    for (int wi = lane; wi < p.VE / 2; wi += 32) {
+    // visit nibbles: 0 inside the grid, 15 on the border / row padding, 1 under the rover
+    uint32_t* vis_e = p.vis4 + (size_t)e * p.VE;
+    const int VW = p.VW;
+    for (int wi = lane; wi < p.VE; wi += 32) {
+        const int vx = wi / VW - 2, c0 = (wi % VW) * 8 - 2;
         uint32_t word = 0;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            const int el = 2 * wi + hf;
-            const int vx = el / VS - 2, vy = el % VS - 2;
-            uint32_t v = 0xffffu;                                   // border / tail padding
-            if ((unsigned)vx < (unsigned)G && (unsigned)vy < (unsigned)G) v = (el == rcell) ? 1u : 0u;
-            word |= v << (16 * hf);
+        for (int k = 0; k < 8; ++k) {
+            const int vy = c0 + k;
+            uint32_t v = 15u;
+            if ((unsigned)vx < (unsigned)G && (unsigned)vy < (unsigned)G) v = (vx == rx && vy == ry) ? 1u : 0u;
+            word |= v << (4 * k);
         }
-        vw[wi] = word;
+        vis_e[wi] = word;
     }
     __syncwarp();
     EnvRec r;
@@ -210,7 +211,8 @@ __device__ __forceinline__ void step_env_warp(const Params& p, const Tables& t, 
     const unsigned posw = __shfl_sync(0xffffffffu, ra.x, 0);
     int x = posw & 0xff, y = (posw >> 8) & 0xff;
     uint64_t* types_e = p.types + (size_t)e * p.TS + (size_t)p.R * p.W;   // grid row 0
-    uint16_t* visits_e = p.visits + (size_t)e * p.VE;
+    uint32_t* vis_e = p.vis4 + (size_t)e * p.VE;
+    uint16_t* visov_e = p.visov + (size_t)e * p.G * p.G;
 
     // stage the rows the step can look at: x-R-1 .. x+R+1 (move of one row + LIDAR reach)
     const int lo = max(0, x - p.R - 1), hi = min(p.G - 1, x + p.R + 1);
@@ -225,8 +227,9 @@ __device__ __forceinline__ void step_env_warp(const Params& p, const Tables& t, 
         action_target(r, action, p.G, tx, ty, inb);
         const int widx = inb ? tx * p.W + (ty >> 5) : 0;
         const uint64_t word = inb ? plane[widx] : kObstAll;
-        uint64_t newword = word;
-        const StepOut o = apply_action(r, action, tx, ty, inb, word, &newword, visits_e, p.VS, p.max_steps);
+        uint64_t newword = word;   // (generic pointer to a local: plain accessors only)
+        const StepOut o = apply_action(r, action, tx, ty, inb, word, &newword, vis_e, visov_e, p.G, p.VW,
+                                       p.max_steps, PlainMem());
         if (o.watered) { plane[widx] = newword; types_e[widx] = newword; }
         r.ret += t.rw64[o.ridx];
         io.reward[e] = t.rw32[o.ridx];
@@ -241,7 +244,7 @@ __device__ __forceinline__ void step_env_warp(const Params& p, const Tables& t, 
     x = flagw & 0xff; y = (flagw >> 8) & 0xff;
     const bool done = (flagw >> 16) & 1;
 
-    build_obs_warp(p, t, plane, visits_e, x, y, obs_s, lane);
+    build_obs_warp(p, t, plane, vis_e, x, y, obs_s, lane);
     float* obs_row = io.obs + (size_t)e * p.D;
     if (!done) {
         store_obs_row(obs_s, obs_row, p.D, lane);
@@ -260,7 +263,7 @@ __device__ __forceinline__ void step_env_warp(const Params& p, const Tables& t, 
         episode = __shfl_sync(0xffffffffu, episode, 0);
         __syncwarp();
         const EnvRec nr = reset_env_warp(p, e, episode, plane, lane);
-        build_obs_warp(p, t, plane, visits_e, nr.x, nr.y, obs_s, lane);
+        build_obs_warp(p, t, plane, vis_e, nr.x, nr.y, obs_s, lane);
         store_obs_row(obs_s, obs_row, p.D, lane);
         if (lane == 0) pack_rec(nr, ra, rb);
     }
@@ -297,8 +300,7 @@ k_reset_all(const Params p, float* obs) {
         if (lane == 0) episode = (int)p.rec[2 * (size_t)e].w;
         episode = __shfl_sync(0xffffffffu, episode, 0);
         const EnvRec nr = reset_env_warp(p, e, episode, plane, lane);
-        const uint16_t* visits_e = p.visits + (size_t)e * p.VE;
-        build_obs_warp(p, t, plane, visits_e, nr.x, nr.y, obs_s, lane);
+        build_obs_warp(p, t, plane, p.vis4 + (size_t)e * p.VE, nr.x, nr.y, obs_s, lane);
         store_obs_row(obs_s, obs + (size_t)e * p.D, p.D, lane);
         if (lane == 0) {
             uint4 ra, rb;
@@ -318,7 +320,10 @@ __global__ void k_get_state(const Params p, uint8_t* cells, int32_t* visits) {
         const int e = (int)(i / gg), c = (int)(i - (size_t)e * gg);
         const int x = c / p.G, y = c - x * p.G;
         if (cells) cells[i] = (uint8_t)cell_of(p.types[(size_t)e * p.TS + (size_t)(x + p.R) * p.W + (y >> 5)], y & 31);
-        if (visits) visits[i] = (int32_t)p.visits[(size_t)e * p.VE + visit_index(x, y, p.VS)];
+        if (visits) {
+            const unsigned nib = (p.vis4[(size_t)e * p.VE + nib_word(x, y, p.VW)] >> nib_shift(y)) & 15u;
+            visits[i] = nib < 15u ? (int32_t)nib : (int32_t)p.visov[(size_t)e * gg + c];
+        }
     }
 }
 
@@ -350,11 +355,24 @@ __global__ void k_set_state(const Params p, const uint8_t* cells, const int32_t*
         r.thirsty = warp_sum_i(n_thirsty);
     }
     if (visits) {
-        uint16_t* ve = p.visits + (size_t)e * p.VE;
-        for (int c = lane; c < gg; c += 32) {
-            const int x = c / G, y = c - x * G;
-            const int v = visits[(size_t)e * gg + c];
-            ve[visit_index(x, y, p.VS)] = (uint16_t)(v < 0 ? 0 : (v > 65534 ? 65534 : v));
+        uint32_t* vis_e = p.vis4 + (size_t)e * p.VE;
+        uint16_t* visov_e = p.visov + (size_t)e * gg;
+        const int VW = p.VW;
+        for (int wi = lane; wi < p.VE; wi += 32) {     // one lane owns a whole nibble word
+            const int vx = wi / VW - 2, c0 = (wi % VW) * 8 - 2;
+            uint32_t word = 0;
+            for (int k = 0; k < 8; ++k) {
+                const int vy = c0 + k;
+                uint32_t nib = 15u;
+                if ((unsigned)vx < (unsigned)G && (unsigned)vy < (unsigned)G) {
+                    int v = visits[(size_t)e * gg + vx * G + vy];
+                    v = v < 0 ? 0 : (v > 65535 ? 65535 : v);
+                    nib = v < 15 ? (uint32_t)v : 15u;
+                    if (v >= 15) visov_e[vx * G + vy] = (uint16_t)v;
+                }
+                word |= nib << (4 * k);
+            }
+            vis_e[wi] = word;
         }
     }
     if (sc) {

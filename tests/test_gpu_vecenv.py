@@ -38,7 +38,7 @@ def test_infos_match_dummyvecenv_monitor():
                 seen_done += 1
                 assert gi["episode"]["r"] == oi["episode"]["r"] and gi["episode"]["l"] == oi["episode"]["l"]
                 assert np.array_equal(gi["terminal_observation"].cpu().numpy(), oi["terminal_observation"])
-    assert seen_done >= 3
+    assert seen_done >= 2
     stats = env.episode_stats(all_reduce=False)
     k = fx["term_t"] < 700
     assert stats["episodes"] == k.sum()
