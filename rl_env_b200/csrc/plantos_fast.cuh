@@ -36,8 +36,27 @@ namespace plantos_dev {
 constexpr int kFastWarps = 4;
 
 __host__ __device__ inline int fast_warp_scratch_bytes(int G, int D) {
-    return 16 * D + align_up(G * 8, 16);   // 4-env obs tile + type plane for phase C / tail
+    return 2 * 16 * D + align_up(G * 8, 16);   // two 4-env obs tiles + type plane for phase C / tail
 }
+
+// ---- TMA (bulk async copy) helpers: shared -> global stores of finished observation tiles
+__device__ __forceinline__ uint32_t smem_u32(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// make this thread's shared-memory writes visible to the async proxy (the TMA unit)
+__device__ __forceinline__ void fence_smem_to_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 :: "l"(gdst), "r"(ssrc), "r"(bytes), "l"(pol) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait_read() {     // <= N groups still reading smem
+    asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 struct Prefetch {
     uint64_t row;       // this lane's type row of the env's window
@@ -64,7 +83,7 @@ k_step_fast(const Params p, const StepIO io) {
     if (e0 >= p.N) return;
     unsigned char* scratch = smem + tables_bytes(G, R, C) + warp * fast_warp_scratch_bytes(G, D);
     float* tile = reinterpret_cast<float*>(scratch);
-    uint64_t* plane = reinterpret_cast<uint64_t*>(scratch + 16 * D);
+    uint64_t* plane = reinterpret_cast<uint64_t*>(scratch + 2 * 16 * D);
 
     if (p.N - e0 < EPW) {   // ragged last tile
         for (int e = e0; e < p.N; ++e) step_env_warp(p, t, io, e, plane, tile, lane);
@@ -125,8 +144,8 @@ k_step_fast(const Params p, const StepIO io) {
     // the two window cells this lane converts: q = sub and q = sub + 16 -> (row lane, nibble shift)
     const int vsrc0 = hbase + sub / 5, vsh0 = 4 * (sub % 5);
     const int vsrc1 = hbase + (sub + 16) / 5, vsh1 = 4 * ((sub + 16) % 5);
-    float* const rowA = tile + half * D;          // env 2*it + half of an even iteration
-    float* const rowB = tile + (2 + half) * D;    // ... of an odd iteration
+    // observation tiles: group g (4 envs) is assembled in buffer g & 1; env 2*it + half of an
+    // even iteration goes to row `half`, of an odd iteration to row 2 + half
     const float4* onehot = reinterpret_cast<const float4*>(t.onehot);
     constexpr uint64_t LOWPAD = kObstAll & ((1ull << (2 * R)) - 1ull);
 
@@ -181,17 +200,16 @@ k_step_fast(const Params p, const StepIO io) {
     };
 
     float4* const obs4 = reinterpret_cast<float4*>(io.obs) + (size_t)(e0 >> 2) * D;
-    const float4* src4 = reinterpret_cast<const float4*>(tile);
+    const uint64_t pol_stream = policy_evict_first();
+    const uint32_t tile_s = smem_u32(tile);
+    // A finished group leaves through the TMA unit: one bulk shared->global copy of 16*D bytes
+    // (16-byte aligned because e0 and the group start are multiples of 4), tagged evict-first.
+    // The copy is asynchronous; the buffer is reused two groups later, after wait_group.read.
     auto flush = [&](int group) {
-        // four env rows = D float4, 16-byte aligned because e0 and the group start are multiples of 4
+        fence_smem_to_async();
         __syncwarp();
-        float4* dst4 = obs4 + (size_t)group * D;
-#pragma unroll
-        for (int k = 0; k < (D + 31) / 32; ++k) {
-            const int idx = k * 32 + lane;
-            if (idx < D && !(p.dbg & 1)) __stcs(dst4 + idx, src4[idx]);
-        }
-        __syncwarp();
+        if (lane == 0 && !(p.dbg & 1))
+            bulk_store(obs4 + (size_t)group * D, tile_s + (group & 1) * 16 * D, 16 * D, pol_stream);
     };
 
     constexpr int NIT = EPW / 2;
@@ -199,12 +217,20 @@ k_step_fast(const Params p, const StepIO io) {
     issue(0, pa);
 #pragma unroll 1
     for (int it = 0; it < NIT; it += 2) {
+        const int group = it >> 1;
+        float* const tb = tile + (group & 1) * 4 * D;
         issue(it + 1, pb);
-        compute(pa, rowA);
+        if (group >= 2) {                 // buffer last used by group - 2: its bulk read must be done
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+        }
+        compute(pa, tb + half * D);
         if (it + 2 < NIT) issue(it + 2, pa);
-        compute(pb, rowB);
-        flush(it >> 1);
+        compute(pb, tb + (2 + half) * D);
+        flush(group);
     }
+    if (lane == 0) bulk_wait_all();       // stores complete before phase C may overwrite rows / exit
+    __syncwarp();
 
     // ---- phase C: auto-reset of finished envs (rare; warp-cooperative generic code)
     unsigned dmask = __ballot_sync(FULL, act && done);
