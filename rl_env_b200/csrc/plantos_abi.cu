@@ -201,7 +201,9 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     p.G = cfg->grid_size; p.P = cfg->num_plants; p.O = cfg->num_obstacles;
     p.R = cfg->lidar_range; p.C = cfg->lidar_channels; p.D = plantos_obs_dim(cfg);
     p.W = (p.G + 31) / 32;
-    p.TS = (p.G + 2 * p.R) * p.W;                       // wall-padded type plane, u64 words per env
+    // wall-padded type plane, u64 words per env: R wall rows above and below the grid plus one
+    // spare row (the fast kernel's 16-byte aligned row fetch may start one row early), even count
+    p.TS = ((p.G + 2 * p.R + 2) & ~1) * p.W;
     p.VW = ((p.G + 4 + 7) / 8 + 3) / 4 * 4;              // u32 words per visit-nibble row (16-byte rows)
     p.VE = (p.G + 4) * p.VW;                            // u32 words per env, bordered nibble plane
     p.max_steps = cfg->max_steps; p.nclusters = cfg->num_obstacles / 3;
@@ -294,7 +296,7 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
         return fail(PLANTOS_EINVAL, "PLANTOS_KERNEL_FAST requested but (G, R, C) has no fast-kernel instantiation");
     }
     h->generic_smem = tables_bytes(p.G, p.R, p.C) + kGenericWarps * generic_warp_scratch_bytes(p.G, p.W, p.D);
-    h->fast_smem = tables_bytes(p.G, p.R, p.C) + kFastWarps * fast_warp_scratch_bytes(p.G, p.D);
+    h->fast_smem = tables_bytes(p.G, p.R, p.C) + kFastWarps * fast_warp_scratch_bytes(h->fast_epw ? h->fast_epw : 32, p.R, p.G, p.D);
     cudaError_t e1 = cudaFuncSetAttribute(k_step_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);
     cudaError_t e2 = cudaFuncSetAttribute(k_reset_all, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {

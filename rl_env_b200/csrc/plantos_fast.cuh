@@ -5,22 +5,25 @@
 // default (G21 R2 C10, D=77; plantos_env.py:25-26) qualify; everything else runs
 // k_step_generic.
 //
-// Work split inside one warp, which owns a tile of EPW consecutive envs:
+// One warp owns a tile of EPW consecutive envs and goes through:
 //   phase A  one LANE per env   -- the scalar transition (plantos_env.py:160-222): record
 //            load, action, target-cell lookup, visit-nibble read-modify-write, watering,
 //            reward / done / record stores.  Outputs are coalesced across the tile.
+//   fetch    still one lane per env: as soon as a lane knows its env's new position it asks
+//            the TMA unit for the two pieces of state the observation needs -- 2R+2 rows of the
+//            wall-padded type plane (112 contiguous bytes for R=6, covering x-R .. x+R) and the five
+//            16-byte visit-nibble rows of the 5x5 window (80 contiguous bytes) -- with two
+//            cp.async.bulk global->shared copies that complete on the warp's mbarrier.  All
+//            2*EPW copies of the tile are in flight at once and cost no registers.
 //   phase B  one HALF-WARP per env, two envs per iteration -- the observation
-//            (plantos_env.py:251-315): 2R+1 lanes each fetch one 8-byte row of the wall-padded
-//            type plane and shift it into a rover-centred window word (no bounds checks
-//            anywhere); one lane per ray marches the integer offset table, with a warp
-//            shuffle as the row lookup; five lanes fetch the five 16-byte visit-nibble rows
-//            of the 5x5 window (80 contiguous bytes) and cut the 20-bit slice the window
-//            needs, which the 25 cell lanes read by shuffle.  Rows are assembled in a 4-env
+//            (plantos_env.py:251-315) from shared memory: 2R+1 lanes shift their type row into
+//            a rover-centred window word (the padding makes bounds checks unnecessary); one
+//            lane per ray marches the integer offset table with a warp shuffle as the row
+//            lookup; five lanes cut the 20-bit slice of their visit row that the window
+//            needs and the 25 cell lanes read it by shuffle.  Rows are assembled in a 4-env
 //            shared-memory tile whose 16*D bytes are 16-byte aligned in the [N, D] fp32
-//            buffer and leave with streaming 128-bit stores (st.global.cs.v4, evict-first)
-//            so that the write-once observation stream does not evict the env state from L2.
-//            The loop is unrolled by two with ping-pong prefetch registers: the loads of
-//            iteration i+1 are in flight during the arithmetic of iteration i.
+//            buffer and leave with streaming 128-bit stores (st.global.cs.v4, evict-first),
+//            so the write-once observation stream does not evict the env state from L2.
 //   phase C  whole warp, rare   -- SB3 auto-reset of finished envs (terminal observation,
 //            Philox / injected map, fresh observation) via the generic warp routines.
 // A ragged last tile (N % EPW != 0) is stepped env by env with step_env_warp.
@@ -31,38 +34,45 @@
 namespace plantos_dev {
 
 #ifndef PLANTOS_FAST_MINBLOCKS
-#define PLANTOS_FAST_MINBLOCKS 8
+#define PLANTOS_FAST_MINBLOCKS 4
 #endif
-constexpr int kFastWarps = 4;
+constexpr int kFastWarps = 7;        // 7 warps x 4 blocks = 28 resident warps per SM
+constexpr int kVisWinBytes = 5 * 16; // five nibble rows
+// rows per env fetched from the type plane: the 2R+1 window rows plus one, rounded up to even,
+// because the copy starts on an even row (16-byte aligned source and size)
+__host__ __device__ constexpr int type_win_rows(int R) { return (2 * R + 3) & ~1; }
 
-__host__ __device__ inline int fast_warp_scratch_bytes(int G, int D) {
-    return 2 * 16 * D + align_up(G * 8, 16);   // two 4-env obs tiles + type plane for phase C / tail
+// per-warp scratch: [type windows | visit windows | obs tile (4 envs)] + mbarrier.
+// Phase C / the ragged tail reuse the window area as the generic code's type plane.
+__host__ __device__ inline int fast_warp_scratch_bytes(int EPW, int R, int G, int D) {
+    int win = EPW * (type_win_rows(R) * 8 + kVisWinBytes);
+    if (win < align_up(G * 8, 16)) win = align_up(G * 8, 16);
+    return win + 16 * D + 16;
 }
 
-// ---- TMA (bulk async copy) helpers: shared -> global stores of finished observation tiles
+// ---- TMA (bulk async copy) + mbarrier helpers -------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
-__device__ __forceinline__ uint64_t policy_evict_first() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-// make this thread's shared-memory writes visible to the async proxy (the TMA unit)
-__device__ __forceinline__ void fence_smem_to_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes, uint64_t pol) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                 :: "l"(gdst), "r"(ssrc), "r"(bytes), "l"(pol) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
 }
-template <int N> __device__ __forceinline__ void bulk_wait_read() {     // <= N groups still reading smem
-    asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    return ok;
 }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-struct Prefetch {
-    uint64_t row;       // this lane's type row of the env's window
-    unsigned vlo, vhi;  // the two nibble words of this lane's visit row that hold the window
-    unsigned pw;        // x | y << 8 of the env
-};
+// order this thread's earlier global stores before its later async-proxy (TMA) reads
+__device__ __forceinline__ void fence_global_to_async() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void bulk_load(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(sdst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
+}
 
 template <int R, int C, int EPW, bool KEEP>
 __global__ void __launch_bounds__(kFastWarps * 32, PLANTOS_FAST_MINBLOCKS)
@@ -71,6 +81,8 @@ k_step_fast(const Params p, const StepIO io) {
     constexpr int NROW = 2 * R + 1;
     constexpr int VW = 4;                 // nibble words per visit row (G + 4 <= 32)
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int kTypeWinRows = type_win_rows(R);
+    constexpr int kTypeWinBytes = kTypeWinRows * 8;
     static_assert(NROW <= 16 && C <= 16, "fast kernel shape limits");
     static_assert(EPW % 4 == 0 && EPW <= 32, "tile must be whole 4-env groups");
 
@@ -81,14 +93,21 @@ k_step_fast(const Params p, const StepIO io) {
     const int G = p.G, VE = p.VE, TS = p.TS;
     const int e0 = (blockIdx.x * kFastWarps + warp) * EPW;
     if (e0 >= p.N) return;
-    unsigned char* scratch = smem + tables_bytes(G, R, C) + warp * fast_warp_scratch_bytes(G, D);
-    float* tile = reinterpret_cast<float*>(scratch);
-    uint64_t* plane = reinterpret_cast<uint64_t*>(scratch + 2 * 16 * D);
+    unsigned char* scratch = smem + tables_bytes(G, R, C) + warp * fast_warp_scratch_bytes(EPW, R, G, D);
+    constexpr int kWinBytes = EPW * (kTypeWinBytes + kVisWinBytes);
+    const int win_bytes = kWinBytes < align_up(G * 8, 16) ? align_up(G * 8, 16) : kWinBytes;
+    const uint64_t* twin = reinterpret_cast<const uint64_t*>(scratch);                        // [EPW][14]
+    const uint32_t* vwin = reinterpret_cast<const uint32_t*>(scratch + EPW * kTypeWinBytes);  // [EPW][5][4]
+    float* tile = reinterpret_cast<float*>(scratch + win_bytes);
+    uint64_t* plane = reinterpret_cast<uint64_t*>(scratch);     // generic-path scratch (phase C, tail)
+    const uint32_t mbar = smem_u32(scratch + win_bytes + 16 * D);
 
     if (p.N - e0 < EPW) {   // ragged last tile
         for (int e = e0; e < p.N; ++e) step_env_warp(p, t, io, e, plane, tile, lane);
         return;
     }
+    if (lane == 0) mbar_init(mbar, 1);
+    __syncwarp();
 
     // ---- phase A: transition, one lane per env
     const bool act = lane < EPW;
@@ -121,8 +140,22 @@ k_step_fast(const Params p, const StepIO io) {
         }
         posw = (unsigned)r.x | ((unsigned)r.y << 8);
     }
+
+    // ---- fetch: every lane asks the TMA unit for its env's two windows
+    if (lane == 0) mbar_arrive_expect_tx(mbar, EPW * (kTypeWinBytes + kVisWinBytes));
+    __syncwarp();
+    if (act) {
+        const int e = e0 + lane;
+        fence_global_to_async();     // the nibble / type words this lane just wrote
+        // padded type rows x .. x+2R hold grid rows x-R .. x+R; start on the even row below so
+        // that source and size are 16-byte multiples (the plane has one spare row for this)
+        const uint64_t* tsrc = p.types + (size_t)e * TS + (r.x & ~1);
+        bulk_load(smem_u32(twin + lane * kTypeWinRows), tsrc, kTypeWinBytes, mbar);
+        // padded nibble rows x .. x+4 hold grid rows x-2 .. x+2
+        const uint32_t* vsrc = p.vis4 + (size_t)e * VE + (size_t)r.x * VW;
+        bulk_load(smem_u32(vwin + lane * 5 * VW), vsrc, kVisWinBytes, mbar);
+    }
     accumulate_stats(p, act && done, r, term, trunc, lane);
-    __syncwarp();   // phase A's plane updates are visible to the other lanes' loads below
 
     // ---- phase B: observations, half-warp per env
     const int sub = lane & 15, half = lane >> 4, hbase = lane & 16;
@@ -134,47 +167,38 @@ k_step_fast(const Params p, const StepIO io) {
         srcl[rr] = hbase + dx + R;     // lane holding window row x+dx
         shf[rr] = 2 * (dy + R);        // bit offset of column y+dy inside the window word
     }
-    // lane-constant bases (byte pointers + unsigned 32-bit byte offsets keep the per-iteration
-    // address math short): padded type row (x - R + sub) + R = x + sub; visit-nibble row
-    // (x - 2 + sub) + 2 = x + sub for sub < 5, 16 bytes each
-    const char* trow = reinterpret_cast<const char*>(p.types + (size_t)e0 * TS + sub);
-    const char* vrow = reinterpret_cast<const char*>(p.vis4 + (size_t)e0 * VE + (size_t)sub * VW);
-    const unsigned TS8 = 8u * TS, VE4 = 4u * VE;
     const bool has_row = sub < NROW, has_ray = sub < C, has_vrow = sub < 5, has_v1 = sub < 9;
     // the two window cells this lane converts: q = sub and q = sub + 16 -> (row lane, nibble shift)
     const int vsrc0 = hbase + sub / 5, vsh0 = 4 * (sub % 5);
     const int vsrc1 = hbase + (sub + 16) / 5, vsh1 = 4 * ((sub + 16) % 5);
-    // observation tiles: group g (4 envs) is assembled in buffer g & 1; env 2*it + half of an
-    // even iteration goes to row `half`, of an odd iteration to row 2 + half
     const float4* onehot = reinterpret_cast<const float4*>(t.onehot);
     constexpr uint64_t LOWPAD = kObstAll & ((1ull << (2 * R)) - 1ull);
 
-    auto issue = [&](int it, Prefetch& n) {
-        const int j = 2 * it + half;
-        n.pw = __shfl_sync(FULL, posw, j);
-        const unsigned x = n.pw & 0xff, y = n.pw >> 8;
-        n.row = kObstAll;
-        if (has_row && !(p.dbg & 4))
-            n.row = mem.ld64(reinterpret_cast<const uint64_t*>(trow + ((unsigned)j * TS8 + 8u * x)));
-        n.vlo = 0; n.vhi = 0;
-        if (has_vrow && !(p.dbg & 2)) {
-            // window nibbles y .. y+4 of this row start in word y>>3 and may spill into the next
-            const unsigned w0 = y >> 3, w1 = w0 < 3u ? w0 + 1u : 3u;
-            const char* base = vrow + ((unsigned)j * VE4 + 16u * x);
-            n.vlo = mem.ld32(reinterpret_cast<const uint32_t*>(base + 4u * w0));
-            n.vhi = mem.ld32(reinterpret_cast<const uint32_t*>(base + 4u * w1));
+    // wait for the windows (bounded spin: a lost completion must trap, not hang the GPU)
+    {
+        uint32_t spins = 0;
+        while (!mbar_try_wait(mbar, 0)) {
+            if (++spins > (1u << 24)) __trap();
         }
-    };
+    }
 
-    auto compute = [&](const Prefetch& c, float* row) {
-        const int x = c.pw & 0xff, y = c.pw >> 8;
+    auto compute = [&](int j, float* row) {
+        const unsigned pw = __shfl_sync(FULL, posw, j);
+        const int x = pw & 0xff, y = pw >> 8;
         // rover-centred window word: cells y-R .. y+R of this lane's row, walls outside
+        uint64_t trow = kObstAll;
+        if (has_row) trow = twin[j * kTypeWinRows + (x & 1) + sub];
         const int s = 2 * y;
-        const uint64_t ext = (c.row << (2 * R)) | LOWPAD;
+        const uint64_t ext = (trow << (2 * R)) | LOWPAD;
         const unsigned w = (unsigned)((ext >> s) | ((kObstAll << 1) << (63 - s)));
-        // this lane's visit row: the 5 nibbles y .. y+4 (20 bits; when they sit entirely in
-        // word 3 the funnel's high half is unused)
-        const unsigned vslice = __funnelshift_r(c.vlo, c.vhi, 4 * (y & 7));
+        // this lane's visit row: the 5 nibbles y .. y+4 start in word y>>3 and may spill into
+        // the next one (when they sit entirely in word 3 the funnel's high half is unused)
+        unsigned vslice = 0;
+        if (has_vrow) {
+            const unsigned w0 = y >> 3, w1 = w0 < 3u ? w0 + 1u : 3u;
+            const uint32_t* vr = vwin + (j * 5 + sub) * VW;
+            vslice = __funnelshift_r(vr[w0], vr[w1], 4 * (y & 7));
+        }
         // LIDAR march (plantos_env.py:260-284): sample rr looks at window row srcl[rr], bits shf[rr]
         unsigned acc = 0;
 #pragma unroll
@@ -200,37 +224,23 @@ k_step_fast(const Params p, const StepIO io) {
     };
 
     float4* const obs4 = reinterpret_cast<float4*>(io.obs) + (size_t)(e0 >> 2) * D;
-    const uint64_t pol_stream = policy_evict_first();
-    const uint32_t tile_s = smem_u32(tile);
-    // A finished group leaves through the TMA unit: one bulk shared->global copy of 16*D bytes
-    // (16-byte aligned because e0 and the group start are multiples of 4), tagged evict-first.
-    // The copy is asynchronous; the buffer is reused two groups later, after wait_group.read.
-    auto flush = [&](int group) {
-        fence_smem_to_async();
-        __syncwarp();
-        if (lane == 0 && !(p.dbg & 1))
-            bulk_store(obs4 + (size_t)group * D, tile_s + (group & 1) * 16 * D, 16 * D, pol_stream);
-    };
-
-    constexpr int NIT = EPW / 2;
-    Prefetch pa, pb;
-    issue(0, pa);
+    const float4* src4 = reinterpret_cast<const float4*>(tile);
+    float* const rowA = tile + half * D;          // env 4g + half
+    float* const rowB = tile + (2 + half) * D;    // env 4g + 2 + half
 #pragma unroll 1
-    for (int it = 0; it < NIT; it += 2) {
-        const int group = it >> 1;
-        float* const tb = tile + (group & 1) * 4 * D;
-        issue(it + 1, pb);
-        if (group >= 2) {                 // buffer last used by group - 2: its bulk read must be done
-            if (lane == 0) bulk_wait_read<1>();
-            __syncwarp();
+    for (int g = 0; g < EPW / 4; ++g) {
+        compute(4 * g + half, rowA);
+        compute(4 * g + 2 + half, rowB);
+        // flush four env rows = D float4, 16-byte aligned because e0 and 4g are multiples of 4
+        __syncwarp();
+        float4* dst4 = obs4 + (size_t)g * D;
+#pragma unroll
+        for (int k = 0; k < (D + 31) / 32; ++k) {
+            const int idx = k * 32 + lane;
+            if (idx < D && !(p.dbg & 1)) __stcs(dst4 + idx, src4[idx]);
         }
-        compute(pa, tb + half * D);
-        if (it + 2 < NIT) issue(it + 2, pa);
-        compute(pb, tb + (2 + half) * D);
-        flush(group);
+        __syncwarp();
     }
-    if (lane == 0) bulk_wait_all();       // stores complete before phase C may overwrite rows / exit
-    __syncwarp();
 
     // ---- phase C: auto-reset of finished envs (rare; warp-cooperative generic code)
     unsigned dmask = __ballot_sync(FULL, act && done);
