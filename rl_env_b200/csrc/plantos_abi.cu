@@ -201,11 +201,13 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     p.G = cfg->grid_size; p.P = cfg->num_plants; p.O = cfg->num_obstacles;
     p.R = cfg->lidar_range; p.C = cfg->lidar_channels; p.D = plantos_obs_dim(cfg);
     p.W = (p.G + 31) / 32;
-    // wall-padded type plane, u64 words per env: R wall rows above and below the grid plus one
-    // spare row (the fast kernel's 16-byte aligned row fetch may start one row early), even count
-    p.TS = ((p.G + 2 * p.R + 2) & ~1) * p.W;
+    // wall-padded type plane, u64 words per env: R+2 wall rows above the grid and R+2 (or one
+    // more, to make the row count even = 16-byte env stride) below: the fast kernel fetches
+    // rows x-R-1 .. x+R+1 (+1 for alignment) around any rover row x without bounds checks
+    p.TP = p.R + 2;
+    p.TS = ((p.TP + p.G + p.R + 2 + 1) & ~1) * p.W;
     p.VW = ((p.G + 4 + 7) / 8 + 3) / 4 * 4;              // u32 words per visit-nibble row (16-byte rows)
-    p.VE = (p.G + 4) * p.VW;                            // u32 words per env, bordered nibble plane
+    p.VE = (p.G + 2 * kVisRowPad) * p.VW;                // u32 words per env, bordered nibble plane
     p.max_steps = cfg->max_steps; p.nclusters = cfg->num_obstacles / 3;
     {
         double th = std::floor((double)cfg->thirsty_plant_prob * 4294967296.0);
@@ -269,7 +271,9 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     const bool fast_ok = (p.W == 1) && (p.VW == 4) && (p.G + p.R <= 32) && (2 * p.R + 1 <= 16) && (p.C <= 16);
     h->use_fast = false;
     if (cfg->kernel != PLANTOS_KERNEL_GENERIC && fast_ok) {
-        int epw = 32;
+        // envs per warp tile: 16 gives two waves of warps at the benchmark size, so the fetch of
+        // one wave overlaps the arithmetic of the other; smaller tiles for small N
+        int epw = 16;
         const long long fill = (long long)h->num_sms * 16;   // warps wanted in flight
         while (epw > 4 && (long long)(p.N + epw - 1) / epw < fill) epw >>= 1;
         if (const char* s = std::getenv("PLANTOS_EPW")) {
@@ -283,8 +287,10 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
         p.l2_keep = keep;
         if (keep) {
             // evict_last lines only persist inside the persisting-L2 set-aside, which is 0 by
-            // default: claim the device maximum (82.9 MB of the 132.6 MB L2 on B200)
-            size_t want = (size_t)prop.persistingL2CacheMaxSize;
+            // default.  Measured on B200 (132.6 MB L2, max set-aside 82.9 MB): up to 56 MB helps
+            // slightly, 64 MB and more slows the step down by 40 %, so stay at 56 MB.
+            size_t want = (size_t)56 << 20;
+            if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
             if (const char* s = std::getenv("PLANTOS_L2_PERSIST_MB")) want = (size_t)std::atoi(s) << 20;
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
         }

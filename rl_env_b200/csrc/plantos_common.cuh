@@ -3,18 +3,20 @@
 //
 // Persistent state in HBM, per env (SoA across envs, all little-endian):
 //   rec     32 B   hot scalars, two uint4 (see EnvRec)
-//   types   (G+2R)*W*8  2-bit cell codes (0 empty 1 obstacle 2 hydrated 3 thirsty), row-major,
+//   types   TS*8   2-bit cell codes (0 empty 1 obstacle 2 hydrated 3 thirsty), row-major,
 //                  W = ceil(G/32) u64 words per row, cell y of row x at bits [2*(y&31), +2)
-//                  of word (x+R)*W + (y>>5).  The plane is WALL-PADDED so that the LIDAR never
-//                  needs a bounds check: R all-obstacle rows above and below the grid, and the
-//                  columns >= G of the last word of every row hold the obstacle code (01).
-//   vis4    (G+4)*VW*4  visit_counts (plantos_env.py:146) as saturating 4-BIT counters, 8 per
+//                  of word (x+TP)*W + (y>>5).  The plane is WALL-PADDED so that neither the
+//                  LIDAR nor a move needs a bounds check: TP = R+2 all-obstacle rows above the
+//                  grid, at least R+2 below, and the columns >= G of the last word of every row
+//                  hold the obstacle code (01).
+//   vis4    VE*4   visit_counts (plantos_env.py:146) as saturating 4-BIT counters, 8 per
 //                  u32 word, rows of VW words (a multiple of 4, i.e. 16-byte rows), with a
-//                  2-cell border on every side: cell (x,y) is nibble (y+2) of row (x+2).
-//                  Border nibbles hold 15.  The observation only needs min(v,10)/10
-//                  (plantos_env.py:308) and 15 maps to the 1.0 the reference writes for
-//                  out-of-bounds window cells (:310-311), so the 5x5 window is FIVE CONSECUTIVE
-//                  16-byte rows (80 contiguous bytes when G <= 28) read without bounds checks.
+//                  border of 3 rows above/below and 2 columns left/right: cell (x,y) is nibble
+//                  (y+2) of row (x+3).  Border nibbles hold 15.  The observation only needs
+//                  min(v,10)/10 (plantos_env.py:308) and 15 maps to the 1.0 the reference
+//                  writes for out-of-bounds window cells (:310-311), so the 5x5 window is FIVE
+//                  CONSECUTIVE 16-byte rows (when G <= 28) read without bounds checks, and the
+//                  7 rows around the pre-move position are one contiguous 112-byte fetch.
 //   visov   G*G*2  exact u16 count of the cells whose nibble has saturated (v >= 15); never
 //                  read or written for the others, so it stays out of cache and DRAM traffic.
 //                  visit_counts[x,y] = nibble < 15 ? nibble : visov[x*G+y]  (exact up to 65535).
@@ -36,9 +38,10 @@ struct Params {
     long long env_base;
     int G, P, O, R, C, D;
     int W;          // u64 words per type row
-    int TS;         // u64 words per env in the type plane: (G + 2R) * W
+    int TP;         // wall rows above the grid in the type plane (R + 2)
+    int TS;         // u64 words per env in the type plane: (TP + G + R + 2, even) * W
     int VW;         // u32 words per nibble row (multiple of 4)
-    int VE;         // u32 words per env in the nibble plane: (G + 4) * VW
+    int VE;         // u32 words per env in the nibble plane: (G + 2 * kVisRowPad) * VW
     int max_steps;
     int nclusters;  // O / 3 (plantos_env.py:341)
     unsigned long long thirsty_thresh;  // floor(prob * 2^32); draw < thresh => thirsty
@@ -119,7 +122,8 @@ __device__ __forceinline__ void pack_rec(const EnvRec& r, uint4& a, uint4& b) {
 __device__ __forceinline__ int cell_of(uint64_t word, int ylow) { return (int)((word >> (2 * ylow)) & 3ull); }
 
 // nibble plane addressing of grid cell (x, y): u32 word index inside the env, and bit shift
-__device__ __forceinline__ int nib_word(int x, int y, int VW) { return (x + 2) * VW + ((y + 2) >> 3); }
+constexpr int kVisRowPad = 3;   // border rows above / below the grid in the nibble plane
+__device__ __forceinline__ int nib_word(int x, int y, int VW) { return (x + kVisRowPad) * VW + ((y + 2) >> 3); }
 __device__ __forceinline__ int nib_shift(int y) { return 4 * ((y + 2) & 7); }
 
 // valid-column mask (bit0 of each cell) for word w of a row
@@ -279,6 +283,7 @@ struct StepOut {
     int terminated;  // exploration >= 100 % (plantos_env.py:176,244-246)
     int truncated;   // step_count >= max_steps (:177)
     int watered;     // a thirsty plant was hydrated this step
+    int moved;       // the rover entered (tx, ty): its visit count goes up by one
 };
 
 __device__ __forceinline__ void action_target(const EnvRec& r, long long action, int G, int& tx, int& ty, bool& inb) {
@@ -294,29 +299,20 @@ __device__ __forceinline__ void action_target(const EnvRec& r, long long action,
     }
 }
 
-template <class Mem>
-__device__ __forceinline__ StepOut apply_action(EnvRec& r, long long action, int tx, int ty, bool inb,
-                                                uint64_t row_word, uint64_t* word_ptr,
-                                                uint32_t* vis_e, uint16_t* visov_e, int G, int VW,
-                                                int max_steps, const Mem& mem) {
+// The decision part, free of memory accesses: `t` is the code of the cell the action looks at
+// (kObstacle when the move leaves the grid), `nib` the visit nibble of that cell (only
+// meaningful for a valid move).  Sets o.moved / o.watered; the caller applies the two possible
+// state writes (visit count +1 at (tx,ty); cell (tx,ty) thirsty -> hydrated).
+__device__ __forceinline__ StepOut transition_core(EnvRec& r, long long action, int tx, int ty, int t,
+                                                   unsigned nib, int max_steps) {
     StepOut o;
     o.watered = 0;
+    o.moved = 0;
     r.step += 1;                                           // :162
-    const int t = inb ? cell_of(row_word, ty & 31) : kObstacle;
     if (action < 4) {
         if (t != kObstacle) {                              // :193-195 (plants are walkable)
-            uint32_t* vp = vis_e + nib_word(tx, ty, VW);
-            const int sh = nib_shift(ty);
-            const uint32_t w = mem.ld32(vp);
-            const unsigned nib = (w >> sh) & 15u;
             const bool fresh = (nib == 0);                 // :197
-            if (nib < 15u) {                               // :203, count still lives in the nibble
-                mem.st32(vp, w + (1u << sh));
-                if (nib == 14u) visov_e[tx * G + ty] = 15;
-            } else {                                       // saturated: exact count in visov
-                const unsigned v = visov_e[tx * G + ty];
-                if (v < 65535u) visov_e[tx * G + ty] = (uint16_t)(v + 1u);
-            }
+            o.moved = 1;                                   // :203 visit_counts[new] += 1
             r.x = tx; r.y = ty;                            // :199
             r.explored += fresh;                           // explored_map>0 count, :198-200,320
             o.ridx = fresh ? 0 : 1;                        // R_EXPLORATION / R_REVISIT
@@ -327,7 +323,6 @@ __device__ __forceinline__ StepOut apply_action(EnvRec& r, long long action, int
         }
     } else {
         if (t == kThirsty) {                               // :217-219
-            mem.st64(word_ptr, row_word ^ (1ull << (2 * (ty & 31))));  // 3 -> 2
             r.thirsty -= 1;
             r.watered += 1;
             o.watered = 1;
@@ -344,6 +339,39 @@ __device__ __forceinline__ StepOut apply_action(EnvRec& r, long long action, int
         o.ridx += kRwCount;
         r.flags |= kFlagBonus;
     }
+    return o;
+}
+
+// visit count of cell (tx,ty) += 1 given its nibble word `w` (already loaded): the count lives in
+// the nibble until it saturates at 15, from then on in the u16 overflow plane.  Returns the new word.
+template <class Mem>
+__device__ __forceinline__ uint32_t bump_visit(uint32_t* vp, uint32_t w, int sh, uint16_t* ov, const Mem& mem) {
+    const unsigned nib = (w >> sh) & 15u;
+    if (nib < 15u) {
+        w += 1u << sh;
+        mem.st32(vp, w);
+        if (nib == 14u) *ov = 15;
+    } else {
+        const unsigned v = *ov;
+        if (v < 65535u) *ov = (uint16_t)(v + 1u);
+    }
+    return w;
+}
+
+// Transition against the planes in global memory (generic kernel).
+template <class Mem>
+__device__ __forceinline__ StepOut apply_action(EnvRec& r, long long action, int tx, int ty, bool inb,
+                                                uint64_t row_word, uint64_t* word_ptr,
+                                                uint32_t* vis_e, uint16_t* visov_e, int G, int VW,
+                                                int max_steps, const Mem& mem) {
+    const int t = inb ? cell_of(row_word, ty & 31) : kObstacle;
+    uint32_t* vp = vis_e + nib_word(tx, ty, VW);
+    const int sh = nib_shift(ty);
+    uint32_t w = 0;
+    if (action < 4 && t != kObstacle) w = mem.ld32(vp);
+    const StepOut o = transition_core(r, action, tx, ty, t, (w >> sh) & 15u, max_steps);
+    if (o.moved) bump_visit(vp, w, sh, visov_e + tx * G + ty, mem);
+    if (o.watered) mem.st64(word_ptr, row_word ^ (1ull << (2 * (ty & 31))));  // 3 -> 2
     return o;
 }
 

@@ -144,7 +144,7 @@ __device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int epi
     }
     // counts + write-out of the G grid rows (the wall rows above/below were set at create)
     int n_obst = 0, n_thirsty = 0;
-    uint64_t* types_e = p.types + (size_t)e * p.TS + (size_t)p.R * W;
+    uint64_t* types_e = p.types + (size_t)e * p.TS + (size_t)p.TP * W;
     for (int idx = lane; idx < nwords; idx += 32) {
         const uint64_t word = plane[idx];
         const uint64_t m = col_mask(G, idx % W);
@@ -158,7 +158,7 @@ __device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int epi
     uint32_t* vis_e = p.vis4 + (size_t)e * p.VE;
     const int VW = p.VW;
     for (int wi = lane; wi < p.VE; wi += 32) {
-        const int vx = wi / VW - 2, c0 = (wi % VW) * 8 - 2;
+        const int vx = wi / VW - kVisRowPad, c0 = (wi % VW) * 8 - 2;
         uint32_t word = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -210,7 +210,7 @@ __device__ __forceinline__ void step_env_warp(const Params& p, const Tables& t, 
     }
     const unsigned posw = __shfl_sync(0xffffffffu, ra.x, 0);
     int x = posw & 0xff, y = (posw >> 8) & 0xff;
-    uint64_t* types_e = p.types + (size_t)e * p.TS + (size_t)p.R * p.W;   // grid row 0
+    uint64_t* types_e = p.types + (size_t)e * p.TS + (size_t)p.TP * p.W;   // grid row 0
     uint32_t* vis_e = p.vis4 + (size_t)e * p.VE;
     uint16_t* visov_e = p.visov + (size_t)e * p.G * p.G;
 
@@ -319,7 +319,7 @@ __global__ void k_get_state(const Params p, uint8_t* cells, int32_t* visits) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int e = (int)(i / gg), c = (int)(i - (size_t)e * gg);
         const int x = c / p.G, y = c - x * p.G;
-        if (cells) cells[i] = (uint8_t)cell_of(p.types[(size_t)e * p.TS + (size_t)(x + p.R) * p.W + (y >> 5)], y & 31);
+        if (cells) cells[i] = (uint8_t)cell_of(p.types[(size_t)e * p.TS + (size_t)(x + p.TP) * p.W + (y >> 5)], y & 31);
         if (visits) {
             const unsigned nib = (p.vis4[(size_t)e * p.VE + nib_word(x, y, p.VW)] >> nib_shift(y)) & 15u;
             visits[i] = nib < 15u ? (int32_t)nib : (int32_t)p.visov[(size_t)e * gg + c];
@@ -335,7 +335,7 @@ __global__ void k_set_state(const Params p, const uint8_t* cells, const int32_t*
     const int G = p.G, W = p.W, nwords = G * W, gg = G * G;
     uint4 ra = p.rec[2 * (size_t)e], rb = p.rec[2 * (size_t)e + 1];
     EnvRec r = unpack_rec(ra, rb);
-    uint64_t* types_e = p.types + (size_t)e * p.TS + (size_t)p.R * W;
+    uint64_t* types_e = p.types + (size_t)e * p.TS + (size_t)p.TP * W;
     if (cells) {
         int n_obst = 0, n_thirsty = 0;
         for (int idx = lane; idx < nwords; idx += 32) {
@@ -359,7 +359,7 @@ __global__ void k_set_state(const Params p, const uint8_t* cells, const int32_t*
         uint16_t* visov_e = p.visov + (size_t)e * gg;
         const int VW = p.VW;
         for (int wi = lane; wi < p.VE; wi += 32) {     // one lane owns a whole nibble word
-            const int vx = wi / VW - 2, c0 = (wi % VW) * 8 - 2;
+            const int vx = wi / VW - kVisRowPad, c0 = (wi % VW) * 8 - 2;
             uint32_t word = 0;
             for (int k = 0; k < 8; ++k) {
                 const int vy = c0 + k;
