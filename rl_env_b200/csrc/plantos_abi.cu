@@ -31,12 +31,9 @@ int fail(int code, const std::string& msg) {
 
 typedef void (*fast_kernel_t)(const Params, const StepIO);
 
-struct FastVariant { int R, C, EPW, keep; fast_kernel_t fn; };
+struct FastVariant { int R, C, keep; fast_kernel_t fn; };
 
-#define FAST_ROW1(R_, C_, K_)                                                              \
-    {R_, C_, 4, K_, k_step_fast<R_, C_, 4, K_>}, {R_, C_, 8, K_, k_step_fast<R_, C_, 8, K_>},   \
-    {R_, C_, 16, K_, k_step_fast<R_, C_, 16, K_>}, {R_, C_, 32, K_, k_step_fast<R_, C_, 32, K_>}
-#define FAST_ROW(R_, C_) FAST_ROW1(R_, C_, 0), FAST_ROW1(R_, C_, 1)
+#define FAST_ROW(R_, C_) {R_, C_, 0, k_step_fast<R_, C_, false>}, {R_, C_, 1, k_step_fast<R_, C_, true>}
 
 const FastVariant kFastVariants[] = {
     FAST_ROW(6, 16),  // training preset, A2C_training.py:206-212
@@ -64,7 +61,7 @@ struct plantos {
     // launch configuration
     bool use_fast;
     fast_kernel_t fast_fn;
-    int fast_epw;
+    int fast_grid;
     int generic_grid, generic_smem;
     int fast_smem;
     bool did_reset;
@@ -271,15 +268,6 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     const bool fast_ok = (p.W == 1) && (p.VW == 4) && (p.G + p.R <= 32) && (2 * p.R + 1 <= 16) && (p.C <= 16);
     h->use_fast = false;
     if (cfg->kernel != PLANTOS_KERNEL_GENERIC && fast_ok) {
-        // envs per warp tile: 16 gives two waves of warps at the benchmark size, so the fetch of
-        // one wave overlaps the arithmetic of the other; smaller tiles for small N
-        int epw = 16;
-        const long long fill = (long long)h->num_sms * 16;   // warps wanted in flight
-        while (epw > 4 && (long long)(p.N + epw - 1) / epw < fill) epw >>= 1;
-        if (const char* s = std::getenv("PLANTOS_EPW")) {
-            const int v = std::atoi(s);
-            if (v == 4 || v == 8 || v == 16 || v == 32) epw = v;
-        }
         // L2 policy: keep the env state resident (evict_last) when its per-step working set
         // (~5 lines of 128 B per env) can fit next to the streaming outputs
         int keep = ((double)p.N * 5 * 128 < 0.8 * (double)prop.l2CacheSize) ? 1 : 0;
@@ -295,14 +283,22 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
         }
         for (const FastVariant& v : kFastVariants)
-            if (v.R == p.R && v.C == p.C && v.EPW == epw && v.keep == keep) { h->use_fast = true; h->fast_fn = v.fn; h->fast_epw = epw; }
+            if (v.R == p.R && v.C == p.C && v.keep == keep) { h->use_fast = true; h->fast_fn = v.fn; }
     }
     if (cfg->kernel == PLANTOS_KERNEL_FAST && !h->use_fast) {
         free_all(h);
         return fail(PLANTOS_EINVAL, "PLANTOS_KERNEL_FAST requested but (G, R, C) has no fast-kernel instantiation");
     }
     h->generic_smem = tables_bytes(p.G, p.R, p.C) + kGenericWarps * generic_warp_scratch_bytes(p.G, p.W, p.D);
-    h->fast_smem = tables_bytes(p.G, p.R, p.C) + kFastWarps * fast_warp_scratch_bytes(h->fast_epw ? h->fast_epw : 32, p.R, p.G, p.D);
+    h->fast_smem = fast_smem_bytes(p.G, p.R, p.C, p.D);
+    {
+        // persistent grid: PLANTOS_FAST_BLOCKS_PER_SM blocks per SM, each walking its stages of 32 envs
+        long long blocks = (long long)h->num_sms * PLANTOS_FAST_BLOCKS_PER_SM;
+        if (const char* s = std::getenv("PLANTOS_FAST_GRID")) { const int v = std::atoi(s); if (v > 0) blocks = v; }
+        const long long nstages = p.N / kStageEnvs;
+        if (blocks > nstages) blocks = nstages;
+        h->fast_grid = (int)(blocks < 1 ? 1 : blocks);
+    }
     cudaError_t e1 = cudaFuncSetAttribute(k_step_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);
     cudaError_t e2 = cudaFuncSetAttribute(k_reset_all, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
@@ -392,9 +388,7 @@ extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, fl
     CUDA_TRY(cudaSetDevice(h->device));
     const bool aligned = (((uintptr_t)obs) & 15u) == 0;
     if (h->use_fast && aligned) {
-        const int per_block = kFastWarps * h->fast_epw;
-        const int grid = (h->p.N + per_block - 1) / per_block;
-        h->fast_fn<<<grid, kFastWarps * 32, h->fast_smem, (cudaStream_t)stream>>>(h->p, io);
+        h->fast_fn<<<h->fast_grid, kFastThreads, h->fast_smem, (cudaStream_t)stream>>>(h->p, io);
     } else {
         if (h->cfg.kernel == PLANTOS_KERNEL_FAST)
             return fail(PLANTOS_EINVAL, "PLANTOS_KERNEL_FAST needs a 16-byte aligned obs buffer");

@@ -15,10 +15,10 @@ pytestmark = pytest.mark.gpu
 FAST_FIXTURES = ["replay_T_8env", "replay_DFLT_1env"]
 
 
-def _run(name, kernel, **kw):
+def _run(name, kernel, replicas=1, **kw):
     from gpu_backend import GpuBackend
     fx = load_fixture(name)
-    be = GpuBackend(fx, kernel=kernel)
+    be = GpuBackend(fx, kernel=kernel, replicas=replicas)
     try:
         assert be.env.kernel_name == kernel
         res = check_replay(fx, be, **kw)
@@ -36,15 +36,25 @@ def test_generic_kernel_replays_reference(name):
 
 @pytest.mark.parametrize("name", FAST_FIXTURES)
 def test_fast_kernel_replays_reference(name):
+    # fewer than 32 envs: the fast kernel's ragged-tail path
     res = _run(name, "fast")
     assert res["bitexact_obs"] == 1 and res["bitexact_reward"] == 1
 
 
-@pytest.mark.parametrize("epw", [8, 16, 32])
-def test_fast_kernel_tile_sizes(epw, monkeypatch):
-    """Every envs-per-warp tiling of the fast kernel, on a partially filled tile."""
-    monkeypatch.setenv("PLANTOS_EPW", str(epw))
-    res = _run("replay_T_8env", "fast", steps=1100)
+@pytest.mark.parametrize("name,replicas", [("replay_T_8env", 13), ("replay_DFLT_1env", 70)])
+def test_fast_kernel_pipeline_replays_reference(name, replicas):
+    """The producer/consumer pipeline proper: the fixture's envs replicated to fill several
+    32-env stages (104 = 3 stages + 8 tail envs; 70 = 2 stages + 6), every copy checked."""
+    res = _run(name, "fast", replicas=replicas)
+    assert res["bitexact_obs"] == 1 and res["bitexact_reward"] == 1
+
+
+@pytest.mark.parametrize("grid", [1, 2, 5])
+def test_fast_kernel_ring_reuse(grid, monkeypatch):
+    """Few persistent blocks => each walks many stages, so the shared-memory ring wraps and the
+    full/empty mbarrier phases flip several times (24 copies x 8 envs = 6 stages)."""
+    monkeypatch.setenv("PLANTOS_FAST_GRID", str(grid))
+    res = _run("replay_T_8env", "fast", replicas=24, steps=1100)
     assert res["bitexact_obs"] == 1
 
 
