@@ -44,7 +44,7 @@ enum { PLANTOS_MAPS_PHILOX = 0, PLANTOS_MAPS_INJECTED = 1 };
 enum {
     PLANTOS_KERNEL_AUTO = 0,     /* fast kernel when the preset qualifies, else generic */
     PLANTOS_KERNEL_GENERIC = 1,  /* one warp per env, any supported config */
-    PLANTOS_KERNEL_FAST = 2      /* sub-warp per env; G<=32, R<=7, C<=16 (presets T, DFLT) */
+    PLANTOS_KERNEL_FAST = 2      /* persistent pipelined kernel; G<=28, G+R<=32, R<=7, C<=16 and an instantiated (R,C): presets T, DFLT */
 };
 
 /* indices into the reward table (plantos_upload_tables / plantos_compute_tables):

@@ -31,9 +31,12 @@ int fail(int code, const std::string& msg) {
 
 typedef void (*fast_kernel_t)(const Params, const StepIO);
 
-struct FastVariant { int R, C, keep; fast_kernel_t fn; };
+struct FastVariant { int R, C, EPW, keep; fast_kernel_t fn; };
 
-#define FAST_ROW(R_, C_) {R_, C_, 0, k_step_fast<R_, C_, false>}, {R_, C_, 1, k_step_fast<R_, C_, true>}
+#define FAST_ROW1(R_, C_, K_)                                                              \
+    {R_, C_, 4, K_, k_step_fast<R_, C_, 4, K_>}, {R_, C_, 8, K_, k_step_fast<R_, C_, 8, K_>},   \
+    {R_, C_, 16, K_, k_step_fast<R_, C_, 16, K_>}
+#define FAST_ROW(R_, C_) FAST_ROW1(R_, C_, 0), FAST_ROW1(R_, C_, 1)
 
 const FastVariant kFastVariants[] = {
     FAST_ROW(6, 16),  // training preset, A2C_training.py:206-212
@@ -61,7 +64,7 @@ struct plantos {
     // launch configuration
     bool use_fast;
     fast_kernel_t fast_fn;
-    int fast_grid;
+    int fast_epw, fast_grid;
     int generic_grid, generic_smem;
     int fast_smem;
     bool did_reset;
@@ -214,8 +217,6 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     }
     p.seed_lo = (uint32_t)(cfg->seed & 0xffffffffull); p.seed_hi = (uint32_t)(cfg->seed >> 32);
     p.map_source = cfg->map_source; p.map_episodes = 0;
-    p.dbg = 0;
-    if (const char* s = std::getenv("PLANTOS_DEBUG_SKIP")) p.dbg = std::atoi(s);
 
     const size_t N = (size_t)p.N;
 #define ALLOC(ptr, bytes)                                                       \
@@ -268,6 +269,15 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     const bool fast_ok = (p.W == 1) && (p.VW == 4) && (p.G + p.R <= 32) && (2 * p.R + 1 <= 16) && (p.C <= 16);
     h->use_fast = false;
     if (cfg->kernel != PLANTOS_KERNEL_GENERIC && fast_ok) {
+        // envs per warp tile: 8 gives every resident warp (28 per SM) about four tiles to
+        // pipeline at the benchmark size; 4 when there are too few envs to occupy the warps
+        int epw = 8;
+        const long long resident = (long long)h->num_sms * PLANTOS_FAST_MINBLOCKS * kFastWarps;
+        if ((long long)p.N / epw < 2 * resident) epw = 4;
+        if (const char* s = std::getenv("PLANTOS_EPW")) {
+            const int v = std::atoi(s);
+            if (v == 4 || v == 8 || v == 16) epw = v;
+        }
         // L2 policy: keep the env state resident (evict_last) when its per-step working set
         // (~5 lines of 128 B per env) can fit next to the streaming outputs
         int keep = ((double)p.N * 5 * 128 < 0.8 * (double)prop.l2CacheSize) ? 1 : 0;
@@ -283,20 +293,20 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
         }
         for (const FastVariant& v : kFastVariants)
-            if (v.R == p.R && v.C == p.C && v.keep == keep) { h->use_fast = true; h->fast_fn = v.fn; }
+            if (v.R == p.R && v.C == p.C && v.EPW == epw && v.keep == keep) { h->use_fast = true; h->fast_fn = v.fn; h->fast_epw = epw; }
     }
     if (cfg->kernel == PLANTOS_KERNEL_FAST && !h->use_fast) {
         free_all(h);
         return fail(PLANTOS_EINVAL, "PLANTOS_KERNEL_FAST requested but (G, R, C) has no fast-kernel instantiation");
     }
     h->generic_smem = tables_bytes(p.G, p.R, p.C) + kGenericWarps * generic_warp_scratch_bytes(p.G, p.W, p.D);
-    h->fast_smem = fast_smem_bytes(p.G, p.R, p.C, p.D);
-    {
-        // persistent grid: PLANTOS_FAST_BLOCKS_PER_SM blocks per SM, each walking its stages of 32 envs
-        long long blocks = (long long)h->num_sms * PLANTOS_FAST_BLOCKS_PER_SM;
+    h->fast_smem = tables_bytes(p.G, p.R, p.C) + kFastWarps * fast_warp_scratch_bytes(h->fast_epw ? h->fast_epw : 8, p.R, p.G, p.D);
+    if (h->use_fast) {
+        // persistent grid: at most PLANTOS_FAST_MINBLOCKS blocks per SM, each warp walks its tiles
+        long long blocks = (long long)h->num_sms * PLANTOS_FAST_MINBLOCKS;
         if (const char* s = std::getenv("PLANTOS_FAST_GRID")) { const int v = std::atoi(s); if (v > 0) blocks = v; }
-        const long long nstages = p.N / kStageEnvs;
-        if (blocks > nstages) blocks = nstages;
+        const long long need = ((long long)p.N / h->fast_epw + kFastWarps - 1) / kFastWarps;
+        if (blocks > need) blocks = need;
         h->fast_grid = (int)(blocks < 1 ? 1 : blocks);
     }
     cudaError_t e1 = cudaFuncSetAttribute(k_step_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);
@@ -388,7 +398,7 @@ extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, fl
     CUDA_TRY(cudaSetDevice(h->device));
     const bool aligned = (((uintptr_t)obs) & 15u) == 0;
     if (h->use_fast && aligned) {
-        h->fast_fn<<<h->fast_grid, kFastThreads, h->fast_smem, (cudaStream_t)stream>>>(h->p, io);
+        h->fast_fn<<<h->fast_grid, kFastWarps * 32, h->fast_smem, (cudaStream_t)stream>>>(h->p, io);
     } else {
         if (h->cfg.kernel == PLANTOS_KERNEL_FAST)
             return fail(PLANTOS_EINVAL, "PLANTOS_KERNEL_FAST needs a 16-byte aligned obs buffer");

@@ -46,7 +46,6 @@ struct Params {
     int nclusters;  // O / 3 (plantos_env.py:341)
     unsigned long long thirsty_thresh;  // floor(prob * 2^32); draw < thresh => thirsty
     uint32_t seed_lo, seed_hi;
-    int dbg;           // perf-debug mask (PLANTOS_DEBUG_SKIP): 1 no obs stores, 2 no visit loads, 4 no row loads
     int l2_keep;       // 1: tag state accesses L2::evict_last (fast kernel)
     int map_source;    // 0 philox, 1 injected
     int map_episodes;  // injected maps per env

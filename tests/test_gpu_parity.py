@@ -43,17 +43,19 @@ def test_fast_kernel_replays_reference(name):
 
 @pytest.mark.parametrize("name,replicas", [("replay_T_8env", 13), ("replay_DFLT_1env", 70)])
 def test_fast_kernel_pipeline_replays_reference(name, replicas):
-    """The producer/consumer pipeline proper: the fixture's envs replicated to fill several
-    32-env stages (104 = 3 stages + 8 tail envs; 70 = 2 stages + 6), every copy checked."""
+    """The tiled pipeline proper: the fixture's envs replicated to fill many warp tiles
+    (104 envs = 26 tiles of 4; 70 = 17 tiles + 2 tail envs), every copy checked."""
     res = _run(name, "fast", replicas=replicas)
     assert res["bitexact_obs"] == 1 and res["bitexact_reward"] == 1
 
 
-@pytest.mark.parametrize("grid", [1, 2, 5])
-def test_fast_kernel_ring_reuse(grid, monkeypatch):
-    """Few persistent blocks => each walks many stages, so the shared-memory ring wraps and the
-    full/empty mbarrier phases flip several times (24 copies x 8 envs = 6 stages)."""
+@pytest.mark.parametrize("grid,epw", [(1, 4), (1, 8), (2, 16), (5, 8)])
+def test_fast_kernel_buffer_reuse(grid, epw, monkeypatch):
+    """Few persistent blocks => every warp walks several tiles, so both window buffers are
+    reused and the next-tile prefetch path runs (24 copies x 8 envs = 192 envs), for every
+    tile size the library instantiates."""
     monkeypatch.setenv("PLANTOS_FAST_GRID", str(grid))
+    monkeypatch.setenv("PLANTOS_EPW", str(epw))
     res = _run("replay_T_8env", "fast", replicas=24, steps=1100)
     assert res["bitexact_obs"] == 1
 
