@@ -53,6 +53,19 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(envs_per_gpu: int, kernel_name: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture; only valid
+    for the workload it was captured on (131 072 envs, fast kernel), else null."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)
+        if envs_per_gpu == ENVS_PER_GPU and kernel_name == "fast":
+            return int(t["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------ CPU baseline (oracle port)
 def _cpu_worker(conn, n_envs, seed, literal_trig):
     import random
@@ -318,7 +331,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "int (2-bit cells, u16 visits) + f32 table-driven obs/reward", "data": "synthetic",
+            "dtype": "int (2-bit cells, 4-bit/u16 visit counts) + f32 table-driven obs/reward", "data": "synthetic",
             "config": {"workload": workload_name(world), "envs_per_gpu": n, "obs_dim": OBS_DIM,
                        "kernel": kernel_name, "maps": "philox seed 0", "state_bytes_per_env": state_bytes,
                        "l2": f"inputs larger than L2: per-GPU state {n * state_bytes / 1e6:.0f} MB + obs ring "
@@ -329,7 +342,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "steps": e2e_steps, "api": "plantos_step_host (pinned host buffers), per GPU"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": measured_traffic(n, kernel_name),
+                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1_traffic.json)",
+                         "peak_source": peak_src,
                          "alg_bytes_per_env_step": B_ALG, "kernel": f"k_step_{kernel_name}",
                          "avg_launch_us": step_s * 1e6, "isolated_launch_us_median": iso_med_us},
             "clocks": sampler.summary(),

@@ -278,9 +278,11 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
             const int v = std::atoi(s);
             if (v == 4 || v == 8 || v == 16) epw = v;
         }
-        // L2 policy: keep the env state resident (evict_last) when its per-step working set
-        // (~5 lines of 128 B per env) can fit next to the streaming outputs
-        int keep = ((double)p.N * 5 * 128 < 0.8 * (double)prop.l2CacheSize) ? 1 : 0;
+        // L2 policy: PLANTOS_L2_KEEP=1 tags the state accesses evict_last inside a persisting-L2
+        // set-aside.  Off by default: with the compact state layout the plain LRU already keeps
+        // the state resident (steady-state DRAM reads ~16 MB per 131 072-env step), and the
+        // set-aside measured neutral to slightly negative (profiles/r1_summary.md).
+        int keep = 0;
         if (const char* s = std::getenv("PLANTOS_L2_KEEP")) keep = std::atoi(s) ? 1 : 0;
         p.l2_keep = keep;
         if (keep) {
