@@ -5,12 +5,11 @@
 // default (G21 R2 C10, D=77; plantos_env.py:25-26) qualify; everything else runs
 // k_step_generic.
 //
-// Persistent grid (PLANTOS_FAST_MINBLOCKS blocks per SM); every warp walks TILES of EPW
-// consecutive envs (tile = warp id, + number of warps, ...) through a two-deep software
-// pipeline, so that the memory latency of the next tile hides under the arithmetic and the
+// Persistent grid (PLANTOS_FAST_MINBLOCKS blocks per SM); every warp owns a contiguous range of
+// envs and walks it in TILES of EPW consecutive envs through a two-deep software pipeline, so that the memory latency of the next tile hides under the arithmetic and the
 // observation stores of the current one:
-//   fetch    one LANE per env: load the 32-byte record and the action (issued one tile ahead,
-//            held in registers), then fetch everything else the step can touch, centred on the
+//   fetch    the 32-byte records and the actions are copied to shared memory two tiles ahead;
+//            everything else the step can touch is fetched one tile ahead, centred on the
 //            PRE-move position with a margin of one cell: 2R+4 rows of the wall-padded type
 //            plane (128 contiguous bytes for R=6) and 7 rows of the visit-nibble plane (112
 //            contiguous bytes) -- 15 asynchronous 16-byte global->shared copies (cp.async)
@@ -33,7 +32,7 @@
 //            evict the env state from L2.
 //   phase C  whole warp, rare -- SB3 auto-reset of finished envs (terminal observation,
 //            Philox / injected map, fresh observation) via the generic warp routines.
-// Envs beyond the last full tile (N % EPW) are stepped one by one with step_env_warp.
+// The last N % 4 envs are stepped one by one with step_env_warp.
 #pragma once
 #include <type_traits>
 #include "plantos_generic.cuh"
@@ -44,7 +43,7 @@ namespace plantos_dev {
 #define PLANTOS_FAST_MINBLOCKS 4
 #endif
 #ifndef PLANTOS_FAST_WARPS
-#define PLANTOS_FAST_WARPS 7         // 7 warps x 4 blocks = 28 resident warps per SM
+#define PLANTOS_FAST_WARPS 7         // 7 warps x 4 blocks = 28 resident warps per SM (<= 72 registers each)
 #endif
 constexpr int kFastWarps = PLANTOS_FAST_WARPS;
 constexpr int kVisWinRows = 7;       // nibble rows x-3 .. x+3 around the pre-move position
@@ -60,7 +59,7 @@ __host__ __device__ inline int fast_win_bytes(int EPW, int R, int G) {
     return win < align_up(G * 8, 16) ? align_up(G * 8, 16) : win;
 }
 __host__ __device__ inline int fast_warp_scratch_bytes(int EPW, int R, int G, int D) {
-    return 2 * fast_win_bytes(EPW, R, G) + 16 * D;
+    return 2 * fast_win_bytes(EPW, R, G) + 16 * D + 2 * EPW * 40;   // + two record/action buffers
 }
 
 // ---- asynchronous global->shared copies (16-byte cp.async, L2 only) ------------------------
@@ -80,13 +79,11 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
     asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
 }
+__device__ __forceinline__ void cp_async8(uint32_t sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sdst), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-struct RecRegs {       // one env's record + action, held in registers one tile ahead of use
-    uint4 ra, rb;
-    long long action;
-};
 
 template <int R, int C, int EPW, bool KEEP>
 __global__ void __launch_bounds__(kFastWarps * 32, PLANTOS_FAST_MINBLOCKS)
@@ -112,10 +109,14 @@ k_step_fast(const Params p, const StepIO io) {
     auto buf_twin = [&](int b) { return reinterpret_cast<uint64_t*>(scratch + b * win_bytes); };                      // [EPW][TWR]
     auto buf_vwin = [&](int b) { return reinterpret_cast<uint32_t*>(scratch + b * win_bytes + EPW * kTypeWinBytes); };   // [EPW][7][4]
 
-    const int ntiles = p.N / EPW;                                     // full tiles
+    // Every warp owns one contiguous range of Q envs (Q a multiple of 4, the same for all warps, so
+    // the work is balanced to within one 4-env group) and walks it in tiles of EPW; the range's
+    // last tile may be shorter.
     const int gwarp = blockIdx.x * kFastWarps + warp, nwarps = gridDim.x * kFastWarps;
+    const int nfull = p.N & ~3;                                       // envs in whole 4-env groups
+    const int Q = (((nfull + nwarps - 1) / nwarps) + 3) & ~3;
+    const int wbase = min(nfull, gwarp * Q), wend = min(nfull, wbase + Q);
     // ---- per-lane constants of phase B
-    const bool act = lane < EPW;
     const int sub = lane & 15, half = lane >> 4, hbase = lane & 16;
     int srcl[R], shf[R];
 #pragma unroll
@@ -123,7 +124,8 @@ k_step_fast(const Params p, const StepIO io) {
         int dx = 0, dy = 0;
         if (sub < C) { dx = t.off[(sub * R + rr) * 2]; dy = t.off[(sub * R + rr) * 2 + 1]; }
         srcl[rr] = hbase + dx + R;     // lane holding window row x+dx
-        shf[rr] = 2 * (dy + R);        // bit offset of column y+dy inside the window word
+        // left shift that brings column y+dy of the window word (bits 2(dy+R), +1) to bits 30, 31
+        shf[rr] = 30 - 2 * (dy + R);
     }
     const bool has_row = sub < NROW, has_ray = sub < C, has_vrow = sub < 5, has_v1 = sub < 9;
     // the two window cells this lane converts: q = sub and q = sub + 16 -> (row lane, nibble shift)
@@ -135,23 +137,28 @@ k_step_fast(const Params p, const StepIO io) {
     constexpr int NCH = 2;             // envs per half-warp and trip, interleaved for ILP
     const float4* src4 = reinterpret_cast<const float4*>(tile);
 
-    // ---- pipeline helpers
-    auto load_rec = [&](int tl, RecRegs& q) {
-        if (act) {
-            const size_t e = (size_t)tl * EPW + lane;
-            q.ra = mem.ld128(p.rec + 2 * e);
-            q.rb = mem.ld128(p.rec + 2 * e + 1);
-            q.action = __ldcs(io.actions + e);
+    // ---- pipeline helpers.  Records + actions are prefetched two tiles ahead, windows one tile
+    // ahead, all with cp.async into shared memory: the prefetch holds no registers.
+    auto rec_buf = [&](int b) { return reinterpret_cast<uint4*>(scratch + 2 * win_bytes + 16 * D + b * EPW * 40); };
+    auto act_buf = [&](int b) { return reinterpret_cast<long long*>(scratch + 2 * win_bytes + 16 * D + b * EPW * 40 + EPW * 32); };
+    auto fetch_rec = [&](int es, int b) {              // tile starting at env es
+        if (lane < min(EPW, wend - es)) {
+            const size_t e = (size_t)es + lane;
+            cp_async16(smem_u32(rec_buf(b) + 2 * lane), p.rec + 2 * e);
+            cp_async16(smem_u32(rec_buf(b) + 2 * lane + 1), p.rec + 2 * e + 1);
+            cp_async8(smem_u32(act_buf(b) + lane), io.actions + e);
         }
+        cp_async_commit();
     };
     // Window fetch of tile `tl` into buffer b.  LPE = 32/EPW lanes share one env: lane l serves
     // env l % EPW and the 16-byte chunks l / EPW, + LPE, ... of its windows (TCH chunks of type
-    // rows, then 7 nibble rows).  `q` holds the record of env `lane` (lanes < EPW).
+    // rows, then 7 nibble rows).  The tile's records are already in rec_buf(b).
     constexpr int LPE = 32 / EPW, TCH = TWR / 2;
-    auto issue_copies = [&](int tl, int b, const RecRegs& q) {
+    auto issue_copies = [&](int es, int b) {
         const int j = lane % EPW, k0 = lane / EPW;
-        const int x = __shfl_sync(FULL, q.ra.x, j) & 0xff;
-        const size_t e = (size_t)tl * EPW + j;
+        const bool live = j < wend - es;                // the range's last tile may be short
+        const int x = live ? (int)(rec_buf(b)[2 * j].x & 0xff) : 0;
+        const size_t e = (size_t)es + j;
         // grid rows x-R-1 .. x+R+1 are padded rows x+1 .. x+2R+3; start on the even row at or
         // just below x+1 so that every chunk is 16-byte aligned
         const int r0 = (x + 1) & ~1;
@@ -161,40 +168,45 @@ k_step_fast(const Params p, const StepIO io) {
         const uint32_t vdst = smem_u32(buf_vwin(b) + j * kVisWinRows * VW);
 #pragma unroll
         for (int k = k0, i = 0; i < (TCH + kVisWinRows + LPE - 1) / LPE; ++i, k += LPE) {
+            if (!live) continue;
             if (k < TCH) cp_async16(tdst + 16 * k, tsrc + 2 * k);
             else if (k < TCH + kVisWinRows) cp_async16(vdst + 16 * (k - TCH), vsrc + 4 * (k - TCH));
         }
         cp_async_commit();
     };
 
-    RecRegs cur, nxt;
-    cur.ra = cur.rb = nxt.ra = nxt.rb = make_uint4(0, 0, 0, 0);
-    cur.action = nxt.action = 0;
-    if (gwarp < ntiles) { load_rec(gwarp, cur); issue_copies(gwarp, 0, cur); }
+    if (wbase < wend) {
+        fetch_rec(wbase, 0);
+        cp_async_wait_all();
+        __syncwarp();
+        issue_copies(wbase, 0);
+        if (wbase + EPW < wend) fetch_rec(wbase + EPW, 1);
+    }
 
     int it = 0;
-    for (int tl = gwarp; tl < ntiles; tl += nwarps, ++it) {
+    for (int e0 = wbase; e0 < wend; e0 += EPW, ++it) {
         const int b = it & 1;
-        const int tl_next = tl + nwarps;
-        const bool has_next = tl_next < ntiles;
-        if (has_next) load_rec(tl_next, nxt);             // record loads of the next tile, in flight during phase A
+        const int e_next = e0 + EPW;
+        const bool has_next = e_next < wend;
+        const int ts = min(EPW, wend - e0);               // envs in this tile (a multiple of 4)
+        const bool act = lane < ts;
         uint64_t* twin = buf_twin(b);
         uint32_t* vwin = buf_vwin(b);
-        const int e0 = tl * EPW;
         const size_t e = (size_t)e0 + lane;
-        cp_async_wait_all();                              // this tile's windows have landed ...
-        __syncwarp();                                     // ... for every lane of the warp
+        cp_async_wait_all();                              // this tile's windows and the next tile's records
+        __syncwarp();                                     // have landed, for every lane of the warp
 
         // ---- phase A: transition out of shared memory, one lane per env
         int done = 0, term = 0, trunc = 0;
         unsigned posw = 0;
         EnvRec r = {};
         if (act) {
-            uint4 ra = cur.ra, rb = cur.rb;
+            uint4 ra = rec_buf(b)[2 * lane], rb = rec_buf(b)[2 * lane + 1];
+            const long long action = act_buf(b)[lane];
             r = unpack_rec(ra, rb);
             const int x0 = r.x, r0 = (r.x + 1) & ~1;      // the windows are centred on the pre-move row
             int tx, ty; bool inb;
-            action_target(r, cur.action, G, tx, ty, inb);
+            action_target(r, action, G, tx, ty, inb);
             // (tx, ty) is at most one cell away, so it is inside both windows even when it is
             // outside the grid (wall padding / border nibbles)
             uint64_t* tw = twin + lane * TWR + (tx + TP - r0);
@@ -203,7 +215,7 @@ k_step_fast(const Params p, const StepIO io) {
             uint32_t* vw = vwin + (lane * kVisWinRows + (tx - x0 + 3)) * VW + ((ty + 2) >> 3);
             const int sh = nib_shift(ty);
             const uint32_t vword = *vw;
-            const StepOut o = transition_core(r, cur.action, tx, ty, t_cell, (vword >> sh) & 15u, p.max_steps);
+            const StepOut o = transition_core(r, action, tx, ty, t_cell, (vword >> sh) & 15u, p.max_steps);
             if (o.moved)
                 *vw = bump_visit(p.vis4 + e * VE + nib_word(tx, ty, VW), vword, sh,
                                  p.visov + e * G * G + tx * G + ty, mem);
@@ -237,14 +249,15 @@ k_step_fast(const Params p, const StepIO io) {
         __syncwarp();   // window patches are visible to the half-warps below
 
         // the next tile's copies go out now and land while phase B runs
-        if (has_next) issue_copies(tl_next, b ^ 1, nxt);
+        if (has_next) issue_copies(e_next, b ^ 1);
+        if (e_next + EPW < wend) fetch_rec(e_next + EPW, b);     // rec_buf(b) is free again
 
         // ---- phase B: observations.  Each trip builds four rows: two independent chains per
         // half-warp, written stage by stage (all shared-memory reads of both chains, then the
         // shuffles, then the table reads, then the stores) so that their latencies overlap.
         float4* const obs4 = reinterpret_cast<float4*>(io.obs) + (size_t)(e0 >> 2) * D;
 #pragma unroll 1
-        for (int base = 0; base < EPW; base += 4) {
+        for (int base = 0; base < ts; base += 4) {
             int x[NCH], y[NCH], tb[NCH], vb[NCH];
             unsigned w[NCH], vslice[NCH], acc[NCH], s0[NCH], s1[NCH];
             uint64_t trow[NCH];
@@ -283,11 +296,15 @@ k_step_fast(const Params p, const StepIO io) {
             // stage 4: LIDAR march (plantos_env.py:260-284): sample rr looks at window row
             // srcl[rr], bits shf[rr]; visit cells come from the row lanes' slices
 #pragma unroll
-            for (int rr = 0; rr < R; ++rr) {
+            // (far sample first: each step shifts the accumulator left by one cell and funnels the
+            // sample's two bits in from the top of the aligned row word -- two shifts per sample --
+            // so that sample rr ends up at bits 2rr, 2rr+1)
+#pragma unroll
+            for (int rr = R - 1; rr >= 0; --rr) {
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     const unsigned wr = __shfl_sync(FULL, w[c], srcl[rr]);
-                    acc[c] += ((wr >> shf[rr]) & 3u) << (2 * rr);
+                    acc[c] = __funnelshift_l(wr << shf[rr], acc[c], 2);
                 }
             }
 #pragma unroll
@@ -363,12 +380,11 @@ k_step_fast(const Params p, const StepIO io) {
             }
             __syncwarp();
         }
-        cur = nxt;
     }
 
     // ragged tail: envs beyond the last full tile, one at a time (no copies are in flight here)
     if (gwarp == nwarps - 1)
-        for (int e = ntiles * EPW; e < p.N; ++e) step_env_warp(p, t, io, e, buf_twin(0), tile, lane);
+        for (int e = nfull; e < p.N; ++e) step_env_warp(p, t, io, e, buf_twin(0), tile, lane);
 }
 
 }  // namespace plantos_dev
