@@ -31,13 +31,9 @@ int fail(int code, const std::string& msg) {
 
 typedef void (*fast_kernel_t)(const Params, const StepIO);
 
-struct FastVariant { int R, C, EPW, keep; fast_kernel_t fn; };
+struct FastVariant { int R, C, keep; fast_kernel_t fn; };
 
-#define FAST_ROW1(R_, C_, K_)                                                              \
-    {R_, C_, 4, K_, k_step_fast<R_, C_, 4, K_>}, {R_, C_, 8, K_, k_step_fast<R_, C_, 8, K_>},   \
-    {R_, C_, 16, K_, k_step_fast<R_, C_, 16, K_>}
-#define FAST_ROW(R_, C_) FAST_ROW1(R_, C_, 0), FAST_ROW1(R_, C_, 1)
-
+#define FAST_ROW(R_, C_) {R_, C_, 0, k_step_fast<R_, C_, false>}, {R_, C_, 1, k_step_fast<R_, C_, true>}
 const FastVariant kFastVariants[] = {
     FAST_ROW(6, 16),  // training preset, A2C_training.py:206-212
     FAST_ROW(2, 10),  // ctor default, plantos_env.py:25-26
@@ -64,7 +60,9 @@ struct plantos {
     // launch configuration
     bool use_fast;
     fast_kernel_t fast_fn;
-    int fast_epw, fast_grid;
+    int fast_grid;
+    uint4* d_table_blob;
+    int4* d_lane_tab;
     int generic_grid, generic_smem;
     int fast_smem;
     bool did_reset;
@@ -165,13 +163,17 @@ static int upload_tables_impl(plantos_t* h, const int8_t* lidar_off, const float
         CUDA_TRY(cudaMemcpy((void*)p.reward64, reward_tab, sizeof(double) * 2 * PLANTOS_RW_COUNT, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy((void*)p.reward32, r32, sizeof(r32), cudaMemcpyHostToDevice));
     }
+    // re-pack the fast kernel's table image and lane constants from the device tables
+    k_pack_tables<<<1, 128, tables_bytes(p.G, p.R, p.C)>>>(p, h->d_table_blob, h->d_lane_tab);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
     return PLANTOS_OK;
 }
 
 static void free_all(plantos_t* h) {
     if (!h) return;
     cudaFree(h->p.rec); cudaFree(h->p.term_rec); cudaFree(h->p.types); cudaFree(h->p.vis4); cudaFree(h->p.visov);
-    cudaFree(h->d_tables); cudaFree(h->p.stats); cudaFree(h->p.err);
+    cudaFree(h->d_tables); cudaFree(h->d_table_blob); cudaFree(h->d_lane_tab); cudaFree(h->p.stats); cudaFree(h->p.err);
     cudaFree(h->d_map_cells); cudaFree(h->d_map_rover);
     cudaFree(h->s_actions); cudaFree(h->s_obs); cudaFree(h->s_reward); cudaFree(h->s_done);
     delete h;
@@ -237,7 +239,11 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     // tables: rw64 | rw32 | dist | pos | visit | off
     const size_t tb = 2 * kRwCount * 8 + 2 * kRwCount * 4 + (p.R + 1) * 4 + p.G * 4 + 12 * 4 + (size_t)p.C * p.R * 2 + 64;
     ALLOC(h->d_tables, tb);
+    ALLOC(h->d_table_blob, tables_bytes(p.G, p.R, p.C));
+    ALLOC(h->d_lane_tab, 32 * kLaneTabVec * sizeof(int4));
 #undef ALLOC
+    p.table_blob = h->d_table_blob;
+    p.lane_tab = h->d_lane_tab;
     {
         unsigned char* b = (unsigned char*)h->d_tables;
         p.reward64 = (const double*)b; b += 2 * kRwCount * 8;
@@ -269,15 +275,6 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     const bool fast_ok = (p.W == 1) && (p.VW == 4) && (p.G + p.R <= 32) && (2 * p.R + 1 <= 16) && (p.C <= 16);
     h->use_fast = false;
     if (cfg->kernel != PLANTOS_KERNEL_GENERIC && fast_ok) {
-        // envs per warp tile: 8 gives every resident warp (28 per SM) about four tiles to
-        // pipeline at the benchmark size; 4 when there are too few envs to occupy the warps
-        int epw = 8;
-        const long long resident = (long long)h->num_sms * PLANTOS_FAST_MINBLOCKS * kFastWarps;
-        if ((long long)p.N / epw < 2 * resident) epw = 4;
-        if (const char* s = std::getenv("PLANTOS_EPW")) {
-            const int v = std::atoi(s);
-            if (v == 4 || v == 8 || v == 16) epw = v;
-        }
         // L2 policy: PLANTOS_L2_KEEP=1 tags the state accesses evict_last inside a persisting-L2
         // set-aside.  Off by default: with the compact state layout the plain LRU already keeps
         // the state resident (steady-state DRAM reads ~16 MB per 131 072-env step), and the
@@ -295,21 +292,24 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
         }
         for (const FastVariant& v : kFastVariants)
-            if (v.R == p.R && v.C == p.C && v.EPW == epw && v.keep == keep) { h->use_fast = true; h->fast_fn = v.fn; h->fast_epw = epw; }
+            if (v.R == p.R && v.C == p.C && v.keep == keep) { h->use_fast = true; h->fast_fn = v.fn; }
     }
     if (cfg->kernel == PLANTOS_KERNEL_FAST && !h->use_fast) {
         free_all(h);
         return fail(PLANTOS_EINVAL, "PLANTOS_KERNEL_FAST requested but (G, R, C) has no fast-kernel instantiation");
     }
     h->generic_smem = tables_bytes(p.G, p.R, p.C) + kGenericWarps * generic_warp_scratch_bytes(p.G, p.W, p.D);
-    h->fast_smem = tables_bytes(p.G, p.R, p.C) + kFastWarps * fast_warp_scratch_bytes(h->fast_epw ? h->fast_epw : 8, p.R, p.G, p.D);
+    h->fast_smem = tables_bytes(p.G, p.R, p.C) + kFastWarps * fast_warp_scratch_bytes(p.R, p.G, p.D);
     if (h->use_fast) {
-        // persistent grid: at most PLANTOS_FAST_MINBLOCKS blocks per SM, each warp walks its tiles
+        // persistent grid: at most PLANTOS_FAST_MINBLOCKS blocks per SM, each warp walks its own
+        // contiguous env range (at least 8 envs per warp when there are few envs)
         long long blocks = (long long)h->num_sms * PLANTOS_FAST_MINBLOCKS;
         if (const char* s = std::getenv("PLANTOS_FAST_GRID")) { const int v = std::atoi(s); if (v > 0) blocks = v; }
-        const long long need = ((long long)p.N / h->fast_epw + kFastWarps - 1) / kFastWarps;
+        const long long need = ((long long)p.N / 8 + kFastWarps - 1) / kFastWarps;
         if (blocks > need) blocks = need;
         h->fast_grid = (int)(blocks < 1 ? 1 : blocks);
+        const long long nwarps = (long long)h->fast_grid * kFastWarps, nfull = p.N & ~3;
+        p.fast_q = (int)((((nfull + nwarps - 1) / nwarps) + 3) & ~3LL);
     }
     cudaError_t e1 = cudaFuncSetAttribute(k_step_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);
     cudaError_t e2 = cudaFuncSetAttribute(k_reset_all, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);

@@ -33,6 +33,8 @@ constexpr int kRwCount = 6;  // PLANTOS_RW_COUNT
 constexpr int kStatCount = 8;
 constexpr int kScCount = 11;  // PLANTOS_SC_COUNT
 
+constexpr int kLaneTabVec = 5;   // int4 per lane: srcl[8] | shf[8] | vsrc0, vsh0, vsrc1, vsh1
+
 struct Params {
     int N;
     long long env_base;
@@ -62,6 +64,11 @@ struct Params {
     const float* visit_tab;   // [11]
     const float* reward32;    // [2*kRwCount]
     const double* reward64;   // [2*kRwCount]
+    // the same tables pre-packed for the fast kernel by k_pack_tables: the shared-memory image of
+    // load_tables (tables_bytes, copied with 16-byte loads) and its per-lane constants
+    const uint4* table_blob;
+    const int4* lane_tab;     // [32][kLaneTabVec]
+    int fast_q;               // envs per warp of the fast kernel's persistent grid (multiple of 4)
     // injected maps
     const uint8_t* map_cells;   // [N][E][G*G]
     const int16_t* map_rover;   // [N][E][2]
@@ -199,6 +206,28 @@ __host__ __device__ inline int tables_bytes(int G, int R, int C) {
     b += (R + 1) * 4 + G * 4 + 16 * 4;     // dist, pos, visit
     b += align_up(C * R * 2, 16);          // offsets
     return align_up(b, 16);
+}
+
+// Where each table sits in the shared-memory image.
+__device__ __forceinline__ Tables tables_at(unsigned char* smem, int G, int R) {
+    double* rw64 = reinterpret_cast<double*>(smem);
+    float* onehot = reinterpret_cast<float*>(rw64 + 2 * kRwCount);
+    float* rw32 = onehot + 16;
+    float* dist = rw32 + 2 * kRwCount;
+    float* pos = dist + (R + 1);
+    float* visit = pos + G;
+    int8_t* off = reinterpret_cast<int8_t*>(visit + 16);
+    Tables t;
+    t.off = off; t.dist = dist; t.pos = pos; t.visit = visit; t.rw32 = rw32; t.rw64 = rw64; t.onehot = onehot;
+    return t;
+}
+
+// Fast-kernel variant: the image was packed once by k_pack_tables, a block only copies it.
+__device__ __forceinline__ Tables load_table_blob(const Params& p, unsigned char* smem, int G, int R, int C) {
+    const int n16 = tables_bytes(G, R, C) >> 4;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = p.table_blob[i];
+    __syncthreads();
+    return tables_at(smem, G, R);
 }
 
 // Cooperative load by the whole block; ends with __syncthreads().

@@ -6,33 +6,25 @@
 // k_step_generic.
 //
 // Persistent grid (PLANTOS_FAST_MINBLOCKS blocks per SM); every warp owns a contiguous range of
-// envs and walks it in TILES of EPW consecutive envs through a two-deep software pipeline, so that the memory latency of the next tile hides under the arithmetic and the
-// observation stores of the current one:
-//   fetch    the 32-byte records and the actions are copied to shared memory two tiles ahead;
-//            everything else the step can touch is fetched one tile ahead, centred on the
-//            PRE-move position with a margin of one cell: 2R+4 rows of the wall-padded type
-//            plane (128 contiguous bytes for R=6) and 7 rows of the visit-nibble plane (112
-//            contiguous bytes) -- 15 asynchronous 16-byte global->shared copies (cp.async)
-//            per env, spread over the 32/EPW lanes that share an env.  They are issued right
-//            after the current tile's phase A, into the other of the warp's two window
-//            buffers, and are the ONLY reads of plane state the step performs.
-//   phase A  one lane per env, entirely out of shared memory: the transition
-//            (plantos_env.py:160-222) -- target-cell lookup, visit count, watering, reward,
-//            termination.  The (at most two) modified words go back to global memory and are
-//            patched in the shared copy; reward / done / record stores are coalesced.
-//   phase B  one HALF-WARP per env, two envs per half-warp interleaved stage by stage for ILP
-//            -- the observation (plantos_env.py:251-315) from the shared windows: 2R+1 lanes
-//            shift their type row into a rover-centred window word (the padding makes bounds
-//            checks unnecessary); one lane per ray marches the integer offset table with a
-//            warp shuffle as the row lookup; five lanes cut the 20-bit slice of their visit
-//            row that the 5x5 window needs and the 25 cell lanes read it by shuffle.  Rows are
-//            assembled in a 4-env shared-memory tile whose 16*D bytes are 16-byte aligned in
-//            the [N, D] fp32 buffer and leave with streaming 128-bit stores
-//            (st.global.cs.v4, evict-first), so the write-once observation stream does not
-//            evict the env state from L2.
-//   phase C  whole warp, rare -- SB3 auto-reset of finished envs (terminal observation,
-//            Philox / injected map, fresh observation) via the generic warp routines.
-// The last N % 4 envs are stepped one by one with step_env_warp.
+// envs.  The order of work inside a warp keeps every lane busy in the transition and fetches
+// only what is used:
+//   * a warp walks its contiguous env range in MACRO TILES of 32 envs.  The transition
+//     (plantos_env.py:160-222) runs once per macro tile with one lane per env -- all 32 lanes
+//     active instead of 8 -- and needs exactly two words of plane state per env: the type row
+//     and the visit-nibble word of the cell the action looks at.  Those two words (and the
+//     32-byte record + the action before them) are prefetched with cp.async while the previous
+//     macro tile is still building observations.
+//   * the observations (plantos_env.py:251-315) are built in TRIPS of 4 envs, one half-warp per
+//     env and two envs per half-warp, out of shared-memory windows centred on the POST-move
+//     position (no margin rows: 2R+2 type rows and 5 nibble rows = 12 sixteen-byte chunks per env
+//     for R = 6).  The windows of trip k+1 are copied (cp.async, 48 chunks over 32 lanes) while
+//     trip k computes; they are read after the transition's global stores of the same warp, so
+//     no shared-memory patching is needed.
+//   * rows are assembled in a 4-env shared-memory tile whose 16*D bytes are 16-byte aligned in
+//     the [N, D] fp32 buffer and leave with streaming 128-bit stores (st.global.cs.v4,
+//     evict-first), so the write-once observation stream does not evict the env state from L2.
+//   * auto-reset of finished envs (SB3 semantics: terminal observation, Philox / injected map,
+//     fresh observation) and the ragged N % 4 tail use the generic warp routines.
 #pragma once
 #include <type_traits>
 #include "plantos_generic.cuh"
@@ -43,27 +35,26 @@ namespace plantos_dev {
 #define PLANTOS_FAST_MINBLOCKS 4
 #endif
 #ifndef PLANTOS_FAST_WARPS
-#define PLANTOS_FAST_WARPS 7         // 7 warps x 4 blocks = 28 resident warps per SM (<= 72 registers each)
+#define PLANTOS_FAST_WARPS 7          // 7 warps x 4 blocks = 28 resident warps per SM (<= 72 registers each)
 #endif
 constexpr int kFastWarps = PLANTOS_FAST_WARPS;
-constexpr int kVisWinRows = 7;       // nibble rows x-3 .. x+3 around the pre-move position
-constexpr int kVisWinBytes = kVisWinRows * 16;
-// type rows fetched per env: x-R-1 .. x+R+1 (2R+3 rows) plus one because the copy starts on an
-// even row (16-byte aligned source and size)
-__host__ __device__ constexpr int type_win_rows(int R) { return 2 * R + 4; }
+constexpr int kFastEnvs = 32;         // envs per macro tile (one lane each in the transition)
+constexpr int kFastTrip = 4;          // envs per observation trip
+constexpr int kFastVisRows = 5;       // nibble rows x-2 .. x+2
 
-// per-warp scratch: two window buffers [type windows | visit windows] and one 4-env obs tile.
-// Phase C / the tail reuse a window buffer as the generic code's type plane.
-__host__ __device__ inline int fast_win_bytes(int EPW, int R, int G) {
-    int win = EPW * (type_win_rows(R) * 8 + kVisWinBytes);
-    return win < align_up(G * 8, 16) ? align_up(G * 8, 16) : win;
+// type rows fetched per env: x-R .. x+R (2R+1 rows) plus one because the copy starts on an even row
+__host__ __device__ constexpr int fast_type_rows(int R) { return 2 * R + 2; }
+__host__ __device__ inline int fast_win_bytes(int R, int G) {
+    const int win = kFastTrip * (fast_type_rows(R) * 8 + kFastVisRows * 16);
+    return win < align_up(G * 8, 16) ? align_up(G * 8, 16) : win;    // phase C borrows it as a type plane
 }
-__host__ __device__ inline int fast_warp_scratch_bytes(int EPW, int R, int G, int D) {
-    return 2 * fast_win_bytes(EPW, R, G) + 16 * D + 2 * EPW * 40;   // + two record/action buffers
+// per-warp scratch: two window buffers | 4-env obs tile | 32 records | 32 actions | 32+32 target words
+__host__ __device__ inline int fast_warp_scratch_bytes(int R, int G, int D) {
+    return 2 * fast_win_bytes(R, G) + 16 * D + kFastEnvs * (32 + 8 + 8 + 4);
 }
 
 // ---- asynchronous global->shared copies (16-byte cp.async, L2 only) ------------------------
-// The per-env windows sit at per-env addresses, so they are fetched with per-lane 16-byte
+// Records, target words and windows sit at per-env addresses, so they are fetched with per-lane
 // cp.async copies (a cp.async.bulk / TMA copy needs warp-uniform operands: issuing one per
 // env costs a ~15-instruction elect loop per copy, which measured at 27 instructions per env).
 __device__ __forceinline__ uint32_t smem_u32(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
@@ -85,7 +76,13 @@ __device__ __forceinline__ void cp_async8(uint32_t sdst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int R, int C, int EPW, bool KEEP>
+__device__ __forceinline__ void cp_async4(uint32_t sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sdst), "l"(gsrc) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+template <int R, int C, bool KEEP>
 __global__ void __launch_bounds__(kFastWarps * 32, PLANTOS_FAST_MINBLOCKS)
 k_step_fast(const Params p, const StepIO io) {
     constexpr int D = 5 * C + 27;
@@ -93,137 +90,116 @@ k_step_fast(const Params p, const StepIO io) {
     constexpr int VW = 4;                 // nibble words per visit row (G + 4 <= 32)
     constexpr int TP = R + 2;             // wall rows above the grid (== Params.TP)
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int TWR = type_win_rows(R);
-    constexpr int kTypeWinBytes = TWR * 8;
+    constexpr int TWR = fast_type_rows(R);
+    constexpr int TCH = TWR / 2;          // 16-byte chunks of type rows per env
+    constexpr int NCHUNK = TCH + kFastVisRows;
     static_assert(NROW <= 16 && C <= 16, "fast kernel shape limits");
-    static_assert(EPW % 4 == 0 && EPW <= 32, "tile must be whole 4-env groups");
+    static_assert(NCHUNK <= 16, "two copy rounds of 8 chunk lanes per env");
 
     extern __shared__ __align__(16) unsigned char smem[];
-    const Tables t = load_tables(p, smem);
     typename std::conditional<KEEP, KeepMem, PlainMem>::type const mem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int G = p.G, VE = p.VE, TS = p.TS;
-    const int win_bytes = fast_win_bytes(EPW, R, G);
-    unsigned char* scratch = smem + tables_bytes(G, R, C) + warp * fast_warp_scratch_bytes(EPW, R, G, D);
+    const int win_bytes = fast_win_bytes(R, G);
+    unsigned char* scratch = smem + tables_bytes(G, R, C) + warp * fast_warp_scratch_bytes(R, G, D);
     float* tile = reinterpret_cast<float*>(scratch + 2 * win_bytes);
-    auto buf_twin = [&](int b) { return reinterpret_cast<uint64_t*>(scratch + b * win_bytes); };                      // [EPW][TWR]
-    auto buf_vwin = [&](int b) { return reinterpret_cast<uint32_t*>(scratch + b * win_bytes + EPW * kTypeWinBytes); };   // [EPW][7][4]
+    uint4* const recb = reinterpret_cast<uint4*>(scratch + 2 * win_bytes + 16 * D);             // [32][2]
+    long long* const actb = reinterpret_cast<long long*>(recb + 2 * kFastEnvs);                   // [32]
+    uint64_t* const tgt_t = reinterpret_cast<uint64_t*>(actb + kFastEnvs);                        // [32]
+    uint32_t* const tgt_v = reinterpret_cast<uint32_t*>(tgt_t + kFastEnvs);                       // [32]
+    auto win_t = [&](int b) { return reinterpret_cast<uint64_t*>(scratch + b * win_bytes); };                              // [4][TWR]
+    auto win_v = [&](int b) { return reinterpret_cast<uint32_t*>(scratch + b * win_bytes + kFastTrip * TWR * 8); };          // [4][5][4]
 
-    // Every warp owns one contiguous range of Q envs (Q a multiple of 4, the same for all warps, so
-    // the work is balanced to within one 4-env group) and walks it in tiles of EPW; the range's
-    // last tile may be shorter.
+    // Every warp owns one contiguous range of Q envs (Q a multiple of 4, the same for all warps).
+    // (Q = p.fast_q is computed on the host for this grid.)
     const int gwarp = blockIdx.x * kFastWarps + warp, nwarps = gridDim.x * kFastWarps;
     const int nfull = p.N & ~3;                                       // envs in whole 4-env groups
-    const int Q = (((nfull + nwarps - 1) / nwarps) + 3) & ~3;
-    const int wbase = min(nfull, gwarp * Q), wend = min(nfull, wbase + Q);
-    // ---- per-lane constants of phase B
-    const int sub = lane & 15, half = lane >> 4, hbase = lane & 16;
+    const int wbase = min(nfull, gwarp * p.fast_q), wend = min(nfull, wbase + p.fast_q);
+
+    // ---- prefetch helpers (all cp.async into shared memory: a prefetch holds no registers)
+    auto fetch_rec = [&](int es) {                     // records + actions of the macro tile at es
+        if (lane < min(kFastEnvs, wend - es)) {
+            const size_t e = (size_t)es + lane;
+            cp_async16(smem_u32(recb + 2 * lane), p.rec + 2 * e);
+            cp_async16(smem_u32(recb + 2 * lane + 1), p.rec + 2 * e + 1);
+            cp_async8(smem_u32(actb + lane), io.actions + e);
+        }
+        cp_async_commit();
+    };
+    auto issue_target = [&](int es) {                  // the two words the transition will look at
+        if (lane < min(kFastEnvs, wend - es)) {
+            const size_t e = (size_t)es + lane;
+            const uint32_t w0 = recb[2 * lane].x;
+            EnvRec q;
+            q.x = (int)(w0 & 0xff); q.y = (int)((w0 >> 8) & 0xff);
+            int tx, ty; bool inb;
+            action_target(q, actb[lane], G, tx, ty, inb);
+            // (tx, ty) may be one cell outside the grid: wall rows / border nibbles are there
+            cp_async8(smem_u32(tgt_t + lane), p.types + e * TS + TP + tx);
+            cp_async4(smem_u32(tgt_v + lane), p.vis4 + e * VE + nib_word(tx, ty, VW));
+        }
+        cp_async_commit();
+    };
+
+    if (wbase < wend) fetch_rec(wbase);                // overlaps the table load
+    // ---- per-lane constants of the observation phase, precomputed by k_pack_tables:
+    //   srcl[rr]  lane holding window row x+dx of LIDAR sample rr of this lane's ray
+    //   shf[rr]   left shift that brings column y+dy of the window word to bits 30, 31
+    //   vsrc/vsh  the two 5x5 visit cells this lane converts (q = sub, sub + 16): row lane, nibble shift
+    int lt[4 * kLaneTabVec];
+#pragma unroll
+    for (int q = 0; q < kLaneTabVec; ++q) {
+        const int4 v = __ldg(p.lane_tab + lane * kLaneTabVec + q);
+        lt[4 * q] = v.x; lt[4 * q + 1] = v.y; lt[4 * q + 2] = v.z; lt[4 * q + 3] = v.w;
+    }
+    const Tables t = load_table_blob(p, smem, G, R, C);
+    const int sub = lane & 15, half = lane >> 4;
     int srcl[R], shf[R];
 #pragma unroll
-    for (int rr = 0; rr < R; ++rr) {
-        int dx = 0, dy = 0;
-        if (sub < C) { dx = t.off[(sub * R + rr) * 2]; dy = t.off[(sub * R + rr) * 2 + 1]; }
-        srcl[rr] = hbase + dx + R;     // lane holding window row x+dx
-        // left shift that brings column y+dy of the window word (bits 2(dy+R), +1) to bits 30, 31
-        shf[rr] = 30 - 2 * (dy + R);
-    }
+    for (int rr = 0; rr < R; ++rr) { srcl[rr] = lt[rr]; shf[rr] = lt[8 + rr]; }
     const bool has_row = sub < NROW, has_ray = sub < C, has_vrow = sub < 5, has_v1 = sub < 9;
-    // the two window cells this lane converts: q = sub and q = sub + 16 -> (row lane, nibble shift)
-    const int vsrc0 = hbase + sub / 5, vsh0 = 4 * (sub % 5);
-    const int vsrc1 = hbase + (sub + 16) / 5, vsh1 = 4 * ((sub + 16) % 5);
+    const int vsrc0 = lt[16], vsh0 = lt[17], vsrc1 = lt[18], vsh1 = lt[19];
     const uint32_t s_dist = smem_u32(t.dist), s_pos = smem_u32(t.pos), s_visit = smem_u32(t.visit);
     const uint32_t s_onehot = smem_u32(t.onehot), s_rw32 = smem_u32(t.rw32), s_rw64 = smem_u32(t.rw64);
     constexpr uint64_t LOWPAD = kObstAll & ((1ull << (2 * R)) - 1ull);
     constexpr int NCH = 2;             // envs per half-warp and trip, interleaved for ILP
     const float4* src4 = reinterpret_cast<const float4*>(tile);
-
-    // ---- pipeline helpers.  Records + actions are prefetched two tiles ahead, windows one tile
-    // ahead, all with cp.async into shared memory: the prefetch holds no registers.
-    auto rec_buf = [&](int b) { return reinterpret_cast<uint4*>(scratch + 2 * win_bytes + 16 * D + b * EPW * 40); };
-    auto act_buf = [&](int b) { return reinterpret_cast<long long*>(scratch + 2 * win_bytes + 16 * D + b * EPW * 40 + EPW * 32); };
-    auto fetch_rec = [&](int es, int b) {              // tile starting at env es
-        if (lane < min(EPW, wend - es)) {
-            const size_t e = (size_t)es + lane;
-            cp_async16(smem_u32(rec_buf(b) + 2 * lane), p.rec + 2 * e);
-            cp_async16(smem_u32(rec_buf(b) + 2 * lane + 1), p.rec + 2 * e + 1);
-            cp_async8(smem_u32(act_buf(b) + lane), io.actions + e);
-        }
-        cp_async_commit();
-    };
-    // Window fetch of tile `tl` into buffer b.  LPE = 32/EPW lanes share one env: lane l serves
-    // env l % EPW and the 16-byte chunks l / EPW, + LPE, ... of its windows (TCH chunks of type
-    // rows, then 7 nibble rows).  The tile's records are already in rec_buf(b).
-    constexpr int LPE = 32 / EPW, TCH = TWR / 2;
-    auto issue_copies = [&](int es, int b) {
-        const int j = lane % EPW, k0 = lane / EPW;
-        const bool live = j < wend - es;                // the range's last tile may be short
-        const int x = live ? (int)(rec_buf(b)[2 * j].x & 0xff) : 0;
-        const size_t e = (size_t)es + j;
-        // grid rows x-R-1 .. x+R+1 are padded rows x+1 .. x+2R+3; start on the even row at or
-        // just below x+1 so that every chunk is 16-byte aligned
-        const int r0 = (x + 1) & ~1;
-        const uint64_t* tsrc = p.types + e * TS + r0;                       // TWR rows = TCH chunks
-        const uint32_t* vsrc = p.vis4 + e * VE + (size_t)x * VW;            // padded nibble rows x .. x+6
-        const uint32_t tdst = smem_u32(buf_twin(b) + j * TWR);
-        const uint32_t vdst = smem_u32(buf_vwin(b) + j * kVisWinRows * VW);
-#pragma unroll
-        for (int k = k0, i = 0; i < (TCH + kVisWinRows + LPE - 1) / LPE; ++i, k += LPE) {
-            if (!live) continue;
-            if (k < TCH) cp_async16(tdst + 16 * k, tsrc + 2 * k);
-            else if (k < TCH + kVisWinRows) cp_async16(vdst + 16 * (k - TCH), vsrc + 4 * (k - TCH));
-        }
-        cp_async_commit();
-    };
+    // window copy roles: 8 lanes per env of the trip, lane c8 serves chunks c8 and c8 + 8
+    const int cj = lane >> 3, c8 = lane & 7;
 
     if (wbase < wend) {
-        fetch_rec(wbase, 0);
         cp_async_wait_all();
         __syncwarp();
-        issue_copies(wbase, 0);
-        if (wbase + EPW < wend) fetch_rec(wbase + EPW, 1);
+        issue_target(wbase);
     }
 
-    int it = 0;
-    for (int e0 = wbase; e0 < wend; e0 += EPW, ++it) {
-        const int b = it & 1;
-        const int e_next = e0 + EPW;
+    for (int e0 = wbase; e0 < wend; e0 += kFastEnvs) {
+        const int e_next = e0 + kFastEnvs;
         const bool has_next = e_next < wend;
-        const int ts = min(EPW, wend - e0);               // envs in this tile (a multiple of 4)
+        const int ts = min(kFastEnvs, wend - e0);          // envs in this macro tile (a multiple of 4)
         const bool act = lane < ts;
-        uint64_t* twin = buf_twin(b);
-        uint32_t* vwin = buf_vwin(b);
         const size_t e = (size_t)e0 + lane;
-        cp_async_wait_all();                              // this tile's windows and the next tile's records
-        __syncwarp();                                     // have landed, for every lane of the warp
+        cp_async_wait_all();                              // records, actions and target words are here
+        __syncwarp();
 
-        // ---- phase A: transition out of shared memory, one lane per env
+        // ---- phase A: transition, one lane per env
         int done = 0, term = 0, trunc = 0;
         unsigned posw = 0;
         EnvRec r = {};
         if (act) {
-            uint4 ra = rec_buf(b)[2 * lane], rb = rec_buf(b)[2 * lane + 1];
-            const long long action = act_buf(b)[lane];
+            uint4 ra = recb[2 * lane], rb = recb[2 * lane + 1];
+            const long long action = actb[lane];
             r = unpack_rec(ra, rb);
-            const int x0 = r.x, r0 = (r.x + 1) & ~1;      // the windows are centred on the pre-move row
             int tx, ty; bool inb;
             action_target(r, action, G, tx, ty, inb);
-            // (tx, ty) is at most one cell away, so it is inside both windows even when it is
-            // outside the grid (wall padding / border nibbles)
-            uint64_t* tw = twin + lane * TWR + (tx + TP - r0);
-            const uint64_t word = *tw;
+            const uint64_t word = tgt_t[lane];
+            const uint32_t vword = tgt_v[lane];
             const int t_cell = inb ? cell_of(word, ty & 31) : kObstacle;
-            uint32_t* vw = vwin + (lane * kVisWinRows + (tx - x0 + 3)) * VW + ((ty + 2) >> 3);
             const int sh = nib_shift(ty);
-            const uint32_t vword = *vw;
             const StepOut o = transition_core(r, action, tx, ty, t_cell, (vword >> sh) & 15u, p.max_steps);
             if (o.moved)
-                *vw = bump_visit(p.vis4 + e * VE + nib_word(tx, ty, VW), vword, sh,
-                                 p.visov + e * G * G + tx * G + ty, mem);
-            if (o.watered) {
-                const uint64_t nw = word ^ (1ull << (2 * (ty & 31)));          // 3 -> 2
-                *tw = nw;
-                mem.st64(p.types + e * TS + TP + tx, nw);
-            }
+                bump_visit(p.vis4 + e * VE + nib_word(tx, ty, VW), vword, sh, p.visov + e * G * G + tx * G + ty, mem);
+            if (o.watered) mem.st64(p.types + e * TS + TP + tx, word ^ (1ull << (2 * (ty & 31))));   // 3 -> 2
             r.ret += lds_f64(s_rw64 + 8 * o.ridx);
             io.reward[e] = lds_f32(s_rw32 + 4 * o.ridx);
             term = o.terminated; trunc = o.truncated; done = term | trunc;
@@ -237,27 +213,52 @@ k_step_fast(const Params p, const StepIO io) {
                 p.term_rec[2 * e] = ra;
                 p.term_rec[2 * e + 1] = rb;
             }
-            // new position + where its windows start inside the fetched ones:
-            //   type row of grid row x'-R is padded row x'+2, i.e. fetched row x'+2-r0   (0..3)
-            //   nibble row of grid row x'-2 is padded row x'+1, i.e. fetched row x'+1-x0 (0..2)
-            // packed as x | y << 5 | first type row (lane * TWR + x'+2-r0) << 10 | first nibble row
-            // (lane * 7 + x'+1-x0) << 19, i.e. ready-made indices into the window buffers
-            posw = (unsigned)r.x | ((unsigned)r.y << 5) | ((unsigned)(lane * TWR + r.x + 2 - r0) << 10) |
-                   ((unsigned)(lane * kVisWinRows + r.x + 1 - x0) << 19);
+            posw = (unsigned)r.x | ((unsigned)r.y << 5);
         }
         accumulate_stats(p, act && done, r, term, trunc, lane);
-        __syncwarp();   // window patches are visible to the half-warps below
+        // orders the plane stores above before the window copies that other lanes issue below, and
+        // frees the record buffer
+        __syncwarp();
+        if (has_next) fetch_rec(e_next);
 
-        // the next tile's copies go out now and land while phase B runs
-        if (has_next) issue_copies(e_next, b ^ 1);
-        if (e_next + EPW < wend) fetch_rec(e_next + EPW, b);     // rec_buf(b) is free again
+        // Window copy of the trip starting at env e0 + base into buffer wb: grid rows x-R .. x+R
+        // are padded rows x+2 .. x+2R+2; start on the even row at or just below x+2 so that every
+        // chunk is 16-byte aligned.  Nibble rows x-2 .. x+2 are padded rows x+1 .. x+5.
+        auto issue_win = [&](int base, int wb) {
+            const int x = (int)(__shfl_sync(FULL, posw, base + cj) & 31u);
+            const size_t ej = (size_t)e0 + base + cj;
+            const uint64_t* tsrc = p.types + ej * TS + ((x + 2) & ~1);
+            const uint32_t* vsrc = p.vis4 + ej * VE + (size_t)(x + 1) * VW;
+            const uint32_t tdst = smem_u32(win_t(wb) + cj * TWR);
+            const uint32_t vdst = smem_u32(win_v(wb) + cj * kFastVisRows * VW);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int k = c8 + 8 * i;
+                if (k < TCH) cp_async16(tdst + 16 * k, tsrc + 2 * k);
+                else if (k < NCHUNK) cp_async16(vdst + 16 * (k - TCH), vsrc + 4 * (k - TCH));
+            }
+        };
+        issue_win(0, 0);
+        cp_async_commit();
 
-        // ---- phase B: observations.  Each trip builds four rows: two independent chains per
-        // half-warp, written stage by stage (all shared-memory reads of both chains, then the
-        // shuffles, then the table reads, then the stores) so that their latencies overlap.
+        // ---- phase B: observations, one trip = four rows: two independent chains per half-warp,
+        // written stage by stage so that their latencies overlap
         float4* const obs4 = reinterpret_cast<float4*>(io.obs) + (size_t)(e0 >> 2) * D;
+        int trip = 0;
 #pragma unroll 1
-        for (int base = 0; base < ts; base += 4) {
+        for (int base = 0; base < ts; base += kFastTrip, ++trip) {
+            const int wb = trip & 1;
+            // one commit group per trip (empty on the last one): after wait_group<1> everything
+            // but the copies just issued has landed -- this trip's windows, and from the second
+            // trip on the next macro tile's target words
+            if (base + kFastTrip < ts) issue_win(base + kFastTrip, wb ^ 1);
+            cp_async_commit();
+            cp_async_wait_group<1>();
+            __syncwarp();
+            if (trip == 0 && has_next) issue_target(e_next);     // its records landed with this trip's windows
+            const uint64_t* twin = win_t(wb);
+            const uint32_t* vwin = win_v(wb);
+
             int x[NCH], y[NCH], tb[NCH], vb[NCH];
             unsigned w[NCH], vslice[NCH], acc[NCH], s0[NCH], s1[NCH];
             uint64_t trow[NCH];
@@ -266,8 +267,10 @@ k_step_fast(const Params p, const StepIO io) {
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 const unsigned pw = __shfl_sync(FULL, posw, base + 2 * c + half);
-                x[c] = pw & 31; y[c] = (pw >> 5) & 31;
-                tb[c] = (pw >> 10) & 511; vb[c] = pw >> 19;
+                x[c] = pw & 31; y[c] = pw >> 5;
+                // first needed type row inside the fetched window: padded row x+2 minus the even start
+                tb[c] = (2 * c + half) * TWR + (x[c] & 1);
+                vb[c] = (2 * c + half) * kFastVisRows;
             }
             // stage 2: shared-memory reads: this lane's type row and visit-nibble words
 #pragma unroll
@@ -294,11 +297,9 @@ k_step_fast(const Params p, const StepIO io) {
                 acc[c] = 0;
             }
             // stage 4: LIDAR march (plantos_env.py:260-284): sample rr looks at window row
-            // srcl[rr], bits shf[rr]; visit cells come from the row lanes' slices
-#pragma unroll
-            // (far sample first: each step shifts the accumulator left by one cell and funnels the
-            // sample's two bits in from the top of the aligned row word -- two shifts per sample --
-            // so that sample rr ends up at bits 2rr, 2rr+1)
+            // srcl[rr], bits shf[rr].  Far sample first: each step shifts the accumulator left by
+            // one cell and funnels the sample's two bits in from the top of the aligned row word,
+            // so that sample rr ends up at bits 2rr, 2rr+1.
 #pragma unroll
             for (int rr = R - 1; rr >= 0; --rr) {
 #pragma unroll
@@ -347,13 +348,13 @@ k_step_fast(const Params p, const StepIO io) {
                 const int idx = q * 32 + lane;
                 if (idx < D) __stcs(dst4 + idx, src4[idx]);
             }
-            __syncwarp();
+            __syncwarp();   // the tile and this trip's window buffer may be overwritten now
         }
 
-        // ---- phase C: auto-reset of finished envs (rare; warp-cooperative generic code; the
-        // current window buffer is free now and serves as the type-plane scratch)
+        // ---- phase C: auto-reset of finished envs (rare; warp-cooperative generic code; window
+        // buffer 0 is free now and serves as the type-plane scratch)
         unsigned dmask = __ballot_sync(FULL, act && done);
-        uint64_t* plane = buf_twin(b);
+        uint64_t* plane = win_t(0);
         while (dmask) {
             const int j = __ffs(dmask) - 1;
             dmask &= dmask - 1;
@@ -382,9 +383,9 @@ k_step_fast(const Params p, const StepIO io) {
         }
     }
 
-    // ragged tail: envs beyond the last full tile, one at a time (no copies are in flight here)
+    // ragged tail: envs beyond the last 4-env group, one at a time (no copies are in flight here)
     if (gwarp == nwarps - 1)
-        for (int e = nfull; e < p.N; ++e) step_env_warp(p, t, io, e, buf_twin(0), tile, lane);
+        for (int e = nfull; e < p.N; ++e) step_env_warp(p, t, io, e, win_t(0), tile, lane);
 }
 
 }  // namespace plantos_dev

@@ -416,4 +416,34 @@ __global__ void k_stats_out(unsigned long long* acc, double* out, int clear) {
     if (clear) acc[i] = 0ull;
 }
 
+// Packs what the fast kernel's prologue needs (one block, after every table upload): the
+// shared-memory image of the tables, and for each of the 32 lanes its observation-phase constants
+//   srcl[rr] = lane of the half-warp holding window row x+dx of LIDAR sample rr of ray (lane & 15)
+//   shf[rr]  = left shift bringing column y+dy of that window word to bits 30, 31
+//   vsrc/vsh = source lane and nibble shift of the two 5x5 visit cells the lane converts.
+__global__ void k_pack_tables(const Params p, uint4* blob, int4* lane_tab) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int nbytes = tables_bytes(p.G, p.R, p.C);
+    // bytes between the tables are padding: zero them so that the image is deterministic
+    for (int i = threadIdx.x; i < (nbytes >> 4); i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const Tables t = load_tables(p, smem);
+    for (int i = threadIdx.x; i < (nbytes >> 4); i += blockDim.x) blob[i] = reinterpret_cast<const uint4*>(smem)[i];
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x, sub = lane & 15, hbase = lane & 16, R = p.R;
+        int v[4 * kLaneTabVec];
+        for (int i = 0; i < 4 * kLaneTabVec; ++i) v[i] = 0;
+        for (int rr = 0; rr < R && rr < 8; ++rr) {
+            int dx = 0, dy = 0;
+            if (sub < p.C) { dx = t.off[(sub * R + rr) * 2]; dy = t.off[(sub * R + rr) * 2 + 1]; }
+            v[rr] = hbase + dx + R;
+            v[8 + rr] = 30 - 2 * (dy + R);
+        }
+        v[16] = hbase + sub / 5; v[17] = 4 * (sub % 5);
+        v[18] = hbase + (sub + 16) / 5; v[19] = 4 * ((sub + 16) % 5);
+        for (int q = 0; q < kLaneTabVec; ++q)
+            lane_tab[lane * kLaneTabVec + q] = make_int4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+}
+
 }  // namespace plantos_dev

@@ -49,14 +49,14 @@ def test_fast_kernel_pipeline_replays_reference(name, replicas):
     assert res["bitexact_obs"] == 1 and res["bitexact_reward"] == 1
 
 
-@pytest.mark.parametrize("grid,epw", [(1, 4), (1, 8), (2, 16), (5, 8)])
-def test_fast_kernel_buffer_reuse(grid, epw, monkeypatch):
-    """Few persistent blocks => every warp walks several tiles, so both window buffers are
-    reused and the next-tile prefetch path runs (24 copies x 8 envs = 192 envs), for every
-    tile size the library instantiates."""
+@pytest.mark.parametrize("grid,replicas", [(1, 60), (2, 60), (1, 24), (5, 100)])
+def test_fast_kernel_buffer_reuse(grid, replicas, monkeypatch):
+    """Few persistent blocks => every warp walks several 32-env macro tiles (480 envs over 7
+    warps = tiles of 32, 32, 8; over 14 warps = 32, 4), so the record / target-word buffers and
+    both window buffers are reused and the next-tile prefetch path runs; (1, 24) and (5, 100)
+    are single short macro tiles of 28 and 24 envs."""
     monkeypatch.setenv("PLANTOS_FAST_GRID", str(grid))
-    monkeypatch.setenv("PLANTOS_EPW", str(epw))
-    res = _run("replay_T_8env", "fast", replicas=24, steps=1100)
+    res = _run("replay_T_8env", "fast", replicas=replicas, steps=1100)
     assert res["bitexact_obs"] == 1
 
 

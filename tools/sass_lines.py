@@ -2,7 +2,7 @@
 """Per-source-line SASS instruction counts of one kernel in libplantos_b200.so (needs -lineinfo).
 usage: tools/sass_lines.py <mangled-substring> [file-substring]"""
 import collections, os, re, subprocess, sys, tempfile
-so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "rl_env_b200/csrc/libplantos_b200.so")
+so = os.environ.get("PLANTOS_LIB") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "rl_env_b200/csrc/libplantos_b200.so")
 pat = sys.argv[1]; fsub = sys.argv[2] if len(sys.argv) > 2 else "plantos_fast"
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, check=True, capture_output=True)
