@@ -61,6 +61,7 @@ struct plantos {
     bool use_fast;
     fast_kernel_t fast_fn;
     int fast_grid;
+    bool use_pdl;
     uint4* d_table_blob;
     int4* d_lane_tab;
     int generic_grid, generic_smem;
@@ -272,7 +273,8 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     }
 
     // kernel selection
-    const bool fast_ok = (p.W == 1) && (p.VW == 4) && (p.G + p.R <= 32) && (2 * p.R + 1 <= 16) && (p.C <= 16);
+    const bool fast_ok = (p.W == 1) && (p.VW == 4) && (p.G + p.R <= 32) && (2 * p.R + 1 <= 16) && (p.C <= 16) &&
+                         (tables_bytes(p.G, p.R, p.C) >> 4) <= kFastWarps * 32;   // one 16-byte load per thread stages the tables
     h->use_fast = false;
     if (cfg->kernel != PLANTOS_KERNEL_GENERIC && fast_ok) {
         // L2 policy: PLANTOS_L2_KEEP=1 tags the state accesses evict_last inside a persisting-L2
@@ -308,6 +310,8 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
         const long long need = ((long long)p.N / 8 + kFastWarps - 1) / kFastWarps;
         if (blocks > need) blocks = need;
         h->fast_grid = (int)(blocks < 1 ? 1 : blocks);
+        h->use_pdl = true;
+        if (const char* s = std::getenv("PLANTOS_PDL")) h->use_pdl = std::atoi(s) != 0;
         const long long nwarps = (long long)h->fast_grid * kFastWarps, nfull = p.N & ~3;
         p.fast_q = (int)((((nfull + nwarps - 1) / nwarps) + 3) & ~3LL);
     }
@@ -400,7 +404,17 @@ extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, fl
     CUDA_TRY(cudaSetDevice(h->device));
     const bool aligned = (((uintptr_t)obs) & 15u) == 0;
     if (h->use_fast && aligned) {
-        h->fast_fn<<<h->fast_grid, kFastWarps * 32, h->fast_smem, (cudaStream_t)stream>>>(h->p, io);
+        // launched with programmatic stream serialization so that back-to-back steps overlap the
+        // next step's prologue with this step's tail (the kernel waits on griddepcontrol before it
+        // touches any state); PLANTOS_PDL=0 falls back to a plain launch
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)h->fast_grid); lc.blockDim = dim3(kFastWarps * 32);
+        lc.dynamicSmemBytes = (size_t)h->fast_smem; lc.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at; lc.numAttrs = h->use_pdl ? 1 : 0;
+        CUDA_TRY(cudaLaunchKernelEx(&lc, h->fast_fn, h->p, io));
     } else {
         if (h->cfg.kernel == PLANTOS_KERNEL_FAST)
             return fail(PLANTOS_EINVAL, "PLANTOS_KERNEL_FAST needs a 16-byte aligned obs buffer");

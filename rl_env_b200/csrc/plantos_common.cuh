@@ -222,14 +222,6 @@ __device__ __forceinline__ Tables tables_at(unsigned char* smem, int G, int R) {
     return t;
 }
 
-// Fast-kernel variant: the image was packed once by k_pack_tables, a block only copies it.
-__device__ __forceinline__ Tables load_table_blob(const Params& p, unsigned char* smem, int G, int R, int C) {
-    const int n16 = tables_bytes(G, R, C) >> 4;
-    for (int i = threadIdx.x; i < n16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = p.table_blob[i];
-    __syncthreads();
-    return tables_at(smem, G, R);
-}
-
 // Cooperative load by the whole block; ends with __syncthreads().
 __device__ inline Tables load_tables(const Params& p, unsigned char* smem) {
     double* rw64 = reinterpret_cast<double*>(smem);

@@ -76,6 +76,9 @@ __device__ __forceinline__ void cp_async8(uint32_t sdst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// programmatic dependent launch (PTX griddepcontrol): see the kernel prologue
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void cp_async4(uint32_t sdst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sdst), "l"(gsrc) : "memory");
 }
@@ -117,12 +120,18 @@ k_step_fast(const Params p, const StepIO io) {
     const int wbase = min(nfull, gwarp * p.fast_q), wend = min(nfull, wbase + p.fast_q);
 
     // ---- prefetch helpers (all cp.async into shared memory: a prefetch holds no registers)
+    // 32-bit shared-window addresses of this lane's copy destinations, computed once
+    const uint32_t s_scr = smem_u32(scratch);
+    const uint32_t s_rec = s_scr + 2 * win_bytes + 16 * D + 32 * lane;
+    const uint32_t s_act = s_scr + 2 * win_bytes + 16 * D + 32 * kFastEnvs + 8 * lane;
+    const uint32_t s_tgt_t = s_scr + 2 * win_bytes + 16 * D + 40 * kFastEnvs + 8 * lane;
+    const uint32_t s_tgt_v = s_scr + 2 * win_bytes + 16 * D + 48 * kFastEnvs + 4 * lane;
     auto fetch_rec = [&](int es) {                     // records + actions of the macro tile at es
         if (lane < min(kFastEnvs, wend - es)) {
             const size_t e = (size_t)es + lane;
-            cp_async16(smem_u32(recb + 2 * lane), p.rec + 2 * e);
-            cp_async16(smem_u32(recb + 2 * lane + 1), p.rec + 2 * e + 1);
-            cp_async8(smem_u32(actb + lane), io.actions + e);
+            cp_async16(s_rec, p.rec + 2 * e);
+            cp_async16(s_rec + 16, p.rec + 2 * e + 1);
+            cp_async8(s_act, io.actions + e);
         }
         cp_async_commit();
     };
@@ -135,13 +144,21 @@ k_step_fast(const Params p, const StepIO io) {
             int tx, ty; bool inb;
             action_target(q, actb[lane], G, tx, ty, inb);
             // (tx, ty) may be one cell outside the grid: wall rows / border nibbles are there
-            cp_async8(smem_u32(tgt_t + lane), p.types + e * TS + TP + tx);
-            cp_async4(smem_u32(tgt_v + lane), p.vis4 + e * VE + nib_word(tx, ty, VW));
+            cp_async8(s_tgt_t, p.types + e * TS + TP + tx);
+            cp_async4(s_tgt_v, p.vis4 + e * VE + nib_word(tx, ty, VW));
         }
         cp_async_commit();
     };
 
-    if (wbase < wend) fetch_rec(wbase);                // overlaps the table load
+    // Programmatic dependent launch: the next launch in the stream may become resident as soon as
+    // every block of this one has started, and everything above plus the loads of the immutable
+    // tables below may run while the previous launch is still finishing.  No env state, action or
+    // output buffer is touched before griddep_wait() returns (= the previous launch has completed
+    // and its writes are visible).
+    griddep_launch_dependents();
+    const int n16 = tables_bytes(G, R, C) >> 4;        // <= blockDim.x (checked on the host)
+    uint4 tab16 = make_uint4(0, 0, 0, 0);
+    if ((int)threadIdx.x < n16) tab16 = __ldg(p.table_blob + threadIdx.x);
     // ---- per-lane constants of the observation phase, precomputed by k_pack_tables:
     //   srcl[rr]  lane holding window row x+dx of LIDAR sample rr of this lane's ray
     //   shf[rr]   left shift that brings column y+dy of the window word to bits 30, 31
@@ -152,7 +169,11 @@ k_step_fast(const Params p, const StepIO io) {
         const int4 v = __ldg(p.lane_tab + lane * kLaneTabVec + q);
         lt[4 * q] = v.x; lt[4 * q + 1] = v.y; lt[4 * q + 2] = v.z; lt[4 * q + 3] = v.w;
     }
-    const Tables t = load_table_blob(p, smem, G, R, C);
+    griddep_wait();
+    if (wbase < wend) fetch_rec(wbase);                // in flight while the tables are staged
+    if ((int)threadIdx.x < n16) reinterpret_cast<uint4*>(smem)[threadIdx.x] = tab16;
+    __syncthreads();
+    const Tables t = tables_at(smem, G, R);
     const int sub = lane & 15, half = lane >> 4;
     int srcl[R], shf[R];
 #pragma unroll
@@ -164,8 +185,15 @@ k_step_fast(const Params p, const StepIO io) {
     constexpr uint64_t LOWPAD = kObstAll & ((1ull << (2 * R)) - 1ull);
     constexpr int NCH = 2;             // envs per half-warp and trip, interleaved for ILP
     const float4* src4 = reinterpret_cast<const float4*>(tile);
-    // window copy roles: 8 lanes per env of the trip, lane c8 serves chunks c8 and c8 + 8
+    // Window copy roles: 8 lanes per env of the trip, lane c8 serves chunks c8 and c8 + 8 of env
+    // cj (chunks 0 .. TCH-1 are type rows, TCH .. NCHUNK-1 nibble rows; the second round is always
+    // a nibble row because TCH <= 8).  Destination offsets inside a window buffer and the source
+    // element offsets relative to the env's first fetched row are per-lane constants.
     const int cj = lane >> 3, c8 = lane & 7;
+    const bool cp0_type = c8 < TCH, cp1_on = c8 + 8 < NCHUNK;
+    const uint32_t cp0_dst = s_scr + (cp0_type ? cj * TWR * 8 + 16 * c8
+                                               : kFastTrip * TWR * 8 + cj * kFastVisRows * 16 + 16 * (c8 - TCH));
+    const uint32_t cp1_dst = s_scr + kFastTrip * TWR * 8 + cj * kFastVisRows * 16 + 16 * (c8 + 8 - TCH);
 
     if (wbase < wend) {
         cp_async_wait_all();
@@ -227,16 +255,11 @@ k_step_fast(const Params p, const StepIO io) {
         auto issue_win = [&](int base, int wb) {
             const int x = (int)(__shfl_sync(FULL, posw, base + cj) & 31u);
             const size_t ej = (size_t)e0 + base + cj;
-            const uint64_t* tsrc = p.types + ej * TS + ((x + 2) & ~1);
-            const uint32_t* vsrc = p.vis4 + ej * VE + (size_t)(x + 1) * VW;
-            const uint32_t tdst = smem_u32(win_t(wb) + cj * TWR);
-            const uint32_t vdst = smem_u32(win_v(wb) + cj * kFastVisRows * VW);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int k = c8 + 8 * i;
-                if (k < TCH) cp_async16(tdst + 16 * k, tsrc + 2 * k);
-                else if (k < NCHUNK) cp_async16(vdst + 16 * (k - TCH), vsrc + 4 * (k - TCH));
-            }
+            const uint64_t* tsrc = p.types + ej * TS + ((x + 2) & ~1) + 2 * c8;
+            const uint32_t* vsrc = p.vis4 + ej * VE + (x + 1 + c8 - TCH) * VW;       // round 0 row; round 1 is 8 rows on
+            const uint32_t boff = wb * win_bytes;
+            cp_async16(cp0_dst + boff, cp0_type ? (const void*)tsrc : (const void*)vsrc);
+            if (cp1_on) cp_async16(cp1_dst + boff, vsrc + 8 * VW);
         };
         issue_win(0, 0);
         cp_async_commit();
