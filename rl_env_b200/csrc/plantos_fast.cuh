@@ -44,8 +44,14 @@ constexpr int kFastVisRows = 5;       // nibble rows x-2 .. x+2
 
 // type rows fetched per env: x-R .. x+R (2R+1 rows) plus one because the copy starts on an even row
 __host__ __device__ constexpr int fast_type_rows(int R) { return 2 * R + 2; }
+// A window buffer holds the 16-byte chunks of the 4 envs of a trip: chunk k of env j (k < TCH: type
+// rows 2k, 2k+1; then the 5 nibble rows) sits at j*128 + 16k for k < 8 and at
+// 512 + j*S1 + 16(k-8) otherwise (S1 = 16 * (chunks beyond 8)).  The 8 lanes that copy one env thus
+// write 128 contiguous bytes per round: the cp.async shared-memory writes are bank-conflict free
+// (the type-major layout before measured 9.8 wavefronts per copy instruction instead of 4).
+__host__ __device__ constexpr int fast_win_s1(int R) { return (R + 1 + 5 > 8 ? R + 1 + 5 - 8 : 0) * 16; }
 __host__ __device__ inline int fast_win_bytes(int R, int G) {
-    const int win = kFastTrip * (fast_type_rows(R) * 8 + kFastVisRows * 16);
+    const int win = 512 + kFastTrip * fast_win_s1(R);
     return win < align_up(G * 8, 16) ? align_up(G * 8, 16) : win;    // phase C borrows it as a type plane
 }
 // per-warp scratch: two window buffers | 4-env obs tile | 32 records | 32 actions | 32+32 target words
@@ -85,6 +91,16 @@ __device__ __forceinline__ void cp_async4(uint32_t sdst, const void* gsrc) {
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
+// -DPLANTOS_EXP_TIMING builds an instrumented library (tools/exp_timing.py): lane 0 of every warp
+// records %globaltimer at the phase boundaries of its first macro tile and parks the stamps in the
+// ret fields of the terminal-record snapshot.  Never defined in the shipped build.
+#ifdef PLANTOS_EXP_TIMING
+__device__ __forceinline__ unsigned gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (unsigned)t; }
+#define TSTAMP(k) do { if (lane == 0) ts_[k] = gtime(); } while (0)
+#else
+#define TSTAMP(k) do {} while (0)
+#endif
+
 template <int R, int C, bool KEEP>
 __global__ void __launch_bounds__(kFastWarps * 32, PLANTOS_FAST_MINBLOCKS)
 k_step_fast(const Params p, const StepIO io) {
@@ -102,6 +118,10 @@ k_step_fast(const Params p, const StepIO io) {
     extern __shared__ __align__(16) unsigned char smem[];
     typename std::conditional<KEEP, KeepMem, PlainMem>::type const mem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#ifdef PLANTOS_EXP_TIMING
+    unsigned ts_[10] = {};
+#endif
+    TSTAMP(0);
     const int G = p.G, VE = p.VE, TS = p.TS;
     const int win_bytes = fast_win_bytes(R, G);
     unsigned char* scratch = smem + tables_bytes(G, R, C) + warp * fast_warp_scratch_bytes(R, G, D);
@@ -110,8 +130,7 @@ k_step_fast(const Params p, const StepIO io) {
     long long* const actb = reinterpret_cast<long long*>(recb + 2 * kFastEnvs);                   // [32]
     uint64_t* const tgt_t = reinterpret_cast<uint64_t*>(actb + kFastEnvs);                        // [32]
     uint32_t* const tgt_v = reinterpret_cast<uint32_t*>(tgt_t + kFastEnvs);                       // [32]
-    auto win_t = [&](int b) { return reinterpret_cast<uint64_t*>(scratch + b * win_bytes); };                              // [4][TWR]
-    auto win_v = [&](int b) { return reinterpret_cast<uint32_t*>(scratch + b * win_bytes + kFastTrip * TWR * 8); };          // [4][5][4]
+    auto win_buf = [&](int b) { return scratch + b * win_bytes; };
 
     // Every warp owns one contiguous range of Q envs (Q a multiple of 4, the same for all warps).
     // (Q = p.fast_q is computed on the host for this grid.)
@@ -170,6 +189,7 @@ k_step_fast(const Params p, const StepIO io) {
         lt[4 * q] = v.x; lt[4 * q + 1] = v.y; lt[4 * q + 2] = v.z; lt[4 * q + 3] = v.w;
     }
     griddep_wait();
+    TSTAMP(1);
     if (wbase < wend) fetch_rec(wbase);                // in flight while the tables are staged
     if ((int)threadIdx.x < n16) reinterpret_cast<uint4*>(smem)[threadIdx.x] = tab16;
     __syncthreads();
@@ -181,7 +201,7 @@ k_step_fast(const Params p, const StepIO io) {
     const bool has_row = sub < NROW, has_ray = sub < C, has_vrow = sub < 5, has_v1 = sub < 9;
     const int vsrc0 = lt[16], vsh0 = lt[17], vsrc1 = lt[18], vsh1 = lt[19];
     const uint32_t s_dist = smem_u32(t.dist), s_pos = smem_u32(t.pos), s_visit = smem_u32(t.visit);
-    const uint32_t s_onehot = smem_u32(t.onehot), s_rw32 = smem_u32(t.rw32), s_rw64 = smem_u32(t.rw64);
+    const uint32_t s_rw32 = smem_u32(t.rw32), s_rw64 = smem_u32(t.rw64);
     constexpr uint64_t LOWPAD = kObstAll & ((1ull << (2 * R)) - 1ull);
     constexpr int NCH = 2;             // envs per half-warp and trip, interleaved for ILP
     const float4* src4 = reinterpret_cast<const float4*>(tile);
@@ -190,14 +210,24 @@ k_step_fast(const Params p, const StepIO io) {
     // a nibble row because TCH <= 8).  Destination offsets inside a window buffer and the source
     // element offsets relative to the env's first fetched row are per-lane constants.
     const int cj = lane >> 3, c8 = lane & 7;
-    const bool cp0_type = c8 < TCH, cp1_on = c8 + 8 < NCHUNK;
-    const uint32_t cp0_dst = s_scr + (cp0_type ? cj * TWR * 8 + 16 * c8
-                                               : kFastTrip * TWR * 8 + cj * kFastVisRows * 16 + 16 * (c8 - TCH));
-    const uint32_t cp1_dst = s_scr + kFastTrip * TWR * 8 + cj * kFastVisRows * 16 + 16 * (c8 + 8 - TCH);
+    constexpr int S1 = fast_win_s1(R);
+    const bool cp0_type = c8 < TCH, cp0_on = c8 < NCHUNK, cp1_on = c8 + 8 < NCHUNK;
+    const uint32_t cp0_dst = s_scr + cj * 128 + 16 * c8;
+    const uint32_t cp1_dst = s_scr + 512 + cj * S1 + 16 * c8;
+    // byte offset inside a window buffer of nibble row `sub` (chunk TCH + sub) of the two envs this
+    // half-warp handles in a trip (env 2c + half)
+    int voff[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int j = 2 * c + (lane >> 4), kk = TCH + (lane & 15);
+        voff[c] = kk < 8 ? j * 128 + 16 * kk : 512 + j * S1 + 16 * (kk - 8);
+    }
 
+    TSTAMP(2);
     if (wbase < wend) {
         cp_async_wait_all();
         __syncwarp();
+        TSTAMP(3);
         issue_target(wbase);
     }
 
@@ -209,6 +239,7 @@ k_step_fast(const Params p, const StepIO io) {
         const size_t e = (size_t)e0 + lane;
         cp_async_wait_all();                              // records, actions and target words are here
         __syncwarp();
+        TSTAMP(4);
 
         // ---- phase A: transition, one lane per env
         int done = 0, term = 0, trunc = 0;
@@ -247,6 +278,7 @@ k_step_fast(const Params p, const StepIO io) {
         // orders the plane stores above before the window copies that other lanes issue below, and
         // frees the record buffer
         __syncwarp();
+        TSTAMP(5);
         if (has_next) fetch_rec(e_next);
 
         // Window copy of the trip starting at env e0 + base into buffer wb: grid rows x-R .. x+R
@@ -258,7 +290,7 @@ k_step_fast(const Params p, const StepIO io) {
             const uint64_t* tsrc = p.types + ej * TS + ((x + 2) & ~1) + 2 * c8;
             const uint32_t* vsrc = p.vis4 + ej * VE + (x + 1 + c8 - TCH) * VW;       // round 0 row; round 1 is 8 rows on
             const uint32_t boff = wb * win_bytes;
-            cp_async16(cp0_dst + boff, cp0_type ? (const void*)tsrc : (const void*)vsrc);
+            if (cp0_on) cp_async16(cp0_dst + boff, cp0_type ? (const void*)tsrc : (const void*)vsrc);
             if (cp1_on) cp_async16(cp1_dst + boff, vsrc + 8 * VW);
         };
         issue_win(0, 0);
@@ -278,11 +310,12 @@ k_step_fast(const Params p, const StepIO io) {
             cp_async_commit();
             cp_async_wait_group<1>();
             __syncwarp();
+            if (trip == 0) TSTAMP(6);
             if (trip == 0 && has_next) issue_target(e_next);     // its records landed with this trip's windows
-            const uint64_t* twin = win_t(wb);
-            const uint32_t* vwin = win_v(wb);
+            const unsigned char* const wbuf = win_buf(wb);
+            const uint64_t* twin = reinterpret_cast<const uint64_t*>(wbuf);
 
-            int x[NCH], y[NCH], tb[NCH], vb[NCH];
+            int x[NCH], y[NCH], tb[NCH];
             unsigned w[NCH], vslice[NCH], acc[NCH], s0[NCH], s1[NCH];
             uint64_t trow[NCH];
             unsigned vlo[NCH], vhi[NCH];
@@ -292,8 +325,7 @@ k_step_fast(const Params p, const StepIO io) {
                 const unsigned pw = __shfl_sync(FULL, posw, base + 2 * c + half);
                 x[c] = pw & 31; y[c] = pw >> 5;
                 // first needed type row inside the fetched window: padded row x+2 minus the even start
-                tb[c] = (2 * c + half) * TWR + (x[c] & 1);
-                vb[c] = (2 * c + half) * kFastVisRows;
+                tb[c] = (2 * c + half) * 16 + (x[c] & 1);       // 128 bytes per env
             }
             // stage 2: shared-memory reads: this lane's type row and visit-nibble words
 #pragma unroll
@@ -305,7 +337,7 @@ k_step_fast(const Params p, const StepIO io) {
                     // the 5 nibbles y .. y+4 start in word y>>3 and may spill into the next one
                     // (when they sit entirely in word 3 the funnel's high half is unused)
                     const unsigned w0 = (unsigned)y[c] >> 3, w1 = w0 < 3u ? w0 + 1u : 3u;
-                    const uint32_t* vr = vwin + (vb[c] + sub) * VW;
+                    const uint32_t* vr = reinterpret_cast<const uint32_t*>(wbuf + voff[c]);
                     vlo[c] = vr[w0]; vhi[c] = vr[w1];
                 }
             }
@@ -346,7 +378,10 @@ k_step_fast(const Params p, const StepIO io) {
                 const int dist = m ? (bit >> 1) + 1 : R;
                 const int kind = m ? (acc[c] >> bit) & 3 : kEmpty;
                 fd[c] = lds_f32(s_dist + 4 * dist);
-                oh[c] = lds_f32x4(s_onehot + 16 * kind);
+                // one-hot of the hit kind by compares: a 128-bit table read would cost four
+                // shared-memory wavefronts, and this phase is bound by those, not by issue slots
+                oh[c].x = kind == 0 ? 1.0f : 0.0f; oh[c].y = kind == 1 ? 1.0f : 0.0f;
+                oh[c].z = kind == 2 ? 1.0f : 0.0f; oh[c].w = kind == 3 ? 1.0f : 0.0f;
                 fp[c] = lds_f32(s_pos + 4 * (sub ? y[c] : x[c]));
                 fv0[c] = lds_f32(s_visit + 4 * ((s0[c] >> vsh0) & 15u));
                 fv1[c] = lds_f32(s_visit + 4 * ((s1[c] >> vsh1) & 15u));
@@ -372,12 +407,23 @@ k_step_fast(const Params p, const StepIO io) {
                 if (idx < D) __stcs(dst4 + idx, src4[idx]);
             }
             __syncwarp();   // the tile and this trip's window buffer may be overwritten now
+            if (trip == 0) TSTAMP(7);
         }
+        TSTAMP(8);
+#ifdef PLANTOS_EXP_TIMING
+        { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); ts_[9] = sm; }
+        if (lane == 0 && ts >= 8)
+            for (int k = 0; k < 5; ++k) {
+                uint4 v = p.term_rec[2 * ((size_t)e0 + k) + 1];
+                v.z = ts_[2 * k]; v.w = ts_[2 * k + 1];
+                p.term_rec[2 * ((size_t)e0 + k) + 1] = v;
+            }
+#endif
 
         // ---- phase C: auto-reset of finished envs (rare; warp-cooperative generic code; window
         // buffer 0 is free now and serves as the type-plane scratch)
         unsigned dmask = __ballot_sync(FULL, act && done);
-        uint64_t* plane = win_t(0);
+        uint64_t* plane = reinterpret_cast<uint64_t*>(win_buf(0));
         while (dmask) {
             const int j = __ffs(dmask) - 1;
             dmask &= dmask - 1;
@@ -408,7 +454,7 @@ k_step_fast(const Params p, const StepIO io) {
 
     // ragged tail: envs beyond the last 4-env group, one at a time (no copies are in flight here)
     if (gwarp == nwarps - 1)
-        for (int e = nfull; e < p.N; ++e) step_env_warp(p, t, io, e, win_t(0), tile, lane);
+        for (int e = nfull; e < p.N; ++e) step_env_warp(p, t, io, e, reinterpret_cast<uint64_t*>(win_buf(0)), tile, lane);
 }
 
 }  // namespace plantos_dev
