@@ -301,7 +301,7 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
         return fail(PLANTOS_EINVAL, "PLANTOS_KERNEL_FAST requested but (G, R, C) has no fast-kernel instantiation");
     }
     h->generic_smem = tables_bytes(p.G, p.R, p.C) + kGenericWarps * generic_warp_scratch_bytes(p.G, p.W, p.D);
-    h->fast_smem = tables_bytes(p.G, p.R, p.C) + fast_share_bytes() + kFastWarps * fast_warp_scratch_bytes(p.R, p.G, p.D);
+    h->fast_smem = tables_bytes(p.G, p.R, p.C) + kFastWarps * fast_warp_scratch_bytes(p.R, p.G, p.D);
     if (h->use_fast) {
         // persistent grid: at most PLANTOS_FAST_MINBLOCKS blocks per SM, each warp walks its own
         // contiguous env range (at least 8 envs per warp when there are few envs)

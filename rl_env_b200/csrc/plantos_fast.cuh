@@ -32,11 +32,11 @@
 namespace plantos_dev {
 
 #ifndef PLANTOS_FAST_MINBLOCKS
-#define PLANTOS_FAST_MINBLOCKS 1
+#define PLANTOS_FAST_MINBLOCKS 4
 #endif
 #ifndef PLANTOS_FAST_WARPS
-#define PLANTOS_FAST_WARPS 28         // one block of 28 warps per SM (<= 72 registers each): the block-wide
-#endif                                // trip queue of the last round then balances the whole SM
+#define PLANTOS_FAST_WARPS 7          // 7 warps x 4 blocks = 28 resident warps per SM (<= 72 registers each)
+#endif
 constexpr int kFastWarps = PLANTOS_FAST_WARPS;
 constexpr int kFastEnvs = 32;         // envs per macro tile (one lane each in the transition)
 constexpr int kFastTrip = 4;          // envs per observation trip
@@ -58,11 +58,6 @@ __host__ __device__ inline int fast_win_bytes(int R, int G) {
 __host__ __device__ inline int fast_warp_scratch_bytes(int R, int G, int D) {
     return 2 * fast_win_bytes(R, G) + 16 * D + kFastEnvs * (32 + 8 + 8 + 4);
 }
-
-// Block-shared trip queues of the observation phase (after the tables): for every warp of the
-// block the positions of its macro tile's envs, the tile's first env / size / done mask, a ready
-// flag and a completion counter; plus the block's claim counter.
-__host__ __device__ constexpr int fast_share_bytes() { return kFastWarps * (32 * 4 + 5 * 4) + 16; }
 
 // ---- asynchronous global->shared copies (16-byte cp.async, L2 only) ------------------------
 // Records, target words and windows sit at per-env addresses, so they are fetched with per-lane
@@ -129,14 +124,7 @@ k_step_fast(const Params p, const StepIO io) {
     TSTAMP(0);
     const int G = p.G, VE = p.VE, TS = p.TS;
     const int win_bytes = fast_win_bytes(R, G);
-    unsigned* const q_posw = reinterpret_cast<unsigned*>(smem + tables_bytes(G, R, C));      // [warps][32]
-    int* const q_e0 = reinterpret_cast<int*>(q_posw + kFastWarps * 32);                       // [warps] each
-    int* const q_ts = q_e0 + kFastWarps;
-    int* const q_dmask = q_ts + kFastWarps;
-    int* const q_ready = q_dmask + kFastWarps;
-    int* const q_done = q_ready + kFastWarps;
-    int* const q_counter = q_done + kFastWarps;
-    unsigned char* scratch = smem + tables_bytes(G, R, C) + fast_share_bytes() + warp * fast_warp_scratch_bytes(R, G, D);
+    unsigned char* scratch = smem + tables_bytes(G, R, C) + warp * fast_warp_scratch_bytes(R, G, D);
     float* tile = reinterpret_cast<float*>(scratch + 2 * win_bytes);
     uint4* const recb = reinterpret_cast<uint4*>(scratch + 2 * win_bytes + 16 * D);             // [32][2]
     long long* const actb = reinterpret_cast<long long*>(recb + 2 * kFastEnvs);                   // [32]
@@ -204,7 +192,6 @@ k_step_fast(const Params p, const StepIO io) {
     TSTAMP(1);
     if (wbase < wend) fetch_rec(wbase);                // in flight while the tables are staged
     if ((int)threadIdx.x < n16) reinterpret_cast<uint4*>(smem)[threadIdx.x] = tab16;
-    for (int i = threadIdx.x; i < 5 * kFastWarps + 4; i += blockDim.x) q_e0[i] = 0;     // queue heads, flags, counter
     __syncthreads();
     const Tables t = tables_at(smem, G, R);
     const int sub = lane & 15, half = lane >> 4;
@@ -244,21 +231,10 @@ k_step_fast(const Params p, const StepIO io) {
         issue_target(wbase);
     }
 
-    // Rounds: in round rd every warp runs the transition of its rd-th macro tile and publishes the
-    // new positions; the observation trips of the tile are then claimed from trip queues.  Up to the
-    // last round a warp claims only its own trips, in order (a static software pipeline).  In the
-    // LAST round only the first two trips of every tile stay with the owner; the others go to one
-    // block-wide queue (trip k of every warp before trip k+1 of any) that all warps of the block
-    // drain, so that the warps the SM's arbiter favours do not finish early and leave the slow ones
-    // to run alone: measured, the within-SM spread of finishing times was 6.7 us of a 25 us step.
-    const int nrounds = (p.fast_q + kFastEnvs - 1) / kFastEnvs;
-    constexpr int kTripsPerTile = kFastEnvs / kFastTrip, kOwnTrips = 2;
-    for (int rd = 0; rd < nrounds; ++rd) {
-        const int e0 = wbase + rd * kFastEnvs;            // may be >= wend: an empty tile (ts = 0)
+    for (int e0 = wbase; e0 < wend; e0 += kFastEnvs) {
         const int e_next = e0 + kFastEnvs;
         const bool has_next = e_next < wend;
-        const bool last_round = rd == nrounds - 1;
-        const int ts = max(0, min(kFastEnvs, wend - e0));  // envs in this macro tile (a multiple of 4)
+        const int ts = min(kFastEnvs, wend - e0);          // envs in this macro tile (a multiple of 4)
         const bool act = lane < ts;
         const size_t e = (size_t)e0 + lane;
         cp_async_wait_all();                              // records, actions and target words are here
@@ -299,72 +275,43 @@ k_step_fast(const Params p, const StepIO io) {
             posw = (unsigned)r.x | ((unsigned)r.y << 5);
         }
         accumulate_stats(p, act && done, r, term, trunc, lane);
-        unsigned dmask = __ballot_sync(FULL, act && done);
-        // publish the tile for the observation phase
-        q_posw[warp * 32 + lane] = posw;
-        if (lane == 0) { q_e0[warp] = e0; q_ts[warp] = ts; q_dmask[warp] = (int)dmask; }
-        if (last_round) __threadfence_block();            // plane stores + queue entry before the ready flag
-        // (the barrier also orders the plane stores above before the window copies that other lanes
-        // issue below, and frees the record buffer)
+        // orders the plane stores above before the window copies that other lanes issue below, and
+        // frees the record buffer
         __syncwarp();
-        if (last_round && lane == 0) *reinterpret_cast<volatile int*>(q_ready + warp) = 1;
         TSTAMP(5);
         if (has_next) fetch_rec(e_next);
 
-        // ---- trip claims
-        int own_next = 0;
-        const int own_end = last_round ? min(kOwnTrips * kFastTrip, ts) : ts;
-        auto next_claim = [&](int& cw, int& cb) -> bool {
-            if (own_next < own_end) { cw = warp; cb = own_next; own_next += kFastTrip; return true; }
-            if (!last_round) return false;
-            for (;;) {
-                int tq = 0;
-                if (lane == 0) tq = atomicAdd(q_counter, 1);
-                tq = __shfl_sync(FULL, tq, 0);
-                if (tq >= kFastWarps * (kTripsPerTile - kOwnTrips)) return false;
-                const int w = tq % kFastWarps, k = kOwnTrips + tq / kFastWarps;
-                if (lane == 0)
-                    while (*reinterpret_cast<volatile int*>(q_ready + w) == 0) __nanosleep(64);
-                __syncwarp();
-                __threadfence_block();
-                if (k * kFastTrip < *reinterpret_cast<volatile int*>(q_ts + w)) { cw = w; cb = k * kFastTrip; return true; }
-            }
-        };
-        // Window copy of the trip (tile of warp cw, envs cb .. cb+3) into buffer wb: grid rows
-        // x-R .. x+R are padded rows x+2 .. x+2R+2; start on the even row at or just below x+2 so
-        // that every chunk is 16-byte aligned.  Nibble rows x-2 .. x+2 are padded rows x+1 .. x+5.
-        auto issue_win = [&](int cw, int cb, int wb) {
-            const int x = (int)(q_posw[cw * 32 + cb + cj] & 31u);
-            const size_t ej = (size_t)q_e0[cw] + cb + cj;
+        // Window copy of the trip starting at env e0 + base into buffer wb: grid rows x-R .. x+R
+        // are padded rows x+2 .. x+2R+2; start on the even row at or just below x+2 so that every
+        // chunk is 16-byte aligned.  Nibble rows x-2 .. x+2 are padded rows x+1 .. x+5.
+        auto issue_win = [&](int base, int wb) {
+            const int x = (int)(__shfl_sync(FULL, posw, base + cj) & 31u);
+            const size_t ej = (size_t)e0 + base + cj;
             const uint64_t* tsrc = p.types + ej * TS + ((x + 2) & ~1) + 2 * c8;
             const uint32_t* vsrc = p.vis4 + ej * VE + (x + 1 + c8 - TCH) * VW;       // round 0 row; round 1 is 8 rows on
             const uint32_t boff = wb * win_bytes;
             if (cp0_on) cp_async16(cp0_dst + boff, cp0_type ? (const void*)tsrc : (const void*)vsrc);
             if (cp1_on) cp_async16(cp1_dst + boff, vsrc + 8 * VW);
         };
+        issue_win(0, 0);
+        cp_async_commit();
 
         // ---- phase B: observations, one trip = four rows: two independent chains per half-warp,
         // written stage by stage so that their latencies overlap
-        int cw = 0, cb = 0, wb = 0;
-        bool have = next_claim(cw, cb), first = true;
-        if (have) issue_win(cw, cb, 0);
-        cp_async_commit();
+        float4* const obs4 = reinterpret_cast<float4*>(io.obs) + (size_t)(e0 >> 2) * D;
+        int trip = 0;
 #pragma unroll 1
-        while (have) {
-            // one commit group per trip (empty when there is no next claim): after wait_group<1>
-            // everything but the copies just issued has landed -- this trip's windows, and from the
-            // second trip on the next macro tile's target words
-            int nw = 0, nb = 0;
-            const bool have_next_trip = next_claim(nw, nb);
-            if (have_next_trip) issue_win(nw, nb, wb ^ 1);
+        for (int base = 0; base < ts; base += kFastTrip, ++trip) {
+            const int wb = trip & 1;
+            // one commit group per trip (empty on the last one): after wait_group<1> everything
+            // but the copies just issued has landed -- this trip's windows, and from the second
+            // trip on the next macro tile's target words
+            if (base + kFastTrip < ts) issue_win(base + kFastTrip, wb ^ 1);
             cp_async_commit();
             cp_async_wait_group<1>();
             __syncwarp();
-            if (first) TSTAMP(6);
-            if (first && has_next) issue_target(e_next);     // its records landed with this trip's windows
-            const int base = cb;
-            float4* const obs4 = reinterpret_cast<float4*>(io.obs) + (size_t)(q_e0[cw] >> 2) * D;
-            const unsigned* const pos_q = q_posw + cw * 32 + cb;
+            if (trip == 0) TSTAMP(6);
+            if (trip == 0 && has_next) issue_target(e_next);     // its records landed with this trip's windows
             const unsigned char* const wbuf = win_buf(wb);
             const uint64_t* twin = reinterpret_cast<const uint64_t*>(wbuf);
 
@@ -375,7 +322,7 @@ k_step_fast(const Params p, const StepIO io) {
             // stage 1: positions of the two envs this half-warp handles (env base + 2c + half)
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                const unsigned pw = pos_q[2 * c + half];
+                const unsigned pw = __shfl_sync(FULL, posw, base + 2 * c + half);
                 x[c] = pw & 31; y[c] = pw >> 5;
                 // first needed type row inside the fetched window: padded row x+2 minus the even start
                 tb[c] = (2 * c + half) * 16 + (x[c] & 1);       // 128 bytes per env
@@ -460,15 +407,7 @@ k_step_fast(const Params p, const StepIO io) {
                 if (idx < D) __stcs(dst4 + idx, src4[idx]);
             }
             __syncwarp();   // the tile and this trip's window buffer may be overwritten now
-            if (first) TSTAMP(7);
-            first = false;
-            if (last_round) {
-                // completion signal to the tile's owner; when the owner is going to rewrite rows of
-                // this trip (auto-reset), the row stores above must be ordered before it
-                if ((q_dmask[cw] >> cb) & 15) { __threadfence_block(); __syncwarp(); }
-                if (lane == 0) atomicAdd(q_done + cw, 1);
-            }
-            have = have_next_trip; cw = nw; cb = nb; wb ^= 1;
+            if (trip == 0) TSTAMP(7);
         }
         TSTAMP(8);
 #ifdef PLANTOS_EXP_TIMING
@@ -482,14 +421,8 @@ k_step_fast(const Params p, const StepIO io) {
 #endif
 
         // ---- phase C: auto-reset of finished envs (rare; warp-cooperative generic code; window
-        // buffer 0 is free now and serves as the type-plane scratch).  In the last round other
-        // warps may still be building rows of this tile: wait for all of its trips first.
-        if (last_round && dmask) {
-            if (lane == 0)
-                while (*reinterpret_cast<volatile int*>(q_done + warp) < ts / kFastTrip) __nanosleep(64);
-            __syncwarp();
-            __threadfence_block();
-        }
+        // buffer 0 is free now and serves as the type-plane scratch)
+        unsigned dmask = __ballot_sync(FULL, act && done);
         uint64_t* plane = reinterpret_cast<uint64_t*>(win_buf(0));
         while (dmask) {
             const int j = __ffs(dmask) - 1;
