@@ -91,6 +91,20 @@ def test_lockstep_default_preset_ragged(kernel):
     assert _lockstep(DFLT_KW, 1027, 120, 50, kernel, seed=4) >= 2 * 1027
 
 
+@pytest.mark.parametrize("r,c", [(4, 16), (4, 8)])
+def test_lockstep_other_fast_instantiations(r, c):
+    # the remaining (R, C) shapes the fast kernel is instantiated for, ragged N, frequent resets
+    kw = dict(grid_size=14, num_plants=5, num_obstacles=9, lidar_range=r, lidar_channels=c)
+    assert _lockstep(kw, 1543, 140, 35, "fast", seed=8) >= 3 * 1543
+
+
+def test_lockstep_fast_many_rounds_per_warp(monkeypatch):
+    # two persistent blocks => every warp walks ~9 macro tiles of 32 envs (steady-state prefetch of the
+    # next tile's records and target words, short last tile), with auto-resets in between
+    monkeypatch.setenv("PLANTOS_FAST_GRID", "2")
+    assert _lockstep(T_KW, 4000, 130, 45, "fast", seed=9) >= 2 * 4000
+
+
 def test_lockstep_xl_stress():
     assert _lockstep(XL_KW, 256, 90, 40, "generic", seed=5, check_planes_every=30) >= 2 * 256
 
