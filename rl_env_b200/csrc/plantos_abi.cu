@@ -10,6 +10,7 @@
 
 #include "../../include/plantos.h"
 #include "plantos_fast.cuh"
+#include "plantos_lane.cuh"
 
 using namespace plantos_dev;
 
@@ -41,6 +42,28 @@ const FastVariant kFastVariants[] = {
     FAST_ROW(4, 8),
 };
 
+#define LANE_ROW(R_, C_) {R_, C_, 0, k_step_lane<R_, C_, false>}, {R_, C_, 1, k_step_lane<R_, C_, true>}
+const FastVariant kLaneVariants[] = { LANE_ROW(6, 16), LANE_ROW(2, 10), LANE_ROW(4, 16), LANE_ROW(4, 8) };
+
+// Does a LIDAR offset table equal the compile-time one the lane kernel was built with?
+template <int R, int C>
+bool lane_offsets_equal(const int8_t* off) {
+    for (int i = 0; i < C; ++i)
+        for (int r = 0; r < R; ++r)
+            if (off[(i * R + r) * 2] != LidarGen<R, C>::dx(i, r) || off[(i * R + r) * 2 + 1] != LidarGen<R, C>::dy(i, r)) return false;
+    return true;
+}
+bool lane_offsets_match(int R, int C, const int8_t* off) {
+    if (R == 6 && C == 16) return lane_offsets_equal<6, 16>(off);
+    if (R == 2 && C == 10) return lane_offsets_equal<2, 10>(off);
+    if (R == 4 && C == 16) return lane_offsets_equal<4, 16>(off);
+    if (R == 4 && C == 8) return lane_offsets_equal<4, 8>(off);
+    return false;
+}
+
+// launch shape of one persistent specialised kernel
+struct FastLaunch { fast_kernel_t fn; int grid, threads, smem, q; };
+
 }  // namespace
 
 struct plantos {
@@ -58,14 +81,15 @@ struct plantos {
     float* s_reward;
     uint8_t* s_done;
     // launch configuration
-    bool use_fast;
-    fast_kernel_t fast_fn;
-    int fast_grid;
+    bool use_fast;               // a specialised kernel exists for this shape
+    FastLaunch trip;             // k_step_fast (fn == nullptr: none)
+    FastLaunch lane;             // k_step_lane
+    bool lane_offsets_ok;        // the uploaded LIDAR offsets equal the lane kernel's compile-time table
+    bool prefer_lane;
     bool use_pdl;
     uint4* d_table_blob;
     int4* d_lane_tab;
     int generic_grid, generic_smem;
-    int fast_smem;
     bool did_reset;
     int64_t launches;
 };
@@ -154,7 +178,10 @@ extern "C" int plantos_compute_tables(const plantos_config_t* c, int8_t* lidar_o
 static int upload_tables_impl(plantos_t* h, const int8_t* lidar_off, const float* dist_tab, const float* pos_tab,
                               const float* visit_tab, const double* reward_tab) {
     const Params& p = h->p;
-    if (lidar_off) CUDA_TRY(cudaMemcpy((void*)p.lidar_off, lidar_off, (size_t)p.C * p.R * 2, cudaMemcpyHostToDevice));
+    if (lidar_off) {
+        CUDA_TRY(cudaMemcpy((void*)p.lidar_off, lidar_off, (size_t)p.C * p.R * 2, cudaMemcpyHostToDevice));
+        h->lane_offsets_ok = lane_offsets_match(p.R, p.C, lidar_off);
+    }
     if (dist_tab) CUDA_TRY(cudaMemcpy((void*)p.dist_tab, dist_tab, (size_t)(p.R + 1) * 4, cudaMemcpyHostToDevice));
     if (pos_tab) CUDA_TRY(cudaMemcpy((void*)p.pos_tab, pos_tab, (size_t)p.G * 4, cudaMemcpyHostToDevice));
     if (visit_tab) CUDA_TRY(cudaMemcpy((void*)p.visit_tab, visit_tab, 11 * 4, cudaMemcpyHostToDevice));
@@ -294,26 +321,37 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
         }
         for (const FastVariant& v : kFastVariants)
-            if (v.R == p.R && v.C == p.C && v.keep == keep) { h->use_fast = true; h->fast_fn = v.fn; }
+            if (v.R == p.R && v.C == p.C && v.keep == keep) { h->use_fast = true; h->trip.fn = v.fn; }
+        for (const FastVariant& v : kLaneVariants)
+            if (v.R == p.R && v.C == p.C && v.keep == keep) h->lane.fn = v.fn;
     }
     if (cfg->kernel == PLANTOS_KERNEL_FAST && !h->use_fast) {
         free_all(h);
         return fail(PLANTOS_EINVAL, "PLANTOS_KERNEL_FAST requested but (G, R, C) has no fast-kernel instantiation");
     }
     h->generic_smem = tables_bytes(p.G, p.R, p.C) + kGenericWarps * generic_warp_scratch_bytes(p.G, p.W, p.D);
-    h->fast_smem = tables_bytes(p.G, p.R, p.C) + kFastWarps * fast_warp_scratch_bytes(p.R, p.G, p.D);
     if (h->use_fast) {
-        // persistent grid: at most PLANTOS_FAST_MINBLOCKS blocks per SM, each warp walks its own
-        // contiguous env range (at least 8 envs per warp when there are few envs)
-        long long blocks = (long long)h->num_sms * PLANTOS_FAST_MINBLOCKS;
-        if (const char* s = std::getenv("PLANTOS_FAST_GRID")) { const int v = std::atoi(s); if (v > 0) blocks = v; }
-        const long long need = ((long long)p.N / 8 + kFastWarps - 1) / kFastWarps;
-        if (blocks > need) blocks = need;
-        h->fast_grid = (int)(blocks < 1 ? 1 : blocks);
+        // Persistent grids: each warp walks its own contiguous range of q envs (a multiple of 4; at
+        // least 8 envs per warp when there are few envs).  PLANTOS_FAST_IMPL=lane selects the
+        // experimental lane-per-env kernel (k_step_lane) instead of k_step_fast.
+        auto shape = [&](FastLaunch& L, int warps, int blocks_per_sm, int smem) {
+            long long blocks = (long long)h->num_sms * blocks_per_sm;
+            if (const char* s = std::getenv("PLANTOS_FAST_GRID")) { const int v = std::atoi(s); if (v > 0) blocks = v; }
+            const long long need = ((long long)p.N / 8 + warps - 1) / warps;
+            if (blocks > need) blocks = need;
+            L.grid = (int)(blocks < 1 ? 1 : blocks);
+            L.threads = warps * 32; L.smem = smem;
+            const long long nwarps = (long long)L.grid * warps, nfull = p.N & ~3;
+            L.q = (int)((((nfull + nwarps - 1) / nwarps) + 3) & ~3LL);
+        };
+        shape(h->trip, kFastWarps, PLANTOS_FAST_MINBLOCKS,
+              tables_bytes(p.G, p.R, p.C) + kFastWarps * fast_warp_scratch_bytes(p.R, p.G, p.D));
+        shape(h->lane, kLaneWarps, 1, tables_bytes(p.G, p.R, p.C) + kLaneWarps * lane_warp_scratch_bytes(p.R, p.D));
+        if ((tables_bytes(p.G, p.R, p.C) >> 4) > kLaneWarps * 32) h->lane.fn = nullptr;
+        h->prefer_lane = false;
+        if (const char* s = std::getenv("PLANTOS_FAST_IMPL")) h->prefer_lane = std::strcmp(s, "lane") == 0;
         h->use_pdl = true;
         if (const char* s = std::getenv("PLANTOS_PDL")) h->use_pdl = std::atoi(s) != 0;
-        const long long nwarps = (long long)h->fast_grid * kFastWarps, nfull = p.N & ~3;
-        p.fast_q = (int)((((nfull + nwarps - 1) / nwarps) + 3) & ~3LL);
     }
     cudaError_t e1 = cudaFuncSetAttribute(k_step_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);
     cudaError_t e2 = cudaFuncSetAttribute(k_reset_all, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);
@@ -327,8 +365,9 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     const long long want = ((long long)p.N + kGenericWarps - 1) / kGenericWarps;
     const long long cap = (long long)h->num_sms * occ;
     h->generic_grid = (int)(want < cap ? want : cap);
-    if (h->use_fast) {
-        cudaError_t e3 = cudaFuncSetAttribute(h->fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fast_smem);
+    for (FastLaunch* L : {&h->trip, &h->lane}) {
+        if (!h->use_fast || !L->fn) continue;
+        cudaError_t e3 = cudaFuncSetAttribute(L->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, L->smem);
         if (e3 != cudaSuccess) { free_all(h); return fail(PLANTOS_ECUDA, std::string("cudaFuncSetAttribute(fast): ") + cudaGetErrorString(e3)); }
     }
     cudaError_t es = cudaDeviceSynchronize();
@@ -408,13 +447,15 @@ extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, fl
         // next step's prologue with this step's tail (the kernel waits on griddepcontrol before it
         // touches any state); PLANTOS_PDL=0 falls back to a plain launch
         cudaLaunchConfig_t lc = {};
-        lc.gridDim = dim3((unsigned)h->fast_grid); lc.blockDim = dim3(kFastWarps * 32);
-        lc.dynamicSmemBytes = (size_t)h->fast_smem; lc.stream = (cudaStream_t)stream;
+        const FastLaunch& L = (h->prefer_lane && h->lane.fn && h->lane_offsets_ok) ? h->lane : h->trip;
+        h->p.fast_q = L.q;
+        lc.gridDim = dim3((unsigned)L.grid); lc.blockDim = dim3((unsigned)L.threads);
+        lc.dynamicSmemBytes = (size_t)L.smem; lc.stream = (cudaStream_t)stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         lc.attrs = at; lc.numAttrs = h->use_pdl ? 1 : 0;
-        CUDA_TRY(cudaLaunchKernelEx(&lc, h->fast_fn, h->p, io));
+        CUDA_TRY(cudaLaunchKernelEx(&lc, L.fn, h->p, io));
     } else {
         if (h->cfg.kernel == PLANTOS_KERNEL_FAST)
             return fail(PLANTOS_EINVAL, "PLANTOS_KERNEL_FAST needs a 16-byte aligned obs buffer");
@@ -516,7 +557,8 @@ extern "C" int64_t plantos_launch_count(const plantos_t* h) { return h ? h->laun
 
 extern "C" const char* plantos_kernel_name(const plantos_t* h) {
     if (!h) return "";
-    return h->use_fast ? "fast" : "generic";
+    if (!h->use_fast) return "generic";
+    return "fast";
 }
 
 extern "C" int64_t plantos_state_bytes_per_env(const plantos_t* h) {
