@@ -47,3 +47,63 @@ def test_fixture_covers_edge_cases():
     assert np.isclose(t8["rewards"], -10.1).any()
     assert (t8["lidar_dist"][..., 1] == 1).any()  # ray 1 has offset (0,0) at r=1: sees the rover's own cell
     assert int(tiny["cfg_lidar_range"]) > int(tiny["cfg_grid_size"])
+
+
+# ---- observation batches left behind by the reference's own training runs (make_last_obs.py)
+def _last_obs():
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_last_obs.npz")
+    return dict(np.load(path))
+
+
+def test_tables_reproduce_every_value_in_the_reference_runs_last_obs():
+    """`_last_obs` of the four saved policies = 256 real observations of the unmodified reference
+    (training preset).  Every float in them must be bit-identical to an entry of the host tables the
+    kernels read (dist r/R, one-hot 0/1, pos x/G, visits min(k,10)/10): that pins the table
+    arithmetic against numbers the reference itself produced."""
+    from rl_env_b200 import tables
+    G, R, C = 25, 6, 16
+    dist = set(tables.distance_table(R).view(np.uint32).tolist())
+    pos = set(tables.position_table(G).view(np.uint32).tolist())
+    vis = set(tables.visit_table().view(np.uint32).tolist())
+    onehot = set(np.array([0.0, 1.0], dtype=np.float32).view(np.uint32).tolist())
+    batches = _last_obs()
+    assert len(batches) == 4
+    seen_dist, seen_vis = set(), set()
+    for obs in batches.values():
+        assert obs.shape == (64, 5 * C + 27) and obs.dtype == np.float32
+        bits = obs.view(np.uint32)
+        lidar = bits[:, :5 * C].reshape(64, C, 5)
+        assert set(lidar[:, :, 0].ravel().tolist()) <= dist
+        assert set(lidar[:, :, 1:].ravel().tolist()) <= onehot
+        assert (obs[:, :5 * C].reshape(64, C, 5)[:, :, 1:].sum(axis=2) == 1.0).all()       # valid one-hot
+        assert set(bits[:, 5 * C:5 * C + 2].ravel().tolist()) <= pos
+        assert set(bits[:, 5 * C + 2:].ravel().tolist()) <= vis
+        seen_dist |= set(lidar[:, :, 0].ravel().tolist()); seen_vis |= set(bits[:, 5 * C + 2:].ravel().tolist())
+    # the reference runs exercise every distance 1/6 .. 6/6 and every visit level 0 .. 1.0
+    assert seen_dist == dist - {np.float32(0.0).view(np.uint32).item()}
+    assert seen_vis == vis
+
+
+def test_oracle_observations_obey_what_the_reference_runs_show():
+    """Structural facts of the reference's `_last_obs` that the oracle must share: a ray that reports
+    EMPTY is at full range, an out-of-range visit cell reads 1.0, the rover's own cell has been
+    visited (centre of the 5x5 window > 0)."""
+    from oracle.plantos_oracle import PRESETS, PlantOSOracle
+    import random
+    C = 16
+    def facts(obs):
+        lid = obs[:5 * C].reshape(C, 5)
+        empty = lid[:, 1] == 1.0
+        assert (lid[empty, 0] == 1.0).all()
+        assert obs[5 * C + 2 + 12] > 0.0
+    for obs_batch in _last_obs().values():
+        for row in obs_batch:
+            facts(row)
+    random.seed(7)
+    env = PlantOSOracle(**PRESETS["T"])
+    obs = env.reset()
+    rng = np.random.default_rng(7)
+    for _ in range(300):
+        obs, *_ = env.step(int(rng.integers(0, 5)))
+        facts(np.asarray(obs, dtype=np.float32))
