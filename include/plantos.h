@@ -171,6 +171,28 @@ int plantos_set_state(plantos_t* h, const uint8_t* cells_dev, const int32_t* vis
  * the order in which envs finish. */
 int plantos_stats(plantos_t* h, double* out_dev, int clear, void* stream);
 
+/* Per-episode log = what SB3's Monitor wrapper records (A2C_training.py:124, trainingCode.py:109;
+ * train_improved1/gym/env_0.monitor.csv: "r,l,t" rows).  Once enabled, every env that finishes an
+ * episode appends one entry on the device (inside the step kernel, one atomic per warp); the host
+ * drains them whenever it likes.  Entries beyond `capacity` between two drains are dropped and
+ * counted. */
+typedef struct plantos_episode {
+    uint32_t env;          /* env index inside this handle (add env_id_base for the global id) */
+    uint32_t length;       /* Monitor's l */
+    uint32_t step_seq;     /* number of the plantos_step call (0-based) that finished the episode */
+    uint32_t flags;        /* bit 0 terminated, bit 1 truncated */
+    double episode_return; /* Monitor's r: rewards summed in step order, in double */
+    uint32_t collisions;
+    uint32_t watered;
+} plantos_episode_t;
+/* capacity > 0 enables (or resizes and clears) the log, capacity == 0 disables it. */
+int plantos_episode_log_enable(plantos_t* h, int capacity);
+/* Copies up to `max_entries` pending entries to host memory `out`, clears the log, reports how many
+ * were copied (`n_out`) and how many were lost to overflow since the last drain (`dropped_out`, may
+ * be NULL).  Synchronises `stream`. */
+int plantos_episode_log_drain(plantos_t* h, plantos_episode_t* out, int max_entries, int* n_out,
+                              int64_t* dropped_out, void* stream);
+
 /* Sticky device-side error flag (e.g. PLANTOS_ENOMAPS); synchronises `stream`. */
 int plantos_check(plantos_t* h, void* stream);
 

@@ -60,6 +60,8 @@ SIGNATURES = {
     "plantos_set_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "plantos_stats": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "plantos_check": (C.c_int, [_vp, _vp]),
+    "plantos_episode_log_enable": (C.c_int, [_vp, C.c_int]),
+    "plantos_episode_log_drain": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int64), _vp]),
     "plantos_launch_count": (C.c_int64, [_vp]),
     "plantos_kernel_name": (C.c_char_p, [_vp]),
     "plantos_state_bytes_per_env": (C.c_int64, [_vp]),

@@ -92,6 +92,7 @@ struct plantos {
     int generic_grid, generic_smem;
     bool did_reset;
     int64_t launches;
+    int64_t steps;               // plantos_step calls so far (episode log's step_seq)
 };
 
 // ------------------------------------------------------------------ host tables
@@ -203,6 +204,7 @@ static void free_all(plantos_t* h) {
     cudaFree(h->p.rec); cudaFree(h->p.term_rec); cudaFree(h->p.types); cudaFree(h->p.vis4); cudaFree(h->p.visov);
     cudaFree(h->d_tables); cudaFree(h->d_table_blob); cudaFree(h->d_lane_tab); cudaFree(h->p.stats); cudaFree(h->p.err);
     cudaFree(h->d_map_cells); cudaFree(h->d_map_rover);
+    cudaFree(h->p.ep_log); cudaFree(h->p.ep_log_count);
     cudaFree(h->s_actions); cudaFree(h->s_obs); cudaFree(h->s_reward); cudaFree(h->s_done);
     delete h;
 }
@@ -441,6 +443,8 @@ extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, fl
     io.actions = (const long long*)actions; io.obs = obs; io.reward = reward; io.done = done;
     io.terminated = terminated; io.truncated = truncated; io.terminal_obs = terminal_obs;
     CUDA_TRY(cudaSetDevice(h->device));
+    h->p.step_seq = (unsigned)h->steps;
+    h->steps += 1;
     const bool aligned = (((uintptr_t)obs) & 15u) == 0;
     if (h->use_fast && aligned) {
         // launched with programmatic stream serialization so that back-to-back steps overlap the
@@ -550,6 +554,41 @@ extern "C" int plantos_check(plantos_t* h, void* stream) {
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     if (err == PLANTOS_ENOMAPS) return fail(PLANTOS_ENOMAPS, "an env was reset more often than maps were pushed for it");
     if (err != 0) return fail(err, "device-side error flag set");
+    return PLANTOS_OK;
+}
+
+static_assert(sizeof(plantos_episode_t) == 32, "episode log entries are two uint4");
+
+extern "C" int plantos_episode_log_enable(plantos_t* h, int capacity) {
+    if (!h || capacity < 0) return fail(PLANTOS_EINVAL, "handle is NULL / negative capacity");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(h->p.ep_log); cudaFree(h->p.ep_log_count);
+    h->p.ep_log = nullptr; h->p.ep_log_count = nullptr; h->p.ep_log_cap = 0;
+    if (capacity == 0) return PLANTOS_OK;
+    CUDA_TRY(cudaMalloc((void**)&h->p.ep_log, (size_t)capacity * 32));
+    CUDA_TRY(cudaMalloc((void**)&h->p.ep_log_count, 4));
+    CUDA_TRY(cudaMemset(h->p.ep_log_count, 0, 4));
+    h->p.ep_log_cap = capacity;
+    return PLANTOS_OK;
+}
+
+extern "C" int plantos_episode_log_drain(plantos_t* h, plantos_episode_t* out, int max_entries, int* n_out,
+                                         int64_t* dropped_out, void* stream) {
+    if (!h || !n_out || (max_entries > 0 && !out)) return fail(PLANTOS_EINVAL, "handle/out/n_out is NULL");
+    if (!h->p.ep_log) return fail(PLANTOS_ESTATE, "episode log is not enabled (plantos_episode_log_enable)");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned count = 0;
+    CUDA_TRY(cudaMemcpyAsync(&count, h->p.ep_log_count, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const unsigned stored = count < (unsigned)h->p.ep_log_cap ? count : (unsigned)h->p.ep_log_cap;
+    const unsigned n = stored < (unsigned)max_entries ? stored : (unsigned)max_entries;
+    if (n) CUDA_TRY(cudaMemcpyAsync(out, h->p.ep_log, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemsetAsync(h->p.ep_log_count, 0, 4, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *n_out = (int)n;
+    if (dropped_out) *dropped_out = (int64_t)count - (int64_t)n;
     return PLANTOS_OK;
 }
 

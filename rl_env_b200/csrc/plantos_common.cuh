@@ -75,6 +75,12 @@ struct Params {
     // episode statistics (fixed point, see plantos_stats) and sticky error word
     unsigned long long* stats;
     int* err;
+    // optional episode log (SB3 Monitor's r, l per finished episode; plantos_episode_log_*): entries
+    // of two uint4 {env, length, step seq, terminated | truncated << 1} {f64 return, collisions, watered}
+    uint4* ep_log;              // nullptr: disabled
+    unsigned int* ep_log_count; // entries appended since the last drain (may exceed ep_log_cap: dropped)
+    int ep_log_cap;
+    unsigned int step_seq;      // number of the step launch, set by the host
 };
 
 struct StepIO {

@@ -274,7 +274,7 @@ k_step_fast(const Params p, const StepIO io) {
             }
             posw = (unsigned)r.x | ((unsigned)r.y << 5);
         }
-        accumulate_stats(p, act && done, r, term, trunc, lane);
+        accumulate_stats(p, act && done, r, term, trunc, lane, (int)e);
         // orders the plane stores above before the window copies that other lanes issue below, and
         // frees the record buffer
         __syncwarp();

@@ -179,9 +179,25 @@ __device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int epi
 }
 
 // episode statistics of finished envs -> fixed-point accumulators (one atomic per warp)
+// and, when enabled, one episode-log entry per finished env (`env` = the lane's env index;
+// slots are handed out with one atomic per warp)
 __device__ __forceinline__ void accumulate_stats(const Params& p, bool done, const EnvRec& r, int terminated,
-                                                 int truncated, int lane) {
-    if (__ballot_sync(0xffffffffu, done) == 0u) return;
+                                                 int truncated, int lane, int env) {
+    const unsigned dm = __ballot_sync(0xffffffffu, done);
+    if (dm == 0u) return;
+    if (p.ep_log) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(p.ep_log_count, (unsigned)__popc(dm));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned slot = base + (unsigned)__popc(dm & ((1u << lane) - 1u));
+        if (done && slot < (unsigned)p.ep_log_cap) {
+            const unsigned long long rb = (unsigned long long)__double_as_longlong(r.ret);
+            p.ep_log[2 * (size_t)slot] = make_uint4((unsigned)env, (unsigned)r.step, p.step_seq,
+                                                     (unsigned)(terminated | (truncated << 1)));
+            p.ep_log[2 * (size_t)slot + 1] = make_uint4((unsigned)rb, (unsigned)(rb >> 32), (unsigned)r.collisions,
+                                                         (unsigned)r.watered);
+        }
+    }
     long long v[kStatCount];
     v[0] = done ? 1 : 0;
     v[1] = done ? __double2ll_rn(r.ret * 1e6) : 0;
@@ -259,7 +275,7 @@ __device__ __forceinline__ void step_env_warp(const Params& p, const Tables& t, 
             p.term_rec[2 * (size_t)e + 1] = rb;
             episode = r.episode;
         }
-        accumulate_stats(p, lane == 0, r, (flagw >> 17) & 1, (flagw >> 18) & 1, lane);
+        accumulate_stats(p, lane == 0, r, (flagw >> 17) & 1, (flagw >> 18) & 1, lane, e);
         episode = __shfl_sync(0xffffffffu, episode, 0);
         __syncwarp();
         const EnvRec nr = reset_env_warp(p, e, episode, plane, lane);

@@ -181,7 +181,7 @@ k_step_lane(const Params p, const StepIO io) {
                 p.term_rec[2 * e + 1] = rb;
             }
         }
-        accumulate_stats(p, act && done, r, term, trunc, lane);
+        accumulate_stats(p, act && done, r, term, trunc, lane, (int)e);
         TSTAMP(5);
         if (has_next) fetch_rec(e_next);                  // own slot of the record buffer is free again
 

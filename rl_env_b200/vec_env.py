@@ -155,6 +155,7 @@ class PlantOSVecEnv:
         nat.check(self._lib.plantos_default_config(C.byref(cfg)))
         cfg.num_envs = self.num_envs
         cfg.env_id_base = int(env_id_base)
+        self.env_id_base = int(env_id_base)
         cfg.grid_size, cfg.num_plants, cfg.num_obstacles = self.grid_size, self.num_plants, self.num_obstacles
         cfg.lidar_range, cfg.lidar_channels = self.lidar_range, self.lidar_channels
         cfg.max_steps = self.max_steps
@@ -410,6 +411,86 @@ class PlantOSVecEnv:
         and the collective are stream-ordered), for callers that poll it off the step path."""
         nat.check(self._lib.plantos_stats(self._h, self._stats.data_ptr(), int(clear), self._stream()))
         return all_reduce_stats(self._stats) if all_reduce else self._stats
+
+    # --------------------------------------------------------------- per-episode log (SB3 Monitor)
+    EPISODE_DTYPE = np.dtype([("env", "<u4"), ("l", "<u4"), ("step_seq", "<u4"), ("flags", "<u4"),
+                              ("r", "<f8"), ("collisions", "<u4"), ("watered", "<u4")])
+
+    def enable_episode_log(self, capacity: Optional[int] = None) -> None:
+        """Record (env, r, l, ...) of every finished episode on the device -- what SB3's Monitor
+        wrapper records per env (A2C_training.py:124).  `capacity` = entries kept between two
+        drains (default: 4 per env)."""
+        self._ep_cap = int(capacity) if capacity is not None else 4 * self.num_envs
+        nat.check(self._lib.plantos_episode_log_enable(self._h, self._ep_cap))
+        self._ep_buf = np.zeros(self._ep_cap, dtype=self.EPISODE_DTYPE)
+
+    def drain_episode_log(self):
+        """Finished episodes since the last drain as a structured array (fields env [global id], l,
+        step_seq, flags, r, collisions, watered) plus the number of entries lost to overflow."""
+        n, dropped = C.c_int(0), C.c_int64(0)
+        nat.check(self._lib.plantos_episode_log_drain(
+            self._h, self._ep_buf.ctypes.data_as(C.c_void_p), self._ep_cap, C.byref(n), C.byref(dropped),
+            self._stream()))
+        raw = self._ep_buf[:n.value]
+        out = np.zeros(n.value, dtype=[("env", "<i8")] + self.EPISODE_DTYPE.descr[1:])
+        for name in self.EPISODE_DTYPE.names[1:]:
+            out[name] = raw[name]
+        out["env"] = raw["env"].astype(np.int64) + self.env_id_base
+        return out, int(dropped.value)
+
+
+class MonitorCSV:
+    """`monitor.csv` in the format of stable_baselines3.common.monitor.Monitor (header
+    `#{"t_start": ..., "env_id": ...}`, then `r,l,t` rows; reference artefacts
+    train_improved1/gym/env_*.monitor.csv), fed from the device episode log.
+
+    One file for the whole VecEnv (rows in the order episodes were logged, with an extra leading
+    `env` column when `env_column=True`), or one `env_<id>.monitor.csv` per env like the
+    reference's `Monitor(env, f"env_{rank}")` when `per_env_files=True` (small N only).
+    `t` is the wall-clock time of the `flush()` that collected the episode, relative to t_start:
+    steps are enqueued asynchronously, so the host never sees the exact moment an episode ended."""
+
+    def __init__(self, env: "PlantOSVecEnv", directory: str, per_env_files: bool = False,
+                 env_column: bool = False, capacity: Optional[int] = None):
+        import json
+        import os
+        self.env, self.dir = env, directory
+        self.per_env, self.env_column = per_env_files, env_column
+        self.t_start = time.time()
+        self.dropped = 0
+        os.makedirs(directory, exist_ok=True)
+        env.enable_episode_log(capacity)
+        self._files: Dict[Any, Any] = {}
+        self._json, self._os = json, os
+
+    def _file(self, key):
+        f = self._files.get(key)
+        if f is None:
+            name = "monitor.csv" if key is None else f"env_{key}.monitor.csv"
+            f = open(self._os.path.join(self.dir, name), "w")
+            f.write("#%s\n" % self._json.dumps({"t_start": self.t_start, "env_id": "None" if key is None else str(key)}))
+            f.write(("env," if (key is None and self.env_column) else "") + "r,l,t\n")
+            self._files[key] = f
+        return f
+
+    def flush(self) -> int:
+        """Drain the device log and append its episodes; returns how many were written."""
+        eps, dropped = self.env.drain_episode_log()
+        self.dropped += dropped
+        t = round(time.time() - self.t_start, 6)
+        for ep in eps:
+            f = self._file(int(ep["env"]) if self.per_env else None)
+            lead = f"{int(ep['env'])}," if (not self.per_env and self.env_column) else ""
+            f.write(f"{lead}{round(float(ep['r']), 6)},{int(ep['l'])},{t}\n")
+        for f in self._files.values():
+            f.flush()
+        return len(eps)
+
+    def close(self) -> None:
+        self.flush()
+        for f in self._files.values():
+            f.close()
+        self._files.clear()
 
 
 def all_reduce_stats(vec: torch.Tensor) -> torch.Tensor:

@@ -90,3 +90,57 @@ def test_step_host_matches_device_step():
         assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
         assert np.array_equal(d1.cpu().numpy(), d2)
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("kernel", ["fast", "generic"])
+def test_episode_log_and_monitor_csv_match_the_oracle_monitor(kernel, tmp_path):
+    """Device episode log (one entry per finished episode, appended inside the step kernel) against
+    the restated DummyVecEnv + Monitor: same (env, r, l) multiset, r equal after Monitor's own
+    round(sum, 6); and the monitor.csv files carry the reference's format
+    (train_improved1/gym/env_0.monitor.csv)."""
+    import json
+    from rl_env_b200 import MonitorCSV, PlantOSVecEnv
+    name = "replay_T_8env" if kernel == "fast" else "replay_tiny_4env"
+    fx = load_fixture(name)
+    n = fx["actions"].shape[1]
+    ora = PyOracleBackend(fx).env
+    env = PlantOSVecEnv(n, map_source="injected", kernel=kernel, max_steps=int(fx["cfg_max_steps"]), **fixture_kwargs(fx))
+    env.push_maps(fx["maps_cells"], fx["maps_rover"])
+    mon = MonitorCSV(env, str(tmp_path), per_env_files=True)
+    ora.reset(); env.reset()
+    want = []
+    steps = min(2200, fx["actions"].shape[0])
+    for t in range(steps):
+        _, _, o_done, o_infos = ora.step(fx["actions"][t])
+        env.step(fx["actions"][t])
+        for i in range(n):
+            if o_done[i]:
+                want.append((i, o_infos[i]["episode"]["l"], o_infos[i]["episode"]["r"], t))
+        if t % 700 == 699:
+            mon.flush()
+    mon.close()
+    assert mon.dropped == 0 and len(want) >= 2
+    rows = {}
+    for i in range(n):
+        path = tmp_path / f"env_{i}.monitor.csv"
+        if not path.exists():
+            continue
+        lines = path.read_text().splitlines()
+        head = json.loads(lines[0][1:])
+        assert lines[0].startswith("#") and set(head) == {"t_start", "env_id"} and lines[1] == "r,l,t"
+        rows[i] = [(float(a), int(b), float(c)) for a, b, c in (ln.split(",") for ln in lines[2:])]
+    got = sorted((i, l, r) for i, rs in rows.items() for r, l, _ in rs)
+    assert got == sorted((i, l, round(r, 6)) for i, l, r, _ in want)
+    # raw log entries: exact doubles, step numbers, flags
+    env2 = PlantOSVecEnv(n, map_source="injected", kernel=kernel, max_steps=int(fx["cfg_max_steps"]), **fixture_kwargs(fx))
+    env2.push_maps(fx["maps_cells"], fx["maps_rover"])
+    env2.enable_episode_log(capacity=3)                      # tiny capacity: overflow is counted, not fatal
+    env2.reset()
+    for t in range(steps):
+        env2.step(fx["actions"][t])
+    eps, dropped = env2.drain_episode_log()
+    assert len(eps) == min(3, len(want)) and dropped == len(want) - len(eps)
+    for e in eps:
+        match = [w for w in want if w[0] == int(e["env"]) and w[3] == int(e["step_seq"])]
+        assert match and match[0][1] == int(e["l"]) and match[0][2] == round(float(e["r"]), 6)
+        assert int(e["flags"]) in (1, 2, 3)
