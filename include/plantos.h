@@ -171,6 +171,21 @@ int plantos_set_state(plantos_t* h, const uint8_t* cells_dev, const int32_t* vis
  * the order in which envs finish. */
 int plantos_stats(plantos_t* h, double* out_dev, int clear, void* stream);
 
+/* CurriculumWrapper on the device.  mode PLANTOS_CURRICULUM_TERMINATE follows
+ * A2C_training.py:37-109 (reaching the exploration threshold terminates the episode; the reference
+ * constructs it with 40, 100, 10 and max_episodes_per_maze = 3), PLANTOS_CURRICULUM_MARK follows
+ * trainingCode.py:24-98 (the threshold only marks the maze completed; 30, 100, 5, 50).  As in the
+ * reference, visit counts persist into the next episode unless the maze was completed or has been
+ * played max_episodes_per_maze times, the reset observation shows fresh counts, explored_map
+ * restarts every episode, and a new map is drawn at every reset.  Call before plantos_reset; it
+ * restarts every env's curriculum state.  Curriculum steps run on the generic kernel;
+ * plantos_set_state is refused while a curriculum is active.  mode PLANTOS_CURRICULUM_OFF disables. */
+enum { PLANTOS_CURRICULUM_OFF = 0, PLANTOS_CURRICULUM_TERMINATE = 1, PLANTOS_CURRICULUM_MARK = 2 };
+int plantos_set_curriculum(plantos_t* h, int mode, double initial_threshold, double max_threshold,
+                           double threshold_increment, int max_episodes_per_maze);
+/* Current exploration thresholds, f64 [N] device pointer. */
+int plantos_get_curriculum_thresholds(plantos_t* h, double* out_dev, void* stream);
+
 /* Per-episode log = what SB3's Monitor wrapper records (A2C_training.py:124, trainingCode.py:109;
  * train_improved1/gym/env_0.monitor.csv: "r,l,t" rows).  Once enabled, every env that finishes an
  * episode appends one entry on the device (inside the step kernel, one atomic per warp); the host

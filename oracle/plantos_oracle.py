@@ -324,6 +324,73 @@ class PlantOSOracle:
         }
 
 
+class CurriculumOracle:
+    """`CurriculumWrapper` restated -- both variants the reference ships:
+
+      "a2c": A2C_training.py:37-109  (ctor call :121: thresholds 40 -> 100 by 10, 3 episodes per
+             maze, reaching the threshold TERMINATES the episode, :98-100)
+      "dqn": trainingCode.py:24-98   (ctor call :107: 30 -> 100 by 5, 50 episodes per maze, reaching
+             the threshold only marks the maze completed, :88-89)
+
+    What it really does (the map generator ignores `seed`, plantos_env.py:127 vs :344-372, so the
+    "same maze" is a new map every time): `visit_counts` is carried over to the next episode unless
+    the maze was completed or has been played `max_episodes_per_maze` times -- restored AFTER the
+    reset observation was built, so that observation shows fresh counts and the rover's start cell
+    is not counted -- while `explored_map` restarts every episode.  Rewards therefore use the
+    persistent counts (`was_new`, plantos_env.py:197) and the exploration percentage does not."""
+
+    VARIANTS = {
+        "a2c": dict(initial_threshold=40.0, max_threshold=100.0, threshold_increment=10.0,
+                    max_episodes_per_maze=3, terminate_on_threshold=True),
+        "dqn": dict(initial_threshold=30.0, max_threshold=100.0, threshold_increment=5.0,
+                    max_episodes_per_maze=50, terminate_on_threshold=False),
+    }
+
+    def __init__(self, env: "PlantOSOracle", variant: str = "a2c", **override):
+        cfg = dict(self.VARIANTS[variant]); cfg.update(override)
+        self.env = env
+        self.maze_completed = False
+        self.episodes_on_current_maze = 0
+        self.persistent_visit_counts = None
+        self.exploration_threshold = float(cfg["initial_threshold"])
+        self.max_threshold = float(cfg["max_threshold"])
+        self.threshold_increment = float(cfg["threshold_increment"])
+        self.max_episodes_per_maze = int(cfg["max_episodes_per_maze"])
+        self.terminate_on_threshold = bool(cfg["terminate_on_threshold"])
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    def reset(self, map_cells=None, rover=None):
+        self.episodes_on_current_maze += 1
+        timeout = self.episodes_on_current_maze >= self.max_episodes_per_maze
+        if self.maze_completed or timeout:
+            if self.maze_completed:
+                self.exploration_threshold = min(self.exploration_threshold + self.threshold_increment,
+                                                 self.max_threshold)
+            self.maze_completed = False
+            self.episodes_on_current_maze = 0
+            obs, info = self.env.reset(map_cells, rover)
+            self.persistent_visit_counts = None
+        else:
+            obs, info = self.env.reset(map_cells, rover)
+            if self.persistent_visit_counts is not None:
+                self.env.visit_counts = self.persistent_visit_counts.copy()
+            else:
+                self.persistent_visit_counts = self.env.visit_counts.copy()
+        return obs, info
+
+    def step(self, action: int):
+        obs, reward, terminated, truncated, info = self.env.step(action)
+        if info["exploration_percentage"] >= self.exploration_threshold:
+            self.maze_completed = True
+            if self.terminate_on_threshold:
+                terminated = True
+        if self.persistent_visit_counts is not None:
+            self.persistent_visit_counts = self.env.visit_counts.copy()
+        return obs, reward, terminated, truncated, info
+
+
 class OracleVecEnv:
     """`DummyVecEnv([Monitor(PlantOSEnv(**kw))] * n)` restated.
 
@@ -338,9 +405,11 @@ class OracleVecEnv:
     """
 
     def __init__(self, num_envs: int, maps: Optional[List[List[Tuple[np.ndarray, Tuple[int, int]]]]] = None,
-                 **env_kwargs):
+                 curriculum: Optional[Dict[str, Any]] = None, **env_kwargs):
         self.num_envs = num_envs
         self.envs = [PlantOSOracle(**env_kwargs) for _ in range(num_envs)]
+        if curriculum is not None:      # make_env_wrapper: Monitor(CurriculumWrapper(PlantOSEnv)), A2C_training.py:116-125
+            self.envs = [CurriculumOracle(e, **curriculum) for e in self.envs]
         self.obs_dim = self.envs[0].obs_dim
         # maps[i] = queue of (cells, rover) consumed at each reset of env i
         self.maps = maps

@@ -118,8 +118,17 @@ class ReferenceEnv:
     def __getattr__(self, name):
         return getattr(self.env, name)
 
-    def reset(self):
-        return self.env.reset()
+    def reset(self, seed=None, **kwargs):
+        return self.env.reset(seed=seed, **kwargs)
+
+    # CurriculumWrapper reads and ASSIGNS env.visit_counts (A2C_training.py:85-87)
+    @property
+    def visit_counts(self):
+        return self.env.visit_counts
+
+    @visit_counts.setter
+    def visit_counts(self, value):
+        self.env.visit_counts = value
 
     def step(self, action):
         env = self.env
@@ -138,3 +147,21 @@ class ReferenceEnv:
                 reward += env.R_COMPLETE_EXPLORATION
                 env.completion_bonus_given = True
             return obs, reward, terminated, truncated, info
+
+
+def load_curriculum_wrapper(variant: str = "a2c"):
+    """The reference's own `CurriculumWrapper` class, executed from its source file in place
+    (A2C_training.py:37-109 for "a2c", trainingCode.py:24-98 for "dqn").  The training scripts
+    cannot be imported (stable_baselines3 / torch training code at module level), so only the
+    class definition is compiled, against the same gymnasium stub plantos_env.py gets."""
+    import ast
+    if not reference_available():
+        raise RuntimeError(f"reference checkout not found at {REFERENCE_DIR}")
+    _install_stubs()
+    path = os.path.join(REFERENCE_DIR, {"a2c": "A2C_training.py", "dqn": "trainingCode.py"}[variant])
+    source = open(path).read()
+    node = next(n for n in ast.parse(source).body if isinstance(n, ast.ClassDef) and n.name == "CurriculumWrapper")
+    module = ast.Module(body=[node], type_ignores=[])
+    ns = {"gym": sys.modules["gymnasium"], "np": np}
+    exec(compile(module, path, "exec"), ns)
+    return ns["CurriculumWrapper"]

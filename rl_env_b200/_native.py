@@ -21,6 +21,9 @@ STAT_NAMES = ("episodes", "return_sum", "length_sum", "exploration_pct_sum", "co
               "watered_sum", "terminated", "truncated")
 
 
+CURRICULUM_OFF, CURRICULUM_TERMINATE, CURRICULUM_MARK = 0, 1, 2
+
+
 class Config(C.Structure):
     """plantos_config_t"""
     _fields_ = [
@@ -60,6 +63,8 @@ SIGNATURES = {
     "plantos_set_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "plantos_stats": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "plantos_check": (C.c_int, [_vp, _vp]),
+    "plantos_set_curriculum": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]),
+    "plantos_get_curriculum_thresholds": (C.c_int, [_vp, _vp, _vp]),
     "plantos_episode_log_enable": (C.c_int, [_vp, C.c_int]),
     "plantos_episode_log_drain": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int64), _vp]),
     "plantos_launch_count": (C.c_int64, [_vp]),

@@ -205,6 +205,7 @@ static void free_all(plantos_t* h) {
     cudaFree(h->d_tables); cudaFree(h->d_table_blob); cudaFree(h->d_lane_tab); cudaFree(h->p.stats); cudaFree(h->p.err);
     cudaFree(h->d_map_cells); cudaFree(h->d_map_rover);
     cudaFree(h->p.ep_log); cudaFree(h->p.ep_log_count);
+    cudaFree(h->p.cur_thr); cudaFree(h->p.cur_cnt); cudaFree(h->p.expl);
     cudaFree(h->s_actions); cudaFree(h->s_obs); cudaFree(h->s_reward); cudaFree(h->s_done);
     delete h;
 }
@@ -446,7 +447,9 @@ extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, fl
     h->p.step_seq = (unsigned)h->steps;
     h->steps += 1;
     const bool aligned = (((uintptr_t)obs) & 15u) == 0;
-    if (h->use_fast && aligned) {
+    if (h->p.cur_mode && h->cfg.kernel == PLANTOS_KERNEL_FAST)
+        return fail(PLANTOS_EINVAL, "curriculum steps run on the generic kernel (PLANTOS_KERNEL_AUTO or _GENERIC)");
+    if (h->use_fast && aligned && !h->p.cur_mode) {
         // launched with programmatic stream serialization so that back-to-back steps overlap the
         // next step's prologue with this step's tail (the kernel waits on griddepcontrol before it
         // touches any state); PLANTOS_PDL=0 falls back to a plain launch
@@ -461,7 +464,7 @@ extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, fl
         lc.attrs = at; lc.numAttrs = h->use_pdl ? 1 : 0;
         CUDA_TRY(cudaLaunchKernelEx(&lc, L.fn, h->p, io));
     } else {
-        if (h->cfg.kernel == PLANTOS_KERNEL_FAST)
+        if (h->cfg.kernel == PLANTOS_KERNEL_FAST && !h->p.cur_mode)
             return fail(PLANTOS_EINVAL, "PLANTOS_KERNEL_FAST needs a 16-byte aligned obs buffer");
         k_step_generic<<<h->generic_grid, kGenericWarps * 32, h->generic_smem, (cudaStream_t)stream>>>(h->p, io);
     }
@@ -528,6 +531,7 @@ extern "C" int plantos_get_state(plantos_t* h, uint8_t* cells_dev, int32_t* visi
 extern "C" int plantos_set_state(plantos_t* h, const uint8_t* cells_dev, const int32_t* visits_dev,
                                  const int32_t* scalars_dev, void* stream) {
     if (!h) return fail(PLANTOS_EINVAL, "handle is NULL");
+    if (h->p.cur_mode) return fail(PLANTOS_ESTATE, "plantos_set_state is not supported while a curriculum is active");
     CUDA_TRY(cudaSetDevice(h->device));
     const size_t threads = (size_t)h->p.N * 32;
     k_set_state<<<(int)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->p, cells_dev, visits_dev, scalars_dev);
@@ -554,6 +558,48 @@ extern "C" int plantos_check(plantos_t* h, void* stream) {
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     if (err == PLANTOS_ENOMAPS) return fail(PLANTOS_ENOMAPS, "an env was reset more often than maps were pushed for it");
     if (err != 0) return fail(err, "device-side error flag set");
+    return PLANTOS_OK;
+}
+
+namespace {
+__global__ void k_fill_f64(double* dst, double v, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = v;
+}
+}  // namespace
+
+extern "C" int plantos_set_curriculum(plantos_t* h, int mode, double initial_threshold, double max_threshold,
+                                      double threshold_increment, int max_episodes_per_maze) {
+    if (!h) return fail(PLANTOS_EINVAL, "handle is NULL");
+    if (mode < PLANTOS_CURRICULUM_OFF || mode > PLANTOS_CURRICULUM_MARK) return fail(PLANTOS_EINVAL, "unknown curriculum mode");
+    if (mode != PLANTOS_CURRICULUM_OFF && (max_episodes_per_maze < 1 || !(initial_threshold == initial_threshold) ||
+                                           !(max_threshold == max_threshold) || !(threshold_increment == threshold_increment)))
+        return fail(PLANTOS_EINVAL, "curriculum: max_episodes_per_maze >= 1 and finite thresholds required");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    Params& p = h->p;
+    cudaFree(p.cur_thr); cudaFree(p.cur_cnt); cudaFree(p.expl);
+    p.cur_thr = nullptr; p.cur_cnt = nullptr; p.expl = nullptr; p.cur_mode = PLANTOS_CURRICULUM_OFF;
+    if (mode == PLANTOS_CURRICULUM_OFF) return PLANTOS_OK;
+    const size_t N = (size_t)p.N;
+    CUDA_TRY(cudaMalloc((void**)&p.cur_thr, N * 8));
+    CUDA_TRY(cudaMalloc((void**)&p.cur_cnt, N * 8));
+    CUDA_TRY(cudaMalloc((void**)&p.expl, N * p.G * p.W * 4));
+    CUDA_TRY(cudaMemset(p.cur_cnt, 0, N * 8));
+    CUDA_TRY(cudaMemset(p.expl, 0, N * p.G * p.W * 4));
+    k_fill_f64<<<256, 256>>>(p.cur_thr, initial_threshold, p.N);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    p.cur_mode = mode; p.cur_max_eps = max_episodes_per_maze;
+    p.cur_max_thr = max_threshold; p.cur_inc = threshold_increment;
+    h->did_reset = false;
+    return PLANTOS_OK;
+}
+
+extern "C" int plantos_get_curriculum_thresholds(plantos_t* h, double* out_dev, void* stream) {
+    if (!h || !out_dev) return fail(PLANTOS_EINVAL, "handle/out is NULL");
+    if (!h->p.cur_mode) return fail(PLANTOS_ESTATE, "no curriculum is active (plantos_set_curriculum)");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(out_dev, h->p.cur_thr, (size_t)h->p.N * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return PLANTOS_OK;
 }
 

@@ -81,6 +81,13 @@ struct Params {
     unsigned int* ep_log_count; // entries appended since the last drain (may exceed ep_log_cap: dropped)
     int ep_log_cap;
     unsigned int step_seq;      // number of the step launch, set by the host
+    // optional CurriculumWrapper state (plantos_set_curriculum; generic kernel only)
+    int cur_mode;               // 0 off, 1 reaching the threshold terminates (A2C_training.py), 2 marks only (trainingCode.py)
+    int cur_max_eps;            // max_episodes_per_maze
+    double cur_max_thr, cur_inc;
+    double* cur_thr;            // [N] exploration_threshold
+    int2* cur_cnt;              // [N] {episodes_on_current_maze, bit0 maze_completed | bit1 persistent_visit_counts is not None}
+    uint32_t* expl;             // [N][G][W] explored_map > 0, one bit per cell (restarts every episode)
 };
 
 struct StepIO {
@@ -329,8 +336,10 @@ __device__ __forceinline__ void action_target(const EnvRec& r, long long action,
 // (kObstacle when the move leaves the grid), `nib` the visit nibble of that cell (only
 // meaningful for a valid move).  Sets o.moved / o.watered; the caller applies the two possible
 // state writes (visit count +1 at (tx,ty); cell (tx,ty) thirsty -> hydrated).
+// `expl_fresh` (CurriculumWrapper only, where visit counts outlive the episode): 1 / 0 = the
+// cell is / is not yet in this episode's explored_map; -1 = no curriculum, same as nib == 0.
 __device__ __forceinline__ StepOut transition_core(EnvRec& r, long long action, int tx, int ty, int t,
-                                                   unsigned nib, int max_steps) {
+                                                   unsigned nib, int max_steps, int expl_fresh = -1) {
     StepOut o;
     o.watered = 0;
     o.moved = 0;
@@ -340,7 +349,7 @@ __device__ __forceinline__ StepOut transition_core(EnvRec& r, long long action, 
             const bool fresh = (nib == 0);                 // :197
             o.moved = 1;                                   // :203 visit_counts[new] += 1
             r.x = tx; r.y = ty;                            // :199
-            r.explored += fresh;                           // explored_map>0 count, :198-200,320
+            r.explored += expl_fresh < 0 ? (int)fresh : expl_fresh;   // explored_map>0 count, :198-200,320
             o.ridx = fresh ? 0 : 1;                        // R_EXPLORATION / R_REVISIT
         } else {
             r.flags |= kFlagCollided;                      // :209
@@ -389,13 +398,13 @@ template <class Mem>
 __device__ __forceinline__ StepOut apply_action(EnvRec& r, long long action, int tx, int ty, bool inb,
                                                 uint64_t row_word, uint64_t* word_ptr,
                                                 uint32_t* vis_e, uint16_t* visov_e, int G, int VW,
-                                                int max_steps, const Mem& mem) {
+                                                int max_steps, const Mem& mem, int expl_fresh = -1) {
     const int t = inb ? cell_of(row_word, ty & 31) : kObstacle;
     uint32_t* vp = vis_e + nib_word(tx, ty, VW);
     const int sh = nib_shift(ty);
     uint32_t w = 0;
     if (action < 4 && t != kObstacle) w = mem.ld32(vp);
-    const StepOut o = transition_core(r, action, tx, ty, t, (w >> sh) & 15u, max_steps);
+    const StepOut o = transition_core(r, action, tx, ty, t, (w >> sh) & 15u, max_steps, expl_fresh);
     if (o.moved) bump_visit(vp, w, sh, visov_e + tx * G + ty, mem);
     if (o.watered) mem.st64(word_ptr, row_word ^ (1ull << (2 * (ty & 31))));  // 3 -> 2
     return o;

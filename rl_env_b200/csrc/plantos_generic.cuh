@@ -21,8 +21,12 @@ __host__ __device__ inline int generic_warp_scratch_bytes(int G, int W, int D) {
 // ----------------------------------------------------------------- observation
 // plantos_env.py:251-315.  `plane` (shared memory, indexed by grid row) must hold the type
 // rows x-R .. x+R that lie inside the grid; visit nibbles are read from global memory.
+// `fresh_visits`: show the visit window of a just-reset env (1 under the rover, 0 elsewhere) instead of
+// the stored plane -- CurriculumWrapper restores the persistent counts only AFTER env.reset() has
+// built its observation (A2C_training.py:82-87).
 __device__ __forceinline__ void build_obs_warp(const Params& p, const Tables& t, const uint64_t* plane,
-                                               const uint32_t* vis_e, int x, int y, float* obs_s, int lane) {
+                                               const uint32_t* vis_e, int x, int y, float* obs_s, int lane,
+                                               bool fresh_visits = false) {
     const int G = p.G, W = p.W, R = p.R, C = p.C;
     for (int i = lane; i < C; i += 32) {                 // one lane per ray
         int dist = R, kind = kEmpty;                     // :262-263
@@ -48,7 +52,9 @@ __device__ __forceinline__ void build_obs_warp(const Params& p, const Tables& t,
     }
     if (lane < 25) {                                     // :298-313; border nibbles (15) read as 1.0
         const int gx = x + lane / 5 - 2, gy = y + lane % 5 - 2;
-        const unsigned nib = (vis_e[nib_word(gx, gy, p.VW)] >> nib_shift(gy)) & 15u;
+        unsigned nib = (vis_e[nib_word(gx, gy, p.VW)] >> nib_shift(gy)) & 15u;
+        if (fresh_visits)
+            nib = ((unsigned)gx >= (unsigned)G || (unsigned)gy >= (unsigned)G) ? 15u : (lane == 12 ? 1u : 0u);
         obs_s[5 * C + 2 + lane] = t.visit[nib];
     }
     __syncwarp();
@@ -63,7 +69,9 @@ __device__ __forceinline__ void store_obs_row(const float* obs_s, float* dst, in
 // rows and a fresh visit-nibble plane (zeros, rover cell = 1, plantos_env.py:146-147; border
 // 15) to global memory and returns the fresh record in all lanes.  `episode` selects the
 // injected map / Philox counter and is stored incremented.
-__device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int episode, uint64_t* plane, int lane) {
+// `keep_visits` (curriculum): leave the visit planes as they are (persistent_visit_counts).
+__device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int episode, uint64_t* plane, int lane,
+                                                 bool keep_visits = false) {
     const int G = p.G, W = p.W;
     const int nwords = G * W;
     int rx = 0, ry = 0;
@@ -157,7 +165,11 @@ __device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int epi
     // visit nibbles: 0 inside the grid, 15 on the border / row padding, 1 under the rover
     uint32_t* vis_e = p.vis4 + (size_t)e * p.VE;
     const int VW = p.VW;
-    for (int wi = lane; wi < p.VE; wi += 32) {
+    if (p.cur_mode) {                                    // explored_map: zeros, 2 under the rover (:144-145)
+        uint32_t* ex = p.expl + (size_t)e * nwords;
+        for (int idx = lane; idx < nwords; idx += 32) ex[idx] = (idx == rx * W + (ry >> 5)) ? (1u << (ry & 31)) : 0u;
+    }
+    for (int wi = lane; wi < (keep_visits ? 0 : p.VE); wi += 32) {
         const int vx = wi / VW - kVisRowPad, c0 = (wi % VW) * 8 - 2;
         uint32_t word = 0;
 #pragma unroll
@@ -214,6 +226,27 @@ __device__ __forceinline__ void accumulate_stats(const Params& p, bool done, con
     }
 }
 
+// CurriculumWrapper.reset (A2C_training.py:57-90): called by lane 0 before env e is reset; returns
+// whether the visit counts persist into the new episode.
+__device__ __forceinline__ bool curriculum_on_reset(const Params& p, int e) {
+    int2 c = p.cur_cnt[e];
+    double thr = p.cur_thr[e];
+    c.x += 1;                                                  // episodes_on_current_maze += 1
+    const bool timeout = c.x >= p.cur_max_eps;
+    bool keep;
+    if ((c.y & 1) || timeout) {
+        if (c.y & 1) thr = fmin(thr + p.cur_inc, p.cur_max_thr);   // :68-72
+        c.x = 0; c.y = 0;                                      // maze_completed = False; persistent = None
+        keep = false;
+    } else {
+        keep = (c.y & 2) != 0;                                 // :84-87
+        c.y |= 2;
+    }
+    p.cur_cnt[e] = c;
+    p.cur_thr[e] = thr;
+    return keep;
+}
+
 // -------------------------------------------------- one env, one warp (any config)
 __device__ __forceinline__ void step_env_warp(const Params& p, const Tables& t, const StepIO& io, int e,
                                               uint64_t* plane, float* obs_s, int lane) {
@@ -244,8 +277,22 @@ __device__ __forceinline__ void step_env_warp(const Params& p, const Tables& t, 
         const int widx = inb ? tx * p.W + (ty >> 5) : 0;
         const uint64_t word = inb ? plane[widx] : kObstAll;
         uint64_t newword = word;   // (generic pointer to a local: plain accessors only)
-        const StepOut o = apply_action(r, action, tx, ty, inb, word, &newword, vis_e, visov_e, p.G, p.VW,
-                                       p.max_steps, PlainMem());
+        int expl_fresh = -1;
+        if (p.cur_mode && inb && action < 4) {                 // this episode's explored_map (:198-200)
+            uint32_t* ex = p.expl + ((size_t)e * p.G + tx) * p.W + (ty >> 5);
+            const uint32_t bit = 1u << (ty & 31);
+            expl_fresh = (*ex & bit) ? 0 : 1;
+            if (cell_of(word, ty & 31) != kObstacle) *ex |= bit;
+        }
+        StepOut o = apply_action(r, action, tx, ty, inb, word, &newword, vis_e, visov_e, p.G, p.VW,
+                                 p.max_steps, PlainMem(), expl_fresh);
+        if (p.cur_mode) {                                      // CurriculumWrapper.step (:94-100)
+            const double pct = ((double)r.explored / (double)r.total_free) * 100.0;    // plantos_env.py:334
+            if (pct >= p.cur_thr[e]) {
+                p.cur_cnt[e].y |= 1;                           // maze_completed
+                if (p.cur_mode == 1) o.terminated = 1;
+            }
+        }
         if (o.watered) { plane[widx] = newword; types_e[widx] = newword; }
         r.ret += t.rw64[o.ridx];
         io.reward[e] = t.rw32[o.ridx];
@@ -278,8 +325,13 @@ __device__ __forceinline__ void step_env_warp(const Params& p, const Tables& t, 
         accumulate_stats(p, lane == 0, r, (flagw >> 17) & 1, (flagw >> 18) & 1, lane, e);
         episode = __shfl_sync(0xffffffffu, episode, 0);
         __syncwarp();
-        const EnvRec nr = reset_env_warp(p, e, episode, plane, lane);
-        build_obs_warp(p, t, plane, vis_e, nr.x, nr.y, obs_s, lane);
+        int keep = 0;
+        if (p.cur_mode) {
+            if (lane == 0) keep = curriculum_on_reset(p, e) ? 1 : 0;
+            keep = __shfl_sync(0xffffffffu, keep, 0);
+        }
+        const EnvRec nr = reset_env_warp(p, e, episode, plane, lane, keep != 0);
+        build_obs_warp(p, t, plane, vis_e, nr.x, nr.y, obs_s, lane, keep != 0);
         store_obs_row(obs_s, obs_row, p.D, lane);
         if (lane == 0) pack_rec(nr, ra, rb);
     }
@@ -315,8 +367,13 @@ k_reset_all(const Params p, float* obs) {
         int episode = 0;
         if (lane == 0) episode = (int)p.rec[2 * (size_t)e].w;
         episode = __shfl_sync(0xffffffffu, episode, 0);
-        const EnvRec nr = reset_env_warp(p, e, episode, plane, lane);
-        build_obs_warp(p, t, plane, p.vis4 + (size_t)e * p.VE, nr.x, nr.y, obs_s, lane);
+        int keep = 0;
+        if (p.cur_mode) {
+            if (lane == 0) keep = curriculum_on_reset(p, e) ? 1 : 0;
+            keep = __shfl_sync(0xffffffffu, keep, 0);
+        }
+        const EnvRec nr = reset_env_warp(p, e, episode, plane, lane, keep != 0);
+        build_obs_warp(p, t, plane, p.vis4 + (size_t)e * p.VE, nr.x, nr.y, obs_s, lane, keep != 0);
         store_obs_row(obs_s, obs + (size_t)e * p.D, p.D, lane);
         if (lane == 0) {
             uint4 ra, rb;

@@ -49,6 +49,14 @@ class _Box:
         self.high = np.full(self.shape, high, dtype=self.dtype)
 
 
+# the two CurriculumWrapper variants the reference ships, with the arguments of their call sites
+CURRICULA: Dict[str, Dict[str, Any]] = {
+    "a2c": dict(mode="terminate", initial_threshold=40.0, max_threshold=100.0, threshold_increment=10.0,
+                max_episodes_per_maze=3),      # A2C_training.py:40,55,121
+    "dqn": dict(mode="mark", initial_threshold=30.0, max_threshold=100.0, threshold_increment=5.0,
+                max_episodes_per_maze=50),     # trainingCode.py:29,44,107
+}
+
 PRESETS: Dict[str, Dict[str, int]] = {
     # ctor defaults, plantos_env.py:25-26 (D = 77)
     "default": dict(grid_size=21, num_plants=8, num_obstacles=50, lidar_range=2, lidar_channels=10),
@@ -130,7 +138,7 @@ class PlantOSVecEnv:
                  env_id_base: int = 0, kernel: str = "auto",
                  rewards: Optional[Dict[str, float]] = None,
                  track_terminal_obs: bool = True, full_infos: Optional[bool] = None,
-                 obs_ring: int = 1):
+                 obs_ring: int = 1, curriculum: Any = None):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("PlantOSVecEnv runs on a CUDA device only (no CPU path)")
@@ -171,6 +179,20 @@ class PlantOSVecEnv:
         handle = C.c_void_p()
         nat.check(self._lib.plantos_create(C.byref(cfg), dev_index, C.byref(handle)))
         self._h = handle
+
+        # CurriculumWrapper on the device: "a2c" (A2C_training.py:37-109, :121), "dqn"
+        # (trainingCode.py:24-98, :107) or a dict(mode="terminate"|"mark", initial_threshold,
+        # max_threshold, threshold_increment, max_episodes_per_maze)
+        self.curriculum = None
+        if curriculum is not None:
+            cur = dict(CURRICULA[curriculum]) if isinstance(curriculum, str) else dict(curriculum)
+            base = dict(CURRICULA["a2c" if cur.get("mode", "terminate") == "terminate" else "dqn"])
+            base.update(cur)
+            mode = {"terminate": nat.CURRICULUM_TERMINATE, "mark": nat.CURRICULUM_MARK}[base["mode"]]
+            nat.check(self._lib.plantos_set_curriculum(
+                self._h, mode, float(base["initial_threshold"]), float(base["max_threshold"]),
+                float(base["threshold_increment"]), int(base["max_episodes_per_maze"])))
+            self.curriculum = base
 
         # tables evaluated by the Python interpreter, exactly as the reference evaluates them
         off = np.ascontiguousarray(tables.lidar_offsets(self.lidar_channels, self.lidar_range))
@@ -423,6 +445,12 @@ class PlantOSVecEnv:
         self._ep_cap = int(capacity) if capacity is not None else 4 * self.num_envs
         nat.check(self._lib.plantos_episode_log_enable(self._h, self._ep_cap))
         self._ep_buf = np.zeros(self._ep_cap, dtype=self.EPISODE_DTYPE)
+
+    def curriculum_thresholds(self) -> torch.Tensor:
+        """Current exploration threshold of every env (float64 CUDA tensor)."""
+        out = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
+        nat.check(self._lib.plantos_get_curriculum_thresholds(self._h, out.data_ptr(), self._stream()))
+        return out
 
     def drain_episode_log(self):
         """Finished episodes since the last drain as a structured array (fields env [global id], l,

@@ -40,7 +40,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-from oracle.ref_shim import ReferenceEnv  # noqa: E402
+from oracle.ref_shim import ReferenceEnv, load_curriculum_wrapper  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
@@ -71,11 +71,49 @@ def lidar_ints(env, obs: np.ndarray):
     return dist, kind
 
 
+class _Raw:
+    """Uniform access for `record`: `.env` is the raw PlantOSEnv whether or not the reference's
+    CurriculumWrapper sits in between; reset/step go through the outermost layer."""
+
+    def __init__(self, outer, raw_holder):
+        self.outer, self.holder = outer, raw_holder
+
+    @property
+    def env(self):
+        return self.holder.env
+
+    @property
+    def mistake_steps(self):
+        return self.holder.mistake_steps
+
+    def reset(self):
+        return self.outer.reset()
+
+    def step(self, a):
+        return self.outer.step(a)
+
+
 def record(name: str, n: int, steps: int, seed: int, kwargs: dict, max_steps: int = 1000,
-           snap_every: int = 250) -> None:
+           snap_every: int = 250, curriculum: str = "", cur_max_eps: int = 0) -> None:
+    """`curriculum` = "a2c" / "dqn": every env is wrapped in the reference's OWN CurriculumWrapper
+    (class compiled from A2C_training.py / trainingCode.py, constructed as at their call sites
+    :121 / :107) -- Monitor(CurriculumWrapper(PlantOSEnv)) as in make_env_wrapper.
+    `cur_max_eps` overrides max_episodes_per_maze (a plain attribute) so that short fixtures see
+    the time-out branch of the 50-episode variant too."""
     random.seed(seed)
+    np.random.seed(seed)   # CurriculumWrapper draws (unused) maze seeds from numpy's global RNG
     rng = np.random.default_rng(seed)
-    envs = [ReferenceEnv(**kwargs) for _ in range(n)]
+    holders = [ReferenceEnv(**kwargs) for _ in range(n)]
+    if curriculum:
+        wrapper = load_curriculum_wrapper(curriculum)
+        init = {"a2c": 40.0, "dqn": 30.0}[curriculum]
+        outers = [wrapper(h, initial_threshold=init, max_threshold=100.0) for h in holders]
+        for o in outers:
+            if cur_max_eps:
+                o.max_episodes_per_maze = cur_max_eps
+    else:
+        outers = holders
+    envs = [_Raw(o, h) for o, h in zip(outers, holders)]
     for e in envs:
         e.env.max_steps = max_steps  # plain attribute, plantos_env.py:120
     g = kwargs["grid_size"]
@@ -97,6 +135,7 @@ def record(name: str, n: int, steps: int, seed: int, kwargs: dict, max_steps: in
     lidar_dist = np.zeros((steps, n, c), np.uint8)
     lidar_kind = np.zeros((steps, n, c), np.uint8)
     vhash = np.zeros((steps, n), np.uint64)
+    cur_thr = np.zeros((steps, n), np.float64)
     term_t, term_i, term_obs, ep_r, ep_l = [], [], [], [], []
     ep_rewards = [[] for _ in range(n)]
     snap_t, snap_visits, snap_cells = [], [], []
@@ -117,6 +156,8 @@ def record(name: str, n: int, steps: int, seed: int, kwargs: dict, max_steps: in
             ints["collided"][t, i] = info["collided_with_wall"]
             lidar_dist[t, i], lidar_kind[t, i] = lidar_ints(e.env, o)
             vhash[t, i] = visit_hash(e.env.visit_counts)
+            if curriculum:
+                cur_thr[t, i] = e.outer.exploration_threshold
             if te or tr:
                 term_t.append(t)
                 term_i.append(i)
@@ -146,7 +187,8 @@ def record(name: str, n: int, steps: int, seed: int, kwargs: dict, max_steps: in
         path,
         cfg_grid_size=g, cfg_num_plants=kwargs["num_plants"], cfg_num_obstacles=kwargs["num_obstacles"],
         cfg_lidar_range=kwargs["lidar_range"], cfg_lidar_channels=c, cfg_max_steps=max_steps,
-        cfg_seed=seed, cfg_mistake_steps=mistakes,
+        cfg_seed=seed, cfg_mistake_steps=mistakes, cfg_curriculum=curriculum,
+        cfg_cur_max_eps=(cur_max_eps or {"": 0, "a2c": 3, "dqn": 50}[curriculum]), cur_threshold=cur_thr,
         maps_cells=maps_cells, maps_rover=maps_rover, n_maps=n_maps, reset_obs=reset_obs,
         actions=actions, obs=obs, rewards=rewards, terminated=terminated, truncated=truncated,
         term_t=np.array(term_t, np.int32), term_i=np.array(term_i, np.int32),
@@ -177,9 +219,21 @@ FIXTURES = [
      dict(grid_size=64, num_plants=64, num_obstacles=600, lidar_range=32, lidar_channels=16), 100),
 ]
 
+# CurriculumWrapper fixtures: small grids so that thresholds are reached and raised
+CURRICULUM_FIXTURES = [
+    ("replay_curr_a2c_4env", 4, 3000, 21,
+     dict(grid_size=6, num_plants=2, num_obstacles=3, lidar_range=3, lidar_channels=8), 150, "a2c", 0),
+    ("replay_curr_dqn_3env", 3, 3000, 22,
+     dict(grid_size=6, num_plants=2, num_obstacles=3, lidar_range=4, lidar_channels=6), 200, "dqn", 4),
+]
+
 if __name__ == "__main__":
     only = set(sys.argv[1:])
     for name, n, steps, seed, kw, ms in FIXTURES:
         if only and name not in only:
             continue
         record(name, n, steps, seed, kw, max_steps=ms)
+    for name, n, steps, seed, kw, ms, cur, cme in CURRICULUM_FIXTURES:
+        if only and name not in only:
+            continue
+        record(name, n, steps, seed, kw, max_steps=ms, curriculum=cur, cur_max_eps=cme)

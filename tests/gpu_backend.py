@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from replay import fixture_kwargs
+from replay import fixture_curriculum, fixture_kwargs
 
 
 class GpuBackend:
@@ -13,10 +13,15 @@ class GpuBackend:
         (env index = replica * n + i) so that a small fixture fills several 32-env pipeline
         stages of the fast kernel; every copy must behave identically and copy 0 is returned."""
         from rl_env_b200 import PlantOSVecEnv
+        from rl_env_b200.vec_env import CURRICULA
         self.n = fx["actions"].shape[1]
         self.reps = replicas
+        cur = fixture_curriculum(fx)
+        if cur is not None:     # the reference's CurriculumWrapper variant, with the fixture's overrides
+            cur = dict(CURRICULA[cur["variant"]], max_episodes_per_maze=cur["max_episodes_per_maze"])
         self.env = PlantOSVecEnv(self.n * replicas, device=device, map_source="injected", kernel=kernel,
-                                 max_steps=int(fx["cfg_max_steps"]), full_infos=False, **fixture_kwargs(fx))
+                                 max_steps=int(fx["cfg_max_steps"]), full_infos=False, curriculum=cur,
+                                 **fixture_kwargs(fx))
         self.env.push_maps(np.tile(fx["maps_cells"], (replicas, 1, 1, 1)), np.tile(fx["maps_rover"], (replicas, 1, 1)))
 
     def _fold(self, a):

@@ -15,6 +15,7 @@ if ROOT not in sys.path:
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 FIXTURES = ["replay_T_8env", "replay_DFLT_1env", "replay_tiny_4env", "replay_odd_4env", "replay_XL_2env"]
+CURRICULUM_FIXTURES = ["replay_curr_a2c_4env", "replay_curr_dqn_3env"]   # recorded through the reference's CurriculumWrapper
 STATE_KEYS = ("x", "y", "step_count", "explored", "total_cells", "thirsty", "collisions", "collided")
 FLOAT_TOL = 1e-5  # BASELINE.json north_star: rewards / float observations within 1e-5 absolute
 
@@ -28,6 +29,14 @@ def fixture_kwargs(fx) -> Dict[str, int]:
     return dict(grid_size=int(fx["cfg_grid_size"]), num_plants=int(fx["cfg_num_plants"]),
                 num_obstacles=int(fx["cfg_num_obstacles"]), lidar_range=int(fx["cfg_lidar_range"]),
                 lidar_channels=int(fx["cfg_lidar_channels"]))
+
+
+def fixture_curriculum(fx):
+    """None, or the CurriculumWrapper variant + overrides the fixture was recorded with."""
+    variant = str(fx["cfg_curriculum"]) if "cfg_curriculum" in fx else ""
+    if not variant:
+        return None
+    return dict(variant=variant, max_episodes_per_maze=int(fx["cfg_cur_max_eps"]))
 
 
 def visit_hash(v: np.ndarray) -> np.uint64:
@@ -129,7 +138,8 @@ class PyOracleBackend:
         n = fx["actions"].shape[1]
         maps = [[(fx["maps_cells"][i, k], tuple(fx["maps_rover"][i, k])) for k in range(int(fx["n_maps"][i]))]
                 for i in range(n)]
-        self.env = OracleVecEnv(n, maps=maps, max_steps=int(fx["cfg_max_steps"]), **fixture_kwargs(fx))
+        self.env = OracleVecEnv(n, maps=maps, curriculum=fixture_curriculum(fx), max_steps=int(fx["cfg_max_steps"]),
+                                **fixture_kwargs(fx))
         self.n = n
 
     def reset(self):

@@ -4,7 +4,7 @@ EXACTLY: bit-equal float32 observations, exact float64 rewards, identical intege
 import numpy as np
 import pytest
 
-from replay import FIXTURES, COracleBackend, PyOracleBackend, check_replay, load_fixture
+from replay import CURRICULUM_FIXTURES, FIXTURES, COracleBackend, PyOracleBackend, check_replay, load_fixture
 
 
 @pytest.mark.parametrize("name", FIXTURES)
@@ -47,6 +47,17 @@ def test_fixture_covers_edge_cases():
     assert np.isclose(t8["rewards"], -10.1).any()
     assert (t8["lidar_dist"][..., 1] == 1).any()  # ray 1 has offset (0,0) at r=1: sees the rover's own cell
     assert int(tiny["cfg_lidar_range"]) > int(tiny["cfg_grid_size"])
+
+
+@pytest.mark.parametrize("name", CURRICULUM_FIXTURES)
+def test_python_port_replays_reference_curriculum(name):
+    """CurriculumOracle (the restated CurriculumWrapper, both variants) against trajectories
+    recorded through the reference's own wrapper class: persistent visit counts, threshold
+    terminations, threshold increments, the fresh-looking reset observation."""
+    fx = load_fixture(name)
+    res = check_replay(fx, PyOracleBackend(fx))
+    assert res["episodes"] >= 40 and res["bitexact_obs"] == 1 and res["bitexact_reward"] == 1
+    assert len(np.unique(fx["cur_threshold"])) >= 5            # thresholds were reached and raised
 
 
 # ---- observation batches left behind by the reference's own training runs (make_last_obs.py)
