@@ -84,3 +84,50 @@ def test_golden_fixtures_are_reproducible():
         assert set(new.files) == set(old.files)
         for k in old.files:
             assert np.array_equal(new[k], old[k]), k
+
+
+@pytest.mark.parametrize("variant,init,max_eps", [("a2c", 40.0, 3), ("dqn", 30.0, 4)])
+def test_curriculum_port_matches_the_reference_wrapper_class(variant, init, max_eps):
+    """CurriculumOracle vs the reference's own CurriculumWrapper (class compiled from
+    A2C_training.py:37-109 / trainingCode.py:24-98) around the real env, in lock-step: observations,
+    rewards, flags, visit_counts, thresholds -- including the observation returned by reset."""
+    import random
+    from oracle.plantos_oracle import CurriculumOracle, PlantOSOracle
+    from oracle.ref_shim import ReferenceEnv, load_curriculum_wrapper
+
+    def cells_of(env):
+        g = env.grid_size
+        p = np.zeros((g, g), dtype=np.uint8)
+        for (x, y) in env.obstacles:
+            p[x, y] = 1
+        for (x, y), thirsty in env.plants.items():
+            p[x, y] = 3 if thirsty else 2
+        return p
+
+    kw = dict(grid_size=7, num_plants=3, num_obstacles=4, lidar_range=4, lidar_channels=8)
+    random.seed(3)
+    np.random.seed(3)
+    ref = load_curriculum_wrapper(variant)(ReferenceEnv(**kw), initial_threshold=init, max_threshold=100.0)
+    ref.max_episodes_per_maze = max_eps
+    ora = CurriculumOracle(PlantOSOracle(**kw), variant, max_episodes_per_maze=max_eps)
+    raw = ref.env.env
+    raw.max_steps = ora.env.max_steps = 90
+    o, _ = ref.reset()
+    o2, _ = ora.reset(cells_of(raw), raw.rover_pos)
+    assert np.array_equal(o, o2)
+    rng = np.random.default_rng(5)
+    episodes, thresholds = 0, set()
+    for t in range(4000):
+        a = int(rng.integers(0, 5))
+        o, r, te, tr, _ = ref.step(a)
+        o2, r2, te2, tr2, _ = ora.step(a)
+        assert np.array_equal(o, o2) and r == r2 and te == te2 and tr == tr2, t
+        assert np.array_equal(raw.visit_counts, ora.env.visit_counts)
+        assert ref.exploration_threshold == ora.exploration_threshold and ref.maze_completed == ora.maze_completed
+        thresholds.add(ref.exploration_threshold)
+        if te or tr:
+            episodes += 1
+            o, _ = ref.reset()
+            o2, _ = ora.reset(cells_of(raw), raw.rover_pos)
+            assert np.array_equal(o, o2) and np.array_equal(raw.visit_counts, ora.env.visit_counts)
+    assert episodes >= 40 and len(thresholds) >= 4
