@@ -642,7 +642,7 @@ extern "C" int64_t plantos_launch_count(const plantos_t* h) { return h ? h->laun
 
 extern "C" const char* plantos_kernel_name(const plantos_t* h) {
     if (!h) return "";
-    if (!h->use_fast) return "generic";
+    if (!h->use_fast || h->p.cur_mode) return "generic";
     return "fast";
 }
 

@@ -303,6 +303,14 @@ class PlantOSVecEnv:
         self.step_async(actions)
         return self.step_wait()
 
+    # ------------------------------------------------------------------ step_many
+    def make_rollout(self, k: int) -> "GraphRollout":
+        """K open-loop steps as ONE CUDA-graph launch: `rollout(actions[K, N])` returns the K
+        observation / reward / done tensors (static buffers, overwritten by the next call).  For
+        MCTS-style rollouts (mcts_custom_trainer.py:168-243 steps a copied env with a fixed action
+        sequence) and for small batches, where the per-step host launch cost dominates."""
+        return GraphRollout(self, k)
+
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:
             self._lib.plantos_destroy(self._h)
@@ -465,6 +473,43 @@ class PlantOSVecEnv:
             out[name] = raw[name]
         out["env"] = raw["env"].astype(np.int64) + self.env_id_base
         return out, int(dropped.value)
+
+
+class GraphRollout:
+    """See PlantOSVecEnv.make_rollout.  The K plantos_step launches are captured once into a
+    torch.cuda.CUDAGraph with static action / output buffers; a call copies the actions in and
+    replays the graph.  Auto-reset applies inside the rollout exactly as in single steps; infos are
+    not produced (read `env.scalars()` afterwards if needed); the device episode log would stamp
+    every replay with the step numbers of the capture."""
+
+    def __init__(self, env: "PlantOSVecEnv", k: int):
+        if k < 1:
+            raise ValueError("k must be >= 1")
+        n, d, dev = env.num_envs, env.obs_dim, env.device
+        self.env, self.k = env, int(k)
+        self.actions = torch.zeros((k, n), dtype=torch.int64, device=dev)
+        # [K, N, D] view whose per-step stride is padded to 16 bytes (the fast kernel's row stores)
+        stride = (n * d + 3) // 4 * 4
+        self.obs = torch.empty(k * stride, dtype=torch.float32, device=dev).as_strided((k, n, d), (stride, d, 1))
+        self.rewards = torch.empty((k, n), dtype=torch.float32, device=dev)
+        self.dones = torch.zeros((k, n), dtype=torch.bool, device=dev)
+        self.graph = torch.cuda.CUDAGraph()
+        lib, h = env._lib, env._h
+        torch.cuda.synchronize(dev)
+        with torch.cuda.graph(self.graph):
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            for t in range(self.k):
+                nat.check(lib.plantos_step(h, self.actions[t].data_ptr(), self.obs[t].data_ptr(),
+                                           self.rewards[t].data_ptr(), self.dones[t].data_ptr(), None, None, None, stream))
+
+    def __call__(self, actions):
+        if not isinstance(actions, torch.Tensor):
+            actions = torch.as_tensor(np.asarray(actions), dtype=torch.int64)
+        if tuple(actions.shape) != tuple(self.actions.shape):
+            raise ValueError(f"expected actions of shape {tuple(self.actions.shape)}, got {tuple(actions.shape)}")
+        self.actions.copy_(actions, non_blocking=True)
+        self.graph.replay()
+        return self.obs, self.rewards, self.dones
 
 
 class MonitorCSV:

@@ -144,3 +144,26 @@ def test_episode_log_and_monitor_csv_match_the_oracle_monitor(kernel, tmp_path):
         match = [w for w in want if w[0] == int(e["env"]) and w[3] == int(e["step_seq"])]
         assert match and match[0][1] == int(e["l"]) and match[0][2] == round(float(e["r"]), 6)
         assert int(e["flags"]) in (1, 2, 3)
+
+
+@pytest.mark.parametrize("n,kernel", [(4096, "fast"), (515, "fast"), (300, "generic")])
+def test_graph_rollout_equals_single_steps(n, kernel):
+    """make_rollout(K): K steps captured in one CUDA graph (incl. the programmatic-dependent-launch
+    edges of the fast kernel) give exactly what K single steps give, replay after replay."""
+    import torch
+    from rl_env_b200 import PlantOSVecEnv, PRESETS
+    kw = dict(PRESETS["training"], max_steps=37, seed=11, kernel=kernel, full_infos=False)
+    a, b = PlantOSVecEnv(n, **kw), PlantOSVecEnv(n, **kw)
+    assert torch.equal(a.reset(), b.reset())
+    K = 12
+    roll = b.make_rollout(K)
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    for rep in range(5):                                   # 60 steps: every env auto-resets at least once
+        acts = torch.randint(0, 5, (K, n), device="cuda", generator=g)
+        obs_k, rew_k, done_k = roll(acts)
+        for t in range(K):
+            obs, rew, done, _ = a.step(acts[t])
+            assert torch.equal(obs, obs_k[t]) and torch.equal(rew, rew_k[t]) and torch.equal(done, done_k[t]), (rep, t)
+    sa, sb = a.get_state(), b.get_state()
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    a.close(); b.close()
