@@ -241,6 +241,11 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------ ours
 def run_ours(args, rank: int, world: int, local_rank: int):
+    # stdout carries exactly one JSON line: anything libraries write to fd 1 meanwhile (NCCL's version
+    # banner, for one) goes to stderr instead
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from rl_env_b200 import make_sharded
@@ -263,12 +268,30 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The timed loop replays a CUDA graph of ACTION_RING single-step launches (PlantOSVecEnv.make_rollout:
+    # the same plantos_step calls, captured once; every step still reads its actions and writes its own
+    # observation / reward / done / terminal buffers) and steps the remainder eagerly; --no-graph steps
+    # eagerly throughout.
+    roll = None
+    if not args.no_graph:
+        roll = env.make_rollout(ACTION_RING, with_flags=True)
+        roll.actions.copy_(torch.stack(actions))
+
+    def maybe_stats(i):
+        if world > 1 and args.stats_every and (i + 1) % args.stats_every < (ACTION_RING if roll else 1) and i + 1 >= args.stats_every:
+            env.episode_stats_tensor(all_reduce=True)   # NCCL all-reduce of 8 doubles, no host sync
+
     def run_steps(k, start):
-        for i in range(start, start + k):
-            env.step_async(actions[i % ACTION_RING])
-            env.step_wait()
-            if world > 1 and args.stats_every and (i + 1) % args.stats_every == 0:
-                env.episode_stats_tensor(all_reduce=True)   # NCCL all-reduce of 8 doubles, no host sync
+        i, end = start, start + k
+        while i < end:
+            if roll is not None and end - i >= ACTION_RING:
+                roll.graph.replay()
+                i += ACTION_RING
+            else:
+                env.step_async(actions[i % ACTION_RING])
+                env.step_wait()
+                i += 1
+            maybe_stats(i - 1)
 
     run_steps(args.warmup, 0)
     barrier()
@@ -283,7 +306,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     barrier()
     sampler.stop()
     ms = e0.elapsed_time(e1)
-    launches = env.launch_count - launches0
+    launches = (env.launch_count - launches0) if roll is None else args.steps   # graph replays launch the same kernels
     env.check()
 
     # isolated duration of the step kernel: event pair around single launches
@@ -335,7 +358,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "config": {"workload": workload_name(world), "envs_per_gpu": n, "obs_dim": OBS_DIM,
                        "kernel": kernel_name, "maps": "philox seed 0", "state_bytes_per_env": state_bytes,
                        "l2": f"inputs larger than L2: per-GPU state {n * state_bytes / 1e6:.0f} MB + obs ring "
-                             f"{OBS_RING}x{n * OBS_DIM * 4 / 1e6:.0f} MB vs 126 MB L2; no explicit flush",
+                             f"{ACTION_RING if roll is not None else OBS_RING}x{n * OBS_DIM * 4 / 1e6:.0f} MB vs 126 MB L2; no explicit flush",
+                       "launch": ("CUDA graph of %d single-step launches, replayed" % ACTION_RING) if roll is not None else "eager, one launch per step",
                        "stats_allreduce_every": args.stats_every if world > 1 else 0},
             "e2e": {"value": total_envs * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * (4 * OBS_DIM + 4 + 1),
@@ -355,6 +379,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
         else:
             line["cpu_baseline"] = None
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -362,6 +388,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
 
 def main():
+    # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3000)
@@ -374,6 +403,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-terminal-obs", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="step eagerly instead of replaying a CUDA graph of 16 steps")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0"))

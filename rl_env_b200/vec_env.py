@@ -304,12 +304,12 @@ class PlantOSVecEnv:
         return self.step_wait()
 
     # ------------------------------------------------------------------ step_many
-    def make_rollout(self, k: int) -> "GraphRollout":
+    def make_rollout(self, k: int, with_flags: bool = False) -> "GraphRollout":
         """K open-loop steps as ONE CUDA-graph launch: `rollout(actions[K, N])` returns the K
         observation / reward / done tensors (static buffers, overwritten by the next call).  For
         MCTS-style rollouts (mcts_custom_trainer.py:168-243 steps a copied env with a fixed action
         sequence) and for small batches, where the per-step host launch cost dominates."""
-        return GraphRollout(self, k)
+        return GraphRollout(self, k, with_flags)
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:
@@ -482,7 +482,9 @@ class GraphRollout:
     not produced (read `env.scalars()` afterwards if needed); the device episode log would stamp
     every replay with the step numbers of the capture."""
 
-    def __init__(self, env: "PlantOSVecEnv", k: int):
+    def __init__(self, env: "PlantOSVecEnv", k: int, with_flags: bool = False):
+        """`with_flags`: also write the env's terminated / truncated / terminal-observation buffers
+        every step, like a single step does (they hold the last step's values afterwards)."""
         if k < 1:
             raise ValueError("k must be >= 1")
         n, d, dev = env.num_envs, env.obs_dim, env.device
@@ -498,9 +500,12 @@ class GraphRollout:
         torch.cuda.synchronize(dev)
         with torch.cuda.graph(self.graph):
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            term = env._terminated.data_ptr() if with_flags else None
+            trunc = env._truncated.data_ptr() if with_flags else None
+            tobs = env._terminal_obs.data_ptr() if (with_flags and env._terminal_obs is not None) else None
             for t in range(self.k):
                 nat.check(lib.plantos_step(h, self.actions[t].data_ptr(), self.obs[t].data_ptr(),
-                                           self.rewards[t].data_ptr(), self.dones[t].data_ptr(), None, None, None, stream))
+                                           self.rewards[t].data_ptr(), self.dones[t].data_ptr(), term, trunc, tobs, stream))
 
     def __call__(self, actions):
         if not isinstance(actions, torch.Tensor):
