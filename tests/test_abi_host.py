@@ -121,5 +121,7 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
+                # the product package neither imports nor loads anything under oracle/ (a comment may
+                # point at the host mirror of the Philox generator)
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
-                assert "plantos_oracle" not in src or f.endswith(".cuh") is False and "mirrored" in src.lower(), f
+                assert "plantos_oracle" not in src and "ref_shim" not in src, f
