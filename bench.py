@@ -293,6 +293,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 i += 1
             maybe_stats(i - 1)
 
+    # untimed extra steps before the W warm-up steps: first launches, graph instantiation and the
+    # first NCCL collective on every rank (a cold rank once made a whole 4-GPU run 30 % slower)
+    run_steps(2 * ACTION_RING, 0)
+    if world > 1:
+        env.episode_stats_tensor(all_reduce=True)
+    barrier()
     run_steps(args.warmup, 0)
     barrier()
     sampler = ClockSampler(local_rank)
@@ -337,7 +343,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     stats = env.episode_stats_tensor(all_reduce=True).cpu().tolist()
     t_ms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    per_rank_ms = [ms]
     if world > 1:
+        gathered = [torch.zeros_like(t_ms) for _ in range(world)]
+        dist.all_gather(gathered, t_ms)
+        per_rank_ms = [float(g[0]) for g in gathered]     # the timed region of every rank (value uses the max)
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms, e2e_ms = t_ms.tolist()
     kernel_name = env.kernel_name
@@ -372,6 +382,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                          "alg_bytes_per_env_step": B_ALG, "kernel": f"k_step_{kernel_name}",
                          "avg_launch_us": step_s * 1e6, "isolated_launch_us_median": iso_med_us},
             "clocks": sampler.summary(),
+            "ms_per_step_by_rank": [round(m / args.steps, 6) for m in per_rank_ms],
             "episode_stats": dict(zip(("episodes", "return_sum", "length_sum", "exploration_pct_sum",
                                        "collisions_sum", "watered_sum", "terminated", "truncated"), stats)),
         }
