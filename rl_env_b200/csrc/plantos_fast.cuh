@@ -76,6 +76,18 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
     asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
 }
+// window / tile accesses through 32-bit shared addresses (volatile: the data changes every trip).
+// Generic-pointer accesses made the compiler rebuild the shared-window base (S2UR SR_CgaCtaId ...)
+// and the per-warp scratch address from threadIdx inside the trip loop.
+__device__ __forceinline__ uint64_t lds_u64_v(uint32_t a) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32_v(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float4 lds_f32x4_v(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0+%1], %2;" :: "r"(a), "n"(OFF), "f"(v)); }
 __device__ __forceinline__ void cp_async8(uint32_t sdst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sdst), "l"(gsrc) : "memory");
 }
@@ -204,7 +216,6 @@ k_step_fast(const Params p, const StepIO io) {
     const uint32_t s_rw32 = smem_u32(t.rw32), s_rw64 = smem_u32(t.rw64);
     constexpr uint64_t LOWPAD = kObstAll & ((1ull << (2 * R)) - 1ull);
     constexpr int NCH = 2;             // envs per half-warp and trip, interleaved for ILP
-    const float4* src4 = reinterpret_cast<const float4*>(tile);
     // Window copy roles: 8 lanes per env of the trip, lane c8 serves chunks c8 and c8 + 8 of env
     // cj (chunks 0 .. TCH-1 are type rows, TCH .. NCHUNK-1 nibble rows; the second round is always
     // a nibble row because TCH <= 8).  Destination offsets inside a window buffer and the source
@@ -216,12 +227,20 @@ k_step_fast(const Params p, const StepIO io) {
     const uint32_t cp1_dst = s_scr + 512 + cj * S1 + 16 * c8;
     // byte offset inside a window buffer of nibble row `sub` (chunk TCH + sub) of the two envs this
     // half-warp handles in a trip (env 2c + half)
-    int voff[2];
+    uint32_t s_vrow[2];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         const int j = 2 * c + (lane >> 4), kk = TCH + (lane & 15);
-        voff[c] = kk < 8 ? j * 128 + 16 * kk : 512 + j * S1 + 16 * (kk - 8);
+        s_vrow[c] = s_scr + (kk < 8 ? j * 128 + 16 * kk : 512 + j * S1 + 16 * (kk - 8));
     }
+    // 32-bit shared addresses of this lane's type row slot (chain 0, even start row; chain 1 is 256
+    // bytes on), of its ray's five floats and of its visit cell in tile row `half` (chain 1 is two
+    // rows = 8 * D bytes on), and of its float4 of the flush
+    const uint32_t s_trow = s_scr + half * 128 + sub * 8;
+    const uint32_t s_tile = s_scr + 2 * win_bytes;
+    const uint32_t s_ray = s_tile + (half * D + 5 * sub) * 4;
+    const uint32_t s_cell = s_tile + (half * D + 5 * C + 2 + sub) * 4;
+    const uint32_t s_flush = s_tile + 16 * lane;
 
     TSTAMP(2);
     if (wbase < wend) {
@@ -312,8 +331,7 @@ k_step_fast(const Params p, const StepIO io) {
             __syncwarp();
             if (trip == 0) TSTAMP(6);
             if (trip == 0 && has_next) issue_target(e_next);     // its records landed with this trip's windows
-            const unsigned char* const wbuf = win_buf(wb);
-            const uint64_t* twin = reinterpret_cast<const uint64_t*>(wbuf);
+            const uint32_t wboff = wb * win_bytes;
 
             int x[NCH], y[NCH], tb[NCH];
             unsigned w[NCH], vslice[NCH], acc[NCH], s0[NCH], s1[NCH];
@@ -325,20 +343,20 @@ k_step_fast(const Params p, const StepIO io) {
                 const unsigned pw = __shfl_sync(FULL, posw, base + 2 * c + half);
                 x[c] = pw & 31; y[c] = pw >> 5;
                 // first needed type row inside the fetched window: padded row x+2 minus the even start
-                tb[c] = (2 * c + half) * 16 + (x[c] & 1);       // 128 bytes per env
+                tb[c] = (x[c] & 1) * 8;                         // byte offset of the first needed row
             }
             // stage 2: shared-memory reads: this lane's type row and visit-nibble words
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 trow[c] = kObstAll;
-                if (has_row) trow[c] = twin[tb[c] + sub];
+                if (has_row) trow[c] = lds_u64_v(s_trow + c * 256 + wboff + tb[c]);
                 vlo[c] = 0; vhi[c] = 0;
                 if (has_vrow) {
                     // the 5 nibbles y .. y+4 start in word y>>3 and may spill into the next one
                     // (when they sit entirely in word 3 the funnel's high half is unused)
                     const unsigned w0 = (unsigned)y[c] >> 3, w1 = w0 < 3u ? w0 + 1u : 3u;
-                    const uint32_t* vr = reinterpret_cast<const uint32_t*>(wbuf + voff[c]);
-                    vlo[c] = vr[w0]; vhi[c] = vr[w1];
+                    const uint32_t vr = s_vrow[c] + wboff;
+                    vlo[c] = lds_u32_v(vr + 4 * w0); vhi[c] = lds_u32_v(vr + 4 * w1);
                 }
             }
             // stage 3: rover-centred window word (cells y-R .. y+R of this lane's row, walls
@@ -387,24 +405,22 @@ k_step_fast(const Params p, const StepIO io) {
                 fv1[c] = lds_f32(s_visit + 4 * ((s1[c] >> vsh1) & 15u));
             }
             // stage 6: stores into the tile (row 2c + half)
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                float* row = tile + (2 * c + half) * D;
-                if (has_ray) {                                // :286-292
-                    float* q = row + 5 * sub;
-                    q[0] = fd[c]; q[1] = oh[c].x; q[2] = oh[c].y; q[3] = oh[c].z; q[4] = oh[c].w;
-                }
-                if (sub < 2) row[5 * C + sub] = fp[c];        // :294-296
-                row[5 * C + 2 + sub] = fv0[c];                // :298-313
-                if (has_v1) row[5 * C + 18 + sub] = fv1[c];
+            if (has_ray) {                                    // :286-292
+                sts_f32<0>(s_ray, fd[0]); sts_f32<4>(s_ray, oh[0].x); sts_f32<8>(s_ray, oh[0].y);
+                sts_f32<12>(s_ray, oh[0].z); sts_f32<16>(s_ray, oh[0].w);
+                sts_f32<8 * D>(s_ray, fd[1]); sts_f32<8 * D + 4>(s_ray, oh[1].x); sts_f32<8 * D + 8>(s_ray, oh[1].y);
+                sts_f32<8 * D + 12>(s_ray, oh[1].z); sts_f32<8 * D + 16>(s_ray, oh[1].w);
             }
+            if (sub < 2) { sts_f32<-8>(s_cell, fp[0]); sts_f32<8 * D - 8>(s_cell, fp[1]); }      // :294-296
+            sts_f32<0>(s_cell, fv0[0]); sts_f32<8 * D>(s_cell, fv0[1]);                           // :298-313
+            if (has_v1) { sts_f32<64>(s_cell, fv1[0]); sts_f32<8 * D + 64>(s_cell, fv1[1]); }
             // flush four env rows = D float4, 16-byte aligned because e0 and base are multiples of 4
             __syncwarp();
             float4* dst4 = obs4 + (size_t)(base >> 2) * D;
 #pragma unroll
             for (int q = 0; q < (D + 31) / 32; ++q) {
                 const int idx = q * 32 + lane;
-                if (idx < D) __stcs(dst4 + idx, src4[idx]);
+                if (idx < D) __stcs(dst4 + idx, lds_f32x4_v(s_flush + 512 * q));
             }
             __syncwarp();   // the tile and this trip's window buffer may be overwritten now
             if (trip == 0) TSTAMP(7);
