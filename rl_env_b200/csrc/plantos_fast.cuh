@@ -304,13 +304,16 @@ k_step_fast(const Params p, const StepIO io) {
         // are padded rows x+2 .. x+2R+2; start on the even row at or just below x+2 so that every
         // chunk is 16-byte aligned.  Nibble rows x-2 .. x+2 are padded rows x+1 .. x+5.
         auto issue_win = [&](int base, int wb) {
-            const int x = (int)(__shfl_sync(FULL, posw, base + cj) & 31u);
-            const size_t ej = (size_t)e0 + base + cj;
-            const uint64_t* tsrc = p.types + ej * TS + ((x + 2) & ~1) + 2 * c8;
-            const uint32_t* vsrc = p.vis4 + ej * VE + (x + 1 + c8 - TCH) * VW;       // round 0 row; round 1 is 8 rows on
+            // (32-bit element offsets: N * TS and N * VE stay far below 2^32 for any N that fits HBM)
+            const unsigned x = __shfl_sync(FULL, posw, base + cj) & 31u;
+            const unsigned ej = (unsigned)(e0 + base + cj);
+            const uint64_t* tsrc = p.types + (ej * (unsigned)TS + ((x + 2u) & ~1u) + 2u * (unsigned)c8);
+            const unsigned v0 = ej * (unsigned)VE + (x + 1u) * VW;              // nibble row x-2
+            const uint32_t* vsrc0 = p.vis4 + (v0 + (unsigned)(c8 > TCH ? c8 - TCH : 0) * VW);   // round 0: row c8 - TCH
+            const uint32_t* vsrc1 = p.vis4 + (v0 + (unsigned)(c8 + 8 - TCH) * VW);              // round 1: row c8 + 8 - TCH
             const uint32_t boff = wb * win_bytes;
-            if (cp0_on) cp_async16(cp0_dst + boff, cp0_type ? (const void*)tsrc : (const void*)vsrc);
-            if (cp1_on) cp_async16(cp1_dst + boff, vsrc + 8 * VW);
+            if (cp0_on) cp_async16(cp0_dst + boff, cp0_type ? (const void*)tsrc : (const void*)vsrc0);
+            if (cp1_on) cp_async16(cp1_dst + boff, vsrc1);
         };
         issue_win(0, 0);
         cp_async_commit();
