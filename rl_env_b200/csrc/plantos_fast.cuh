@@ -210,8 +210,8 @@ k_step_fast(const Params p, const StepIO io) {
     int srcl[R], shf[R];
 #pragma unroll
     for (int rr = 0; rr < R; ++rr) { srcl[rr] = lt[rr]; shf[rr] = lt[8 + rr]; }
-    const bool has_row = sub < NROW, has_ray = sub < C, has_vrow = sub < 5, has_v1 = sub < 9;
-    const int vsrc0 = lt[16], vsh0 = lt[17], vsrc1 = lt[18], vsh1 = lt[19];
+    const bool has_ray = sub < C, has_v1 = sub < 9;
+    const int vsrc0 = lt[16], vrot0 = (lt[17] + 30) & 31, vsrc1 = lt[18], vrot1 = (lt[19] + 30) & 31;
     const uint32_t s_dist = smem_u32(t.dist), s_pos = smem_u32(t.pos), s_visit = smem_u32(t.visit);
     const uint32_t s_rw32 = smem_u32(t.rw32), s_rw64 = smem_u32(t.rw64);
     constexpr uint64_t LOWPAD = kObstAll & ((1ull << (2 * R)) - 1ull);
@@ -230,7 +230,8 @@ k_step_fast(const Params p, const StepIO io) {
     uint32_t s_vrow[2];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-        const int j = 2 * c + (lane >> 4), kk = TCH + (lane & 15);
+        // (lanes beyond the five nibble rows re-read row 0: a broadcast, no extra bank conflicts)
+        const int j = 2 * c + (lane >> 4), kk = TCH + ((lane & 15) < kFastVisRows ? (lane & 15) : 0);
         s_vrow[c] = s_scr + (kk < 8 ? j * 128 + 16 * kk : 512 + j * S1 + 16 * (kk - 8));
     }
     // 32-bit shared addresses of this lane's type row slot (chain 0, even start row; chain 1 is 256
@@ -351,10 +352,11 @@ k_step_fast(const Params p, const StepIO io) {
             // stage 2: shared-memory reads: this lane's type row and visit-nibble words
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                trow[c] = kObstAll;
-                if (has_row) trow[c] = lds_u64_v(s_trow + c * 256 + wboff + tb[c]);
-                vlo[c] = 0; vhi[c] = 0;
-                if (has_vrow) {
+                // (every lane loads: lanes beyond the 2R+1 type rows / the 5 nibble rows read other
+                // parts of the warp's scratch and nobody asks them for the result, which is cheaper
+                // than branching around the loads)
+                trow[c] = lds_u64_v(s_trow + c * 256 + wboff + tb[c]);
+                {
                     // the 5 nibbles y .. y+4 start in word y>>3 and may spill into the next one
                     // (when they sit entirely in word 3 the funnel's high half is unused)
                     const unsigned w0 = (unsigned)y[c] >> 3, w1 = w0 < 3u ? w0 + 1u : 3u;
@@ -404,8 +406,9 @@ k_step_fast(const Params p, const StepIO io) {
                 oh[c].x = kind == 0 ? 1.0f : 0.0f; oh[c].y = kind == 1 ? 1.0f : 0.0f;
                 oh[c].z = kind == 2 ? 1.0f : 0.0f; oh[c].w = kind == 3 ? 1.0f : 0.0f;
                 fp[c] = lds_f32(s_pos + 4 * (sub ? y[c] : x[c]));
-                fv0[c] = lds_f32(s_visit + 4 * ((s0[c] >> vsh0) & 15u));
-                fv1[c] = lds_f32(s_visit + 4 * ((s1[c] >> vsh1) & 15u));
+                // 4 * nibble in two instructions: rotate the nibble to bits 2..5, mask
+                fv0[c] = lds_f32(s_visit + (__funnelshift_r(s0[c], s0[c], vrot0) & 0x3cu));
+                fv1[c] = lds_f32(s_visit + (__funnelshift_r(s1[c], s1[c], vrot1) & 0x3cu));
             }
             // stage 6: stores into the tile (row 2c + half)
             if (has_ray) {                                    // :286-292
