@@ -304,7 +304,9 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
 
     // kernel selection
     const bool fast_ok = (p.W == 1) && (p.VW == 4) && (p.G + p.R <= 32) && (2 * p.R + 1 <= 16) && (p.C <= 16) &&
-                         (tables_bytes(p.G, p.R, p.C) >> 4) <= kFastWarps * 32;   // one 16-byte load per thread stages the tables
+                         (tables_bytes(p.G, p.R, p.C) >> 4) <= kFastWarps * 32 &&  // one 16-byte load per thread stages the tables
+                         (long long)p.N * (p.TS > p.VE ? p.TS : p.VE) < (1LL << 31) &&  // the fast kernels index the planes with
+                         (long long)p.N * p.G * p.G < (1LL << 31);                      // 32-bit element offsets
     h->use_fast = false;
     if (cfg->kernel != PLANTOS_KERNEL_GENERIC && fast_ok) {
         // L2 policy: PLANTOS_L2_KEEP=1 tags the state accesses evict_last inside a persisting-L2

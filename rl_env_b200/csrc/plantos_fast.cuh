@@ -159,7 +159,7 @@ k_step_fast(const Params p, const StepIO io) {
     const uint32_t s_tgt_v = s_scr + 2 * win_bytes + 16 * D + 48 * kFastEnvs + 4 * lane;
     auto fetch_rec = [&](int es) {                     // records + actions of the macro tile at es
         if (lane < min(kFastEnvs, wend - es)) {
-            const size_t e = (size_t)es + lane;
+            const unsigned e = (unsigned)(es + lane);   // 32-bit element offsets (N * TS, N * VE, N * G * G < 2^32: host check)
             cp_async16(s_rec, p.rec + 2 * e);
             cp_async16(s_rec + 16, p.rec + 2 * e + 1);
             cp_async8(s_act, io.actions + e);
@@ -168,7 +168,7 @@ k_step_fast(const Params p, const StepIO io) {
     };
     auto issue_target = [&](int es) {                  // the two words the transition will look at
         if (lane < min(kFastEnvs, wend - es)) {
-            const size_t e = (size_t)es + lane;
+            const unsigned e = (unsigned)(es + lane);   // 32-bit element offsets (N * TS, N * VE, N * G * G < 2^32: host check)
             const uint32_t w0 = recb[2 * lane].x;
             EnvRec q;
             q.x = (int)(w0 & 0xff); q.y = (int)((w0 >> 8) & 0xff);
@@ -256,7 +256,7 @@ k_step_fast(const Params p, const StepIO io) {
         const bool has_next = e_next < wend;
         const int ts = min(kFastEnvs, wend - e0);          // envs in this macro tile (a multiple of 4)
         const bool act = lane < ts;
-        const size_t e = (size_t)e0 + lane;
+        const unsigned e = (unsigned)(e0 + lane);
         cp_async_wait_all();                              // records, actions and target words are here
         __syncwarp();
         TSTAMP(4);
