@@ -211,7 +211,8 @@ k_step_fast(const Params p, const StepIO io) {
 #pragma unroll
     for (int rr = 0; rr < R; ++rr) { srcl[rr] = lt[rr]; shf[rr] = lt[8 + rr]; }
     const bool has_ray = sub < C, has_v1 = sub < 9;
-    const int vsrc0 = lt[16], vrot0 = (lt[17] + 30) & 31, vsrc1 = lt[18], vrot1 = (lt[19] + 30) & 31;
+    // the two 5x5 visit cells this lane converts: q = sub and q = sub + 16 -> nibble row q / 5, column q % 5
+    const int vrow0 = sub / 5, vcol0 = sub % 5, vrow1 = (sub + 16) / 5 < kFastVisRows ? (sub + 16) / 5 : 0, vcol1 = (sub + 16) % 5;
     const uint32_t s_dist = smem_u32(t.dist), s_pos = smem_u32(t.pos), s_visit = smem_u32(t.visit);
     const uint32_t s_rw32 = smem_u32(t.rw32), s_rw64 = smem_u32(t.rw64);
     constexpr uint64_t LOWPAD = kObstAll & ((1ull << (2 * R)) - 1ull);
@@ -227,12 +228,14 @@ k_step_fast(const Params p, const StepIO io) {
     const uint32_t cp1_dst = s_scr + 512 + cj * S1 + 16 * c8;
     // byte offset inside a window buffer of nibble row `sub` (chunk TCH + sub) of the two envs this
     // half-warp handles in a trip (env 2c + half)
-    uint32_t s_vrow[2];
+    // shared address of the nibble row (chunk TCH + row) each of the lane's two cells lives in, per chain
+    // (env 2c + half); cells are read straight out of the window: no row slices, no shuffles
+    uint32_t s_vc0[2], s_vc1[2];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-        // (lanes beyond the five nibble rows re-read row 0: a broadcast, no extra bank conflicts)
-        const int j = 2 * c + (lane >> 4), kk = TCH + ((lane & 15) < kFastVisRows ? (lane & 15) : 0);
-        s_vrow[c] = s_scr + (kk < 8 ? j * 128 + 16 * kk : 512 + j * S1 + 16 * (kk - 8));
+        const int j = 2 * c + (lane >> 4), k0 = TCH + vrow0, k1 = TCH + vrow1;
+        s_vc0[c] = s_scr + (k0 < 8 ? j * 128 + 16 * k0 : 512 + j * S1 + 16 * (k0 - 8));
+        s_vc1[c] = s_scr + (k1 < 8 ? j * 128 + 16 * k1 : 512 + j * S1 + 16 * (k1 - 8));
     }
     // 32-bit shared addresses of this lane's type row slot (chain 0, even start row; chain 1 is 256
     // bytes on), of its ray's five floats and of its visit cell in tile row `half` (chain 1 is two
@@ -338,9 +341,9 @@ k_step_fast(const Params p, const StepIO io) {
             const uint32_t wboff = wb * win_bytes;
 
             int x[NCH], y[NCH], tb[NCH];
-            unsigned w[NCH], vslice[NCH], acc[NCH], s0[NCH], s1[NCH];
+            unsigned w[NCH], acc[NCH], s0[NCH], s1[NCH];
             uint64_t trow[NCH];
-            unsigned vlo[NCH], vhi[NCH];
+            unsigned n0[NCH], n1[NCH];
             // stage 1: positions of the two envs this half-warp handles (env base + 2c + half)
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
@@ -356,22 +359,18 @@ k_step_fast(const Params p, const StepIO io) {
                 // parts of the warp's scratch and nobody asks them for the result, which is cheaper
                 // than branching around the loads)
                 trow[c] = lds_u64_v(s_trow + c * 256 + wboff + tb[c]);
-                {
-                    // the 5 nibbles y .. y+4 start in word y>>3 and may spill into the next one
-                    // (when they sit entirely in word 3 the funnel's high half is unused)
-                    const unsigned w0 = (unsigned)y[c] >> 3, w1 = w0 < 3u ? w0 + 1u : 3u;
-                    const uint32_t vr = s_vrow[c] + wboff;
-                    vlo[c] = lds_u32_v(vr + 4 * w0); vhi[c] = lds_u32_v(vr + 4 * w1);
-                }
+                // grid column y-2+col sits at nibble y+col of the padded row: word (y+col)>>3
+                n0[c] = (unsigned)y[c] + vcol0; n1[c] = (unsigned)y[c] + vcol1;
+                s0[c] = lds_u32_v(s_vc0[c] + wboff + ((n0[c] >> 3) << 2));
+                s1[c] = lds_u32_v(s_vc1[c] + wboff + ((n1[c] >> 3) << 2));
             }
             // stage 3: rover-centred window word (cells y-R .. y+R of this lane's row, walls
-            // outside) and visit slice (nibbles y .. y+4 of this lane's visit row)
+            // outside) 
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 const int sft = 2 * y[c];
                 const uint64_t ext = (trow[c] << (2 * R)) | LOWPAD;
                 w[c] = (unsigned)((ext >> sft) | ((kObstAll << 1) << (63 - sft)));
-                vslice[c] = __funnelshift_r(vlo[c], vhi[c], 4 * (y[c] & 7));
                 acc[c] = 0;
             }
             // stage 4: LIDAR march (plantos_env.py:260-284): sample rr looks at window row
@@ -385,11 +384,6 @@ k_step_fast(const Params p, const StepIO io) {
                     const unsigned wr = __shfl_sync(FULL, w[c], srcl[rr]);
                     acc[c] = __funnelshift_l(wr << shf[rr], acc[c], 2);
                 }
-            }
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                s0[c] = __shfl_sync(FULL, vslice[c], vsrc0);
-                s1[c] = __shfl_sync(FULL, vslice[c], vsrc1);
             }
             // stage 5: first hit per ray, then every table read of both chains
             float fd[NCH], fp[NCH], fv0[NCH], fv1[NCH];
@@ -407,8 +401,8 @@ k_step_fast(const Params p, const StepIO io) {
                 oh[c].z = kind == 2 ? 1.0f : 0.0f; oh[c].w = kind == 3 ? 1.0f : 0.0f;
                 fp[c] = lds_f32(s_pos + 4 * (sub ? y[c] : x[c]));
                 // 4 * nibble in two instructions: rotate the nibble to bits 2..5, mask
-                fv0[c] = lds_f32(s_visit + (__funnelshift_r(s0[c], s0[c], vrot0) & 0x3cu));
-                fv1[c] = lds_f32(s_visit + (__funnelshift_r(s1[c], s1[c], vrot1) & 0x3cu));
+                fv0[c] = lds_f32(s_visit + (__funnelshift_r(s0[c], s0[c], (4 * n0[c] + 30) & 31) & 0x3cu));
+                fv1[c] = lds_f32(s_visit + (__funnelshift_r(s1[c], s1[c], (4 * n1[c] + 30) & 31) & 0x3cu));
             }
             // stage 6: stores into the tile (row 2c + half)
             if (has_ray) {                                    // :286-292
