@@ -178,7 +178,7 @@ int plantos_stats(plantos_t* h, double* out_dev, int clear, void* stream);
  * reference, visit counts persist into the next episode unless the maze was completed or has been
  * played max_episodes_per_maze times, the reset observation shows fresh counts, explored_map
  * restarts every episode, and a new map is drawn at every reset.  Call before plantos_reset; it
- * restarts every env's curriculum state.  Curriculum steps run on the generic kernel;
+ * restarts every env's curriculum state.  Both step kernels implement it;
  * plantos_set_state is refused while a curriculum is active.  mode PLANTOS_CURRICULUM_OFF disables. */
 enum { PLANTOS_CURRICULUM_OFF = 0, PLANTOS_CURRICULUM_TERMINATE = 1, PLANTOS_CURRICULUM_MARK = 2 };
 int plantos_set_curriculum(plantos_t* h, int mode, double initial_threshold, double max_threshold,

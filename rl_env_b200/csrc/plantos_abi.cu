@@ -449,14 +449,13 @@ extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, fl
     h->p.step_seq = (unsigned)h->steps;
     h->steps += 1;
     const bool aligned = (((uintptr_t)obs) & 15u) == 0;
-    if (h->p.cur_mode && h->cfg.kernel == PLANTOS_KERNEL_FAST)
-        return fail(PLANTOS_EINVAL, "curriculum steps run on the generic kernel (PLANTOS_KERNEL_AUTO or _GENERIC)");
-    if (h->use_fast && aligned && !h->p.cur_mode) {
+    if (h->use_fast && aligned) {
         // launched with programmatic stream serialization so that back-to-back steps overlap the
         // next step's prologue with this step's tail (the kernel waits on griddepcontrol before it
         // touches any state); PLANTOS_PDL=0 falls back to a plain launch
         cudaLaunchConfig_t lc = {};
-        const FastLaunch& L = (h->prefer_lane && h->lane.fn && h->lane_offsets_ok) ? h->lane : h->trip;
+        // (the experimental lane kernel has no curriculum path)
+        const FastLaunch& L = (h->prefer_lane && h->lane.fn && h->lane_offsets_ok && !h->p.cur_mode) ? h->lane : h->trip;
         h->p.fast_q = L.q;
         lc.gridDim = dim3((unsigned)L.grid); lc.blockDim = dim3((unsigned)L.threads);
         lc.dynamicSmemBytes = (size_t)L.smem; lc.stream = (cudaStream_t)stream;
@@ -471,7 +470,7 @@ extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, fl
         lc.attrs = at; lc.numAttrs = (h->use_pdl && capturing == cudaStreamCaptureStatusNone) ? 1 : 0;
         CUDA_TRY(cudaLaunchKernelEx(&lc, L.fn, h->p, io));
     } else {
-        if (h->cfg.kernel == PLANTOS_KERNEL_FAST && !h->p.cur_mode)
+        if (h->cfg.kernel == PLANTOS_KERNEL_FAST)
             return fail(PLANTOS_EINVAL, "PLANTOS_KERNEL_FAST needs a 16-byte aligned obs buffer");
         k_step_generic<<<h->generic_grid, kGenericWarps * 32, h->generic_smem, (cudaStream_t)stream>>>(h->p, io);
     }
@@ -649,7 +648,7 @@ extern "C" int64_t plantos_launch_count(const plantos_t* h) { return h ? h->laun
 
 extern "C" const char* plantos_kernel_name(const plantos_t* h) {
     if (!h) return "";
-    if (!h->use_fast || h->p.cur_mode) return "generic";
+    if (!h->use_fast) return "generic";
     return "fast";
 }
 

@@ -54,9 +54,9 @@ __host__ __device__ inline int fast_win_bytes(int R, int G) {
     const int win = 512 + kFastTrip * fast_win_s1(R);
     return win < align_up(G * 8, 16) ? align_up(G * 8, 16) : win;    // phase C borrows it as a type plane
 }
-// per-warp scratch: two window buffers | 4-env obs tile | 32 records | 32 actions | 32+32 target words
+// per-warp scratch: two window buffers | 4-env obs tile | 32 records | 32 actions | 32+32+32 target words
 __host__ __device__ inline int fast_warp_scratch_bytes(int R, int G, int D) {
-    return 2 * fast_win_bytes(R, G) + 16 * D + kFastEnvs * (32 + 8 + 8 + 4);
+    return 2 * fast_win_bytes(R, G) + 16 * D + kFastEnvs * (32 + 8 + 8 + 4 + 4);
 }
 
 // ---- asynchronous global->shared copies (16-byte cp.async, L2 only) ------------------------
@@ -142,6 +142,7 @@ k_step_fast(const Params p, const StepIO io) {
     long long* const actb = reinterpret_cast<long long*>(recb + 2 * kFastEnvs);                   // [32]
     uint64_t* const tgt_t = reinterpret_cast<uint64_t*>(actb + kFastEnvs);                        // [32]
     uint32_t* const tgt_v = reinterpret_cast<uint32_t*>(tgt_t + kFastEnvs);                       // [32]
+    uint32_t* const tgt_e = tgt_v + kFastEnvs;                                                    // [32] explored-bit word (curriculum)
     auto win_buf = [&](int b) { return scratch + b * win_bytes; };
 
     // Every warp owns one contiguous range of Q envs (Q a multiple of 4, the same for all warps).
@@ -157,6 +158,7 @@ k_step_fast(const Params p, const StepIO io) {
     const uint32_t s_act = s_scr + 2 * win_bytes + 16 * D + 32 * kFastEnvs + 8 * lane;
     const uint32_t s_tgt_t = s_scr + 2 * win_bytes + 16 * D + 40 * kFastEnvs + 8 * lane;
     const uint32_t s_tgt_v = s_scr + 2 * win_bytes + 16 * D + 48 * kFastEnvs + 4 * lane;
+    const uint32_t s_tgt_e = s_scr + 2 * win_bytes + 16 * D + 52 * kFastEnvs + 4 * lane;
     auto fetch_rec = [&](int es) {                     // records + actions of the macro tile at es
         if (lane < min(kFastEnvs, wend - es)) {
             const unsigned e = (unsigned)(es + lane);   // 32-bit element offsets (N * TS, N * VE, N * G * G < 2^32: host check)
@@ -177,6 +179,7 @@ k_step_fast(const Params p, const StepIO io) {
             // (tx, ty) may be one cell outside the grid: wall rows / border nibbles are there
             cp_async8(s_tgt_t, p.types + e * TS + TP + tx);
             cp_async4(s_tgt_v, p.vis4 + e * VE + nib_word(tx, ty, VW));
+            if (p.cur_mode && inb) cp_async4(s_tgt_e, p.expl + e * G + tx);   // this episode's explored_map row (W == 1)
         }
         cp_async_commit();
     };
@@ -278,7 +281,22 @@ k_step_fast(const Params p, const StepIO io) {
             const uint32_t vword = tgt_v[lane];
             const int t_cell = inb ? cell_of(word, ty & 31) : kObstacle;
             const int sh = nib_shift(ty);
-            const StepOut o = transition_core(r, action, tx, ty, t_cell, (vword >> sh) & 15u, p.max_steps);
+            // CurriculumWrapper (plantos_set_curriculum): visit counts outlive the episode, so "new cell"
+            // for the exploration percentage comes from this episode's explored bits instead
+            int expl_fresh = -1;
+            if (p.cur_mode && inb && action < 4) {
+                const uint32_t ew = tgt_e[lane], bit = 1u << (ty & 31);
+                expl_fresh = (ew & bit) ? 0 : 1;
+                if (t_cell != kObstacle) p.expl[e * G + tx] = ew | bit;
+            }
+            StepOut o = transition_core(r, action, tx, ty, t_cell, (vword >> sh) & 15u, p.max_steps, expl_fresh);
+            if (p.cur_mode) {                                  // CurriculumWrapper.step, A2C_training.py:94-100
+                const double pct = ((double)r.explored / (double)r.total_free) * 100.0;
+                if (pct >= p.cur_thr[e]) {
+                    p.cur_cnt[e].y |= 1;
+                    if (p.cur_mode == 1) o.terminated = 1;
+                }
+            }
             if (o.moved)
                 bump_visit(p.vis4 + e * VE + nib_word(tx, ty, VW), vword, sh, p.visov + e * G * G + tx * G + ty, mem);
             if (o.watered) mem.st64(p.types + e * TS + TP + tx, word ^ (1ull << (2 * (ty & 31))));   // 3 -> 2
@@ -455,8 +473,13 @@ k_step_fast(const Params p, const StepIO io) {
                 store_obs_row(tile, io.terminal_obs + ej * D, D, lane);
                 __syncwarp();
             }
-            const EnvRec nr = reset_env_warp(p, (int)ej, episode, plane, lane);
-            build_obs_warp(p, t, plane, vis_e, nr.x, nr.y, tile, lane);
+            int keep = 0;
+            if (p.cur_mode) {                                  // CurriculumWrapper.reset
+                if (lane == 0) keep = curriculum_on_reset(p, (int)ej) ? 1 : 0;
+                keep = __shfl_sync(FULL, keep, 0);
+            }
+            const EnvRec nr = reset_env_warp(p, (int)ej, episode, plane, lane, keep != 0);
+            build_obs_warp(p, t, plane, vis_e, nr.x, nr.y, tile, lane, keep != 0);
             store_obs_row(tile, io.obs + ej * D, D, lane);
             if (lane == 0) {
                 uint4 qa, qb;

@@ -222,7 +222,7 @@ FIXTURES = [
 # CurriculumWrapper fixtures: small grids so that thresholds are reached and raised
 CURRICULUM_FIXTURES = [
     ("replay_curr_a2c_4env", 4, 3000, 21,
-     dict(grid_size=6, num_plants=2, num_obstacles=3, lidar_range=3, lidar_channels=8), 150, "a2c", 0),
+     dict(grid_size=6, num_plants=2, num_obstacles=3, lidar_range=4, lidar_channels=8), 150, "a2c", 0),   # (R, C) with a fast-kernel instantiation
     ("replay_curr_dqn_3env", 3, 3000, 22,
      dict(grid_size=6, num_plants=2, num_obstacles=3, lidar_range=4, lidar_channels=6), 200, "dqn", 4),
 ]

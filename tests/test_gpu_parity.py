@@ -49,22 +49,24 @@ def test_fast_kernel_pipeline_replays_reference(name, replicas):
     assert res["bitexact_obs"] == 1 and res["bitexact_reward"] == 1
 
 
-@pytest.mark.parametrize("name", ["replay_curr_a2c_4env", "replay_curr_dqn_3env"])
-def test_device_curriculum_replays_reference_wrapper(name):
-    """CurriculumWrapper on the device (plantos_set_curriculum, generic kernel) against trajectories
+@pytest.mark.parametrize("name,kernel,replicas", [("replay_curr_a2c_4env", "fast", 23), ("replay_curr_a2c_4env", "generic", 1),
+                                                  ("replay_curr_dqn_3env", "generic", 1)])
+def test_device_curriculum_replays_reference_wrapper(name, kernel, replicas):
+    """CurriculumWrapper on the device (plantos_set_curriculum; both step kernels) against trajectories
     recorded through the reference's own wrapper class (A2C_training.py:37-109 / trainingCode.py:24-98):
     visit counts that persist across episodes, threshold terminations, reset observations that show
     fresh counts; plus the per-env thresholds at the end."""
     import torch
     from gpu_backend import GpuBackend
     fx = load_fixture(name)
-    be = GpuBackend(fx, kernel="auto")
+    be = GpuBackend(fx, kernel=kernel, replicas=replicas)
+    assert be.env.kernel_name == kernel
     res = check_replay(fx, be)
     assert res["bitexact_obs"] == 1 and res["bitexact_reward"] == 1 and res["episodes"] >= 40
     # after the last step (and its auto-resets) the thresholds equal the wrapper's
     want = fx["cur_threshold"][-1].copy()
     done_last = fx["terminated"][-1] | fx["truncated"][-1]
-    got = be.env.curriculum_thresholds().cpu().numpy()
+    got = be.env.curriculum_thresholds().cpu().numpy()[:len(want)]
     assert np.array_equal(got[~done_last], want[~done_last])
     with pytest.raises(Exception):
         be.env.set_state(cells=torch.zeros(1))                 # refused while a curriculum is active
