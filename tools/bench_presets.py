@@ -29,7 +29,7 @@ run("ctor-default preset G21/P8/O50/R2/C10", 131072, steps, **PRESETS["default"]
 run("configs[2]: 4096 envs, training preset", 4096, steps, **PRESETS["training"])
 run("configs[2]: 4096 envs, ctor-default preset", 4096, steps, **PRESETS["default"])
 run("configs[4]: XL stress G64/P64/O600/R32/C16, max_steps 100", 32768, max(100, steps // 3), max_steps=100, **PRESETS["xl"])
-run("training preset + CurriculumWrapper 'a2c' (generic kernel)", 131072, max(100, steps // 3), curriculum="a2c", **PRESETS["training"])
+run("training preset + CurriculumWrapper 'a2c'", 131072, max(100, steps // 3), curriculum="a2c", **PRESETS["training"])
 
 # the same small-batch configurations as one CUDA-graph launch of 50 steps (make_rollout)
 def run_graph(label, n, k, reps, **kw):
