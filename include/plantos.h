@@ -186,6 +186,14 @@ int plantos_set_curriculum(plantos_t* h, int mode, double initial_threshold, dou
 /* Current exploration thresholds, f64 [N] device pointer. */
 int plantos_get_curriculum_thresholds(plantos_t* h, double* out_dev, void* stream);
 
+/* Rollout policy of the reference's MCTS planner (mcts_custom_trainer.py:168-216): with probability
+ * 0.7 move to the least visited valid neighbour (first minimum in N, E, S, W order), otherwise -- and
+ * when every move is blocked -- a uniformly random action.  `uniforms_dev` holds two floats in [0, 1)
+ * per env (u[2e] < 0.7 selects the heuristic, floor(5 * u[2e+1]) is the random action), `actions_dev`
+ * receives int64 [N] actions ready for plantos_step.  Together with a K-step rollout graph
+ * (PlantOSVecEnv.make_rollout) this gives device-side MCTS-style rollouts. */
+int plantos_rollout_policy(plantos_t* h, const float* uniforms_dev, int64_t* actions_dev, void* stream);
+
 /* Per-episode log = what SB3's Monitor wrapper records (A2C_training.py:124, trainingCode.py:109;
  * train_improved1/gym/env_0.monitor.csv: "r,l,t" rows).  Once enabled, every env that finishes an
  * episode appends one entry on the device (inside the step kernel, one atomic per warp); the host

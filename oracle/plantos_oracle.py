@@ -324,6 +324,25 @@ class PlantOSOracle:
         }
 
 
+def rollout_policy(env: "PlantOSOracle", u0: float, u1: float) -> int:
+    """The MCTS planner's rollout policy restated (mcts_custom_trainer.py:168-216) with the two random
+    draws supplied: `u0 < 0.7` selects `_exploration_heuristic` (least visited valid neighbour, first
+    minimum in N, E, S, W order, :196-216), otherwise -- and when every move is blocked -- the action is
+    `int(5 * u1)` (the reference draws np.random.randint(5))."""
+    rnd = min(4, max(0, int(np.float32(u1) * np.float32(5.0))))
+    if not (np.float32(u0) < np.float32(0.7)):
+        return rnd
+    x, y = env.rover_pos
+    best, min_visits = None, None
+    for action, (dx, dy) in enumerate([(-1, 0), (0, 1), (1, 0), (0, -1)]):
+        nx, ny = x + dx, y + dy
+        if 0 <= nx < env.grid_size and 0 <= ny < env.grid_size and (nx, ny) not in env.obstacles:
+            visits = int(env.visit_counts[nx, ny])
+            if min_visits is None or visits < min_visits:
+                min_visits, best = visits, action
+    return best if best is not None else rnd
+
+
 class CurriculumOracle:
     """`CurriculumWrapper` restated -- both variants the reference ships:
 

@@ -65,6 +65,7 @@ SIGNATURES = {
     "plantos_check": (C.c_int, [_vp, _vp]),
     "plantos_set_curriculum": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]),
     "plantos_get_curriculum_thresholds": (C.c_int, [_vp, _vp, _vp]),
+    "plantos_rollout_policy": (C.c_int, [_vp, _vp, _vp, _vp]),
     "plantos_episode_log_enable": (C.c_int, [_vp, C.c_int]),
     "plantos_episode_log_drain": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int64), _vp]),
     "plantos_launch_count": (C.c_int64, [_vp]),

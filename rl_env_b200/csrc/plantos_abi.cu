@@ -609,6 +609,16 @@ extern "C" int plantos_get_curriculum_thresholds(plantos_t* h, double* out_dev, 
     return PLANTOS_OK;
 }
 
+extern "C" int plantos_rollout_policy(plantos_t* h, const float* uniforms_dev, int64_t* actions_dev, void* stream) {
+    if (!h || !uniforms_dev || !actions_dev) return fail(PLANTOS_EINVAL, "handle/uniforms/actions is NULL");
+    if (!h->did_reset) return fail(PLANTOS_ESTATE, "plantos_rollout_policy before plantos_reset");
+    CUDA_TRY(cudaSetDevice(h->device));
+    k_policy_heuristic<<<(h->p.N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->p, uniforms_dev, (long long*)actions_dev);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return PLANTOS_OK;
+}
+
 static_assert(sizeof(plantos_episode_t) == 32, "episode log entries are two uint4");
 
 extern "C" int plantos_episode_log_enable(plantos_t* h, int capacity) {

@@ -489,6 +489,32 @@ __global__ void k_stats_out(unsigned long long* acc, double* out, int clear) {
     if (clear) acc[i] = 0ull;
 }
 
+// MCTS rollout policy (mcts_custom_trainer.py:168-216): with probability 0.7 the move to the least
+// visited valid neighbour (first minimum in N, E, S, W order; plants are walkable), else -- and when
+// every move is blocked -- a uniformly random action.  The randomness is supplied by the caller as two
+// uniforms in [0, 1) per env: u[2e] < 0.7 selects the heuristic, floor(5 * u[2e+1]) is the random action.
+__global__ void k_policy_heuristic(const Params p, const float* u, long long* actions) {
+    const int G = p.G, W = p.W;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < p.N; e += gridDim.x * blockDim.x) {
+        const uint32_t w0 = p.rec[2 * (size_t)e].x;
+        const int x = (int)(w0 & 0xff), y = (int)((w0 >> 8) & 0xff);
+        const uint64_t* types_e = p.types + (size_t)e * p.TS + (size_t)p.TP * W;
+        const uint32_t* vis_e = p.vis4 + (size_t)e * p.VE;
+        int best = -1, min_visits = 0x7fffffff;
+        for (int a = 0; a < 4; ++a) {
+            const int nx = x + ((a == 2) - (a == 0)), ny = y + ((a == 1) - (a == 3));
+            if ((unsigned)nx >= (unsigned)G || (unsigned)ny >= (unsigned)G) continue;
+            if (cell_of(types_e[nx * W + (ny >> 5)], ny & 31) == kObstacle) continue;
+            const unsigned nib = (vis_e[nib_word(nx, ny, p.VW)] >> nib_shift(ny)) & 15u;
+            const int v = nib < 15u ? (int)nib : (int)p.visov[(size_t)e * G * G + nx * G + ny];
+            if (v < min_visits) { min_visits = v; best = a; }
+        }
+        int rnd = (int)(u[2 * (size_t)e + 1] * 5.0f);
+        rnd = rnd > 4 ? 4 : (rnd < 0 ? 0 : rnd);
+        actions[e] = (u[2 * (size_t)e] < 0.7f && best >= 0) ? best : rnd;
+    }
+}
+
 // Packs what the fast kernel's prologue needs (one block, after every table upload): the
 // shared-memory image of the tables, and for each of the 32 lanes its observation-phase constants
 //   srcl[rr] = lane of the half-warp holding window row x+dx of LIDAR sample rr of ray (lane & 15)

@@ -311,6 +311,18 @@ class PlantOSVecEnv:
         sequence) and for small batches, where the per-step host launch cost dominates."""
         return GraphRollout(self, k, with_flags)
 
+    def rollout_policy(self, uniforms: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        """Actions of the reference's MCTS rollout policy (mcts_custom_trainer.py:168-216) for the
+        current state of every env: 70 % least-visited valid neighbour, else random.  `uniforms`
+        float32 [N, 2] in [0, 1) (drawn with `generator` if omitted); returns int64 [N] on the device."""
+        if uniforms is None:
+            uniforms = torch.rand((self.num_envs, 2), dtype=torch.float32, device=self.device, generator=generator)
+        uniforms = uniforms.to(device=self.device, dtype=torch.float32).contiguous()
+        actions = torch.empty(self.num_envs, dtype=torch.int64, device=self.device)
+        nat.check(self._lib.plantos_rollout_policy(self._h, uniforms.data_ptr(), actions.data_ptr(), self._stream()))
+        self._policy_uniforms = uniforms  # keep alive until the launch has consumed it
+        return actions
+
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:
             self._lib.plantos_destroy(self._h)

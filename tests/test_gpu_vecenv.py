@@ -167,3 +167,46 @@ def test_graph_rollout_equals_single_steps(n, kernel):
     sa, sb = a.get_state(), b.get_state()
     assert all(torch.equal(sa[k], sb[k]) for k in sa)
     a.close(); b.close()
+
+
+def test_rollout_policy_matches_the_mcts_heuristic():
+    """plantos_rollout_policy against the restated MCTS rollout policy (mcts_custom_trainer.py:168-216)
+    on the same states and the same injected uniforms, while both sides follow that policy for 300
+    steps (visit counts beyond the 4-bit range included: tiny grid, long episodes)."""
+    import torch
+    from oracle.plantos_oracle import rollout_policy
+    from rl_env_b200 import PlantOSVecEnv
+    from oracle.plantos_oracle import OracleVecEnv
+    fx = load_fixture("replay_tiny_4env")
+    n = fx["actions"].shape[1]
+    # the exploring policy finishes the tiny grid quickly: cycle the fixture's maps 40 times
+    k = int(fx["n_maps"].min())
+    cells, rover = np.tile(fx["maps_cells"][:, :k], (1, 40, 1, 1)), np.tile(fx["maps_rover"][:, :k], (1, 40, 1))
+    maps = [[(cells[i, e], tuple(rover[i, e])) for e in range(cells.shape[1])] for i in range(n)]
+    ora = OracleVecEnv(n, maps=maps, max_steps=int(fx["cfg_max_steps"]), **fixture_kwargs(fx))
+    env = PlantOSVecEnv(n, map_source="injected", max_steps=int(fx["cfg_max_steps"]), **fixture_kwargs(fx))
+    env.push_maps(cells, rover)
+    ora.reset(); env.reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    kinds = set()
+    for t in range(600):
+        u = torch.rand((n, 2), dtype=torch.float32, device="cuda", generator=g)
+        acts = env.rollout_policy(u)
+        uh = u.cpu().numpy()
+        want = [rollout_policy(ora.envs[i], uh[i, 0], uh[i, 1]) for i in range(n)]
+        assert acts.cpu().tolist() == want, t
+        kinds |= {("h" if uh[i, 0] < 0.7 else "r") for i in range(n)}
+        o_obs, _, _, _ = ora.step(want)
+        g_obs, _, _, _ = env.step(acts)
+        assert np.array_equal(g_obs.cpu().numpy(), o_obs)
+    assert kinds == {"h", "r"}
+    # visit counts beyond the 4-bit range (overflow plane): overwrite them on both sides
+    gsz = int(fx["cfg_grid_size"])
+    big = np.random.default_rng(3).integers(0, 60, size=(n, gsz, gsz)).astype(np.int32)
+    env.set_state(visits=torch.as_tensor(big))
+    for i in range(n):
+        ora.envs[i].visit_counts[:, :] = big[i]
+    for t in range(20):
+        u = torch.rand((n, 2), dtype=torch.float32, device="cuda", generator=g)
+        uh = u.cpu().numpy()
+        assert env.rollout_policy(u).cpu().tolist() == [rollout_policy(ora.envs[i], uh[i, 0], uh[i, 1]) for i in range(n)]
