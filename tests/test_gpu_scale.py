@@ -233,3 +233,32 @@ def test_full_size_properties_and_kernel_agreement():
     assert sf == sg and sf["episodes"] == n and sf["truncated"] == n and sf["length_sum"] == 40 * n
     fast.check(); gen.check()
     fast.close(); gen.close()
+
+
+@pytest.mark.parametrize("kernel", ["fast", "generic"])
+def test_maze_maps_injected_lockstep(kernel):
+    """Maps from the host-side maze generator (rl_env_b200.maps, the Gradio fork's 'maze' algorithm:
+    corridors and rooms, a much denser LIDAR workload than the cluster maps) pushed as recorded maps:
+    the device and the restated reference env agree step by step, auto-resets included."""
+    import random
+    import torch
+    from oracle.plantos_oracle import OracleVecEnv
+    from rl_env_b200 import PlantOSVecEnv
+    from rl_env_b200.maps import make_maps
+    n, episodes, steps = 36, 6, 260
+    random.seed(12)
+    cells, rover = make_maps("maze", n, episodes, T_KW["grid_size"], T_KW["num_plants"], T_KW["num_obstacles"])
+    maps = [[(cells[i, e], tuple(int(v) for v in rover[i, e])) for e in range(episodes)] for i in range(n)]
+    ora = OracleVecEnv(n, maps=maps, max_steps=60, **T_KW)
+    env = PlantOSVecEnv(n, map_source="injected", kernel=kernel, max_steps=60, **T_KW)
+    env.push_maps(cells, rover)
+    assert env.kernel_name == kernel
+    assert np.array_equal(env.reset().cpu().numpy(), ora.reset())
+    rng = np.random.default_rng(12)
+    for t in range(steps):
+        a = rng.integers(0, 5, size=n)
+        o_obs, o_rew, o_done, _ = ora.step(a)
+        g_obs, g_rew, g_done, _ = env.step(a)
+        assert np.array_equal(g_obs.cpu().numpy().view(np.uint32), o_obs.view(np.uint32)), t
+        assert np.array_equal(g_rew.cpu().numpy(), o_rew) and np.array_equal(g_done.cpu().numpy(), o_done), t
+    env.check()

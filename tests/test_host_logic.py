@@ -55,3 +55,30 @@ def test_philox_mirror_builds_valid_maps_like_the_reference_generator():
         ref_counts.append(len(ref.obstacles))
     assert abs(np.mean(counts) - np.mean(ref_counts)) < 1.5   # SURVEY: mean 25.5 for this preset
     assert min(counts) >= 4 and max(counts) <= 36
+
+
+def test_maze_maps_are_connected_and_well_formed():
+    """Host-side maze generator (rl_env_b200.maps, the Gradio fork's 'maze' algorithm): every free cell
+    is reachable from the rover (the DFS carves one connected system of rooms), plant count and codes
+    are right, the rover stands on an empty cell."""
+    import random
+    from collections import deque
+    from rl_env_b200.maps import make_maps
+    random.seed(4)
+    cells, rover = make_maps("maze", 3, 4, grid_size=25, num_plants=10, num_obstacles=12)
+    assert cells.shape == (3, 4, 25, 25) and rover.shape == (3, 4, 2)
+    for i in range(3):
+        for e in range(4):
+            c, (rx, ry) = cells[i, e], rover[i, e]
+            assert c[rx, ry] == 0 and int(((c == 2) | (c == 3)).sum()) == 10 and set(np.unique(c)) <= {0, 1, 2, 3}
+            free = c != 1
+            assert 100 < int(free.sum()) < 25 * 25 - 24          # carved rooms, solid outer ring
+            seen = np.zeros_like(free); seen[rx, ry] = True
+            queue = deque([(int(rx), int(ry))])
+            while queue:
+                x, y = queue.popleft()
+                for dx, dy in ((-1, 0), (0, 1), (1, 0), (0, -1)):
+                    nx, ny = x + dx, y + dy
+                    if 0 <= nx < 25 and 0 <= ny < 25 and free[nx, ny] and not seen[nx, ny]:
+                        seen[nx, ny] = True; queue.append((nx, ny))
+            assert seen.sum() == free.sum()

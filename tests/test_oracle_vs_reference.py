@@ -131,3 +131,46 @@ def test_curriculum_port_matches_the_reference_wrapper_class(variant, init, max_
             o2, _ = ora.reset(cells_of(raw), raw.rover_pos)
             assert np.array_equal(o, o2) and np.array_equal(raw.visit_counts, ora.env.visit_counts)
     assert episodes >= 40 and len(thresholds) >= 4
+
+
+@pytest.mark.parametrize("algo", ["maze", "original"])
+def test_host_map_generators_equal_the_gradio_fork(algo):
+    """rl_env_b200.maps (host-side generators for map injection) against `_generate_map` of the Gradio
+    fork's env class (gradio-app/plantos_env_new.py:353-604) with the same `random.seed`: same obstacle /
+    plant / rover cells and the same number of RNG draws."""
+    import importlib, os, sys, types
+    from oracle import ref_shim
+    from rl_env_b200.maps import maze_map, original_map
+    fork_dir = os.path.join(ref_shim.REFERENCE_DIR, "gradio-app")
+    if not os.path.isfile(os.path.join(fork_dir, "plantos_env_new.py")):
+        pytest.skip("fork not in the checkout")
+    ref_shim._install_stubs()
+    sys.modules["pygame"].Surface = type("Surface", (), {})
+    for name, attrs in (("plantos_utils", ["print_reset_info", "print_step_info", "print_episode_summary"]),
+                        ("plantos_3d_viewer_new", ["PlantOS3DViewer"])):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            for a in attrs:
+                setattr(m, a, (lambda *args, **kw: None) if a.startswith("print") else type(a, (), {}))
+            sys.modules[name] = m
+    if fork_dir not in sys.path:
+        sys.path.insert(0, fork_dir)
+    fork = importlib.import_module("plantos_env_new")
+    gen = {"maze": maze_map, "original": original_map}[algo]
+    for g, pl, ob in ((25, 10, 12), (21, 8, 50), (31, 12, 30), (13, 4, 9), (8, 3, 6)):
+        for seed in range(5):
+            env = fork.PlantOSEnvNew(grid_size=g, num_plants=pl, num_obstacles=ob, lidar_range=4, lidar_channels=8,
+                                     observation_mode="lidar", map_generation_algo=algo)
+            random.seed(seed)
+            env.obstacles, env.plants = set(), {}
+            env._generate_map()
+            after_ref = random.random()
+            random.seed(seed)
+            cells, rover = gen(g, pl, ob)
+            after_ours = random.random()
+            want = np.zeros((g, g), np.uint8)
+            for (x, y) in env.obstacles:
+                want[x, y] = 1
+            for (x, y), thirsty in env.plants.items():
+                want[x, y] = 3 if thirsty else 2
+            assert np.array_equal(cells, want) and tuple(rover) == tuple(env.rover_pos) and after_ref == after_ours
