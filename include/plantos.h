@@ -221,8 +221,13 @@ int plantos_check(plantos_t* h, void* stream);
 
 /* Number of simulator kernels launched by this handle so far. */
 int64_t plantos_launch_count(const plantos_t* h);
-/* Name of the step kernel the handle selected ("generic" / "fast"). */
+/* Kernel family the handle selected at create ("generic" / "fast"). */
 const char* plantos_kernel_name(const plantos_t* h);
+/* The kernel the latest plantos_step actually launched: "k_step_tile", "k_step_fast" (both are the
+ * "fast" family: lane-per-env tiles resp. the table-driven half-warp kernel used when a caller uploads
+ * LIDAR offsets other than the reference's), "k_step_generic" (also what a fast handle falls back to
+ * for an obs pointer that is not 16-byte aligned), "" before the first step. */
+const char* plantos_last_step_kernel(const plantos_t* h);
 /* Bytes of persistent device state per env. */
 int64_t plantos_state_bytes_per_env(const plantos_t* h);
 

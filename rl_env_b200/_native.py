@@ -70,6 +70,7 @@ SIGNATURES = {
     "plantos_episode_log_drain": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int64), _vp]),
     "plantos_launch_count": (C.c_int64, [_vp]),
     "plantos_kernel_name": (C.c_char_p, [_vp]),
+    "plantos_last_step_kernel": (C.c_char_p, [_vp]),
     "plantos_state_bytes_per_env": (C.c_int64, [_vp]),
     "plantos_last_error": (C.c_char_p, []),
     "plantos_abi_version": (C.c_int, []),

@@ -11,6 +11,7 @@
 #include "../../include/plantos.h"
 #include "plantos_fast.cuh"
 #include "plantos_lane.cuh"
+#include "plantos_tile.cuh"
 
 using namespace plantos_dev;
 
@@ -44,6 +45,10 @@ const FastVariant kFastVariants[] = {
 
 #define LANE_ROW(R_, C_) {R_, C_, 0, k_step_lane<R_, C_, false>}, {R_, C_, 1, k_step_lane<R_, C_, true>}
 const FastVariant kLaneVariants[] = { LANE_ROW(6, 16), LANE_ROW(2, 10), LANE_ROW(4, 16), LANE_ROW(4, 8) };
+
+// k_step_tile (plantos_tile.cuh): lane-per-env simulation + byte-coded observation output
+#define TILE_ROW(R_, C_) {R_, C_, 0, k_step_tile<R_, C_>}
+const FastVariant kTileVariants[] = { TILE_ROW(6, 16), TILE_ROW(2, 10), TILE_ROW(4, 16), TILE_ROW(4, 8) };
 
 // Does a LIDAR offset table equal the compile-time one the lane kernel was built with?
 template <int R, int C>
@@ -84,6 +89,9 @@ struct plantos {
     bool use_fast;               // a specialised kernel exists for this shape
     FastLaunch trip;             // k_step_fast (fn == nullptr: none)
     FastLaunch lane;             // k_step_lane
+    FastLaunch tile;             // k_step_tile
+    int impl;                    // 0: k_step_tile when possible, 1: k_step_fast, 2: k_step_lane (experiments)
+    const char* last_kernel;     // name of the kernel the latest plantos_step launched
     bool lane_offsets_ok;        // the uploaded LIDAR offsets equal the lane kernel's compile-time table
     bool prefer_lane;
     bool use_pdl;
@@ -329,6 +337,8 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
             if (v.R == p.R && v.C == p.C && v.keep == keep) { h->use_fast = true; h->trip.fn = v.fn; }
         for (const FastVariant& v : kLaneVariants)
             if (v.R == p.R && v.C == p.C && v.keep == keep) h->lane.fn = v.fn;
+        for (const FastVariant& v : kTileVariants)
+            if (v.R == p.R && v.C == p.C && h->use_fast) h->tile.fn = v.fn;
     }
     if (cfg->kernel == PLANTOS_KERNEL_FAST && !h->use_fast) {
         free_all(h);
@@ -353,8 +363,23 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
               tables_bytes(p.G, p.R, p.C) + kFastWarps * fast_warp_scratch_bytes(p.R, p.G, p.D));
         shape(h->lane, kLaneWarps, 1, tables_bytes(p.G, p.R, p.C) + kLaneWarps * lane_warp_scratch_bytes(p.R, p.D));
         if ((tables_bytes(p.G, p.R, p.C) >> 4) > kLaneWarps * 32) h->lane.fn = nullptr;
+        {
+            // k_step_tile: one block of kTileWarps warps per SM, every warp walks 32-env tiles
+            FastLaunch& L = h->tile;
+            const long long ntiles = (((long long)p.N & ~3LL) + 31) / 32;
+            long long blocks = (ntiles + kTileWarps - 1) / kTileWarps;
+            if (blocks > (long long)h->num_sms * PLANTOS_TILE_MINBLOCKS) blocks = (long long)h->num_sms * PLANTOS_TILE_MINBLOCKS;
+            if (const char* s = std::getenv("PLANTOS_FAST_GRID")) { const int v = std::atoi(s); if (v > 0 && v < blocks) blocks = v; }
+            L.grid = (int)(blocks < 1 ? 1 : blocks);
+            L.threads = kTileWarps * 32; L.smem = tile_block_smem_bytes(p.R, p.G, p.C); L.q = 32;
+            if (L.smem > (int)prop.sharedMemPerBlockOptin || (tables_bytes(p.G, p.R, p.C) >> 4) > kTileWarps * 32) L.fn = nullptr;
+        }
         h->prefer_lane = false;
-        if (const char* s = std::getenv("PLANTOS_FAST_IMPL")) h->prefer_lane = std::strcmp(s, "lane") == 0;
+        h->impl = 0;
+        if (const char* s = std::getenv("PLANTOS_FAST_IMPL")) {
+            h->prefer_lane = std::strcmp(s, "lane") == 0;
+            h->impl = std::strcmp(s, "trip") == 0 ? 1 : (h->prefer_lane ? 2 : 0);
+        }
         h->use_pdl = true;
         if (const char* s = std::getenv("PLANTOS_PDL")) h->use_pdl = std::atoi(s) != 0;
     }
@@ -370,7 +395,7 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     const long long want = ((long long)p.N + kGenericWarps - 1) / kGenericWarps;
     const long long cap = (long long)h->num_sms * occ;
     h->generic_grid = (int)(want < cap ? want : cap);
-    for (FastLaunch* L : {&h->trip, &h->lane}) {
+    for (FastLaunch* L : {&h->trip, &h->lane, &h->tile}) {
         if (!h->use_fast || !L->fn) continue;
         cudaError_t e3 = cudaFuncSetAttribute(L->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, L->smem);
         if (e3 != cudaSuccess) { free_all(h); return fail(PLANTOS_ECUDA, std::string("cudaFuncSetAttribute(fast): ") + cudaGetErrorString(e3)); }
@@ -455,7 +480,10 @@ extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, fl
         // touches any state); PLANTOS_PDL=0 falls back to a plain launch
         cudaLaunchConfig_t lc = {};
         // (the experimental lane kernel has no curriculum path)
-        const FastLaunch& L = (h->prefer_lane && h->lane.fn && h->lane_offsets_ok && !h->p.cur_mode) ? h->lane : h->trip;
+        const bool use_tile = h->impl == 0 && h->tile.fn && h->lane_offsets_ok;
+        const bool use_lane = h->prefer_lane && h->lane.fn && h->lane_offsets_ok && !h->p.cur_mode;
+        const FastLaunch& L = use_tile ? h->tile : (use_lane ? h->lane : h->trip);
+        h->last_kernel = use_tile ? "k_step_tile" : (use_lane ? "k_step_lane" : "k_step_fast");
         h->p.fast_q = L.q;
         lc.gridDim = dim3((unsigned)L.grid); lc.blockDim = dim3((unsigned)L.threads);
         lc.dynamicSmemBytes = (size_t)L.smem; lc.stream = (cudaStream_t)stream;
@@ -473,6 +501,7 @@ extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, fl
         if (h->cfg.kernel == PLANTOS_KERNEL_FAST)
             return fail(PLANTOS_EINVAL, "PLANTOS_KERNEL_FAST needs a 16-byte aligned obs buffer");
         k_step_generic<<<h->generic_grid, kGenericWarps * 32, h->generic_smem, (cudaStream_t)stream>>>(h->p, io);
+        h->last_kernel = "k_step_generic";
     }
     CUDA_TRY(cudaGetLastError());
     h->launches += 1;
@@ -660,6 +689,10 @@ extern "C" const char* plantos_kernel_name(const plantos_t* h) {
     if (!h) return "";
     if (!h->use_fast) return "generic";
     return "fast";
+}
+
+extern "C" const char* plantos_last_step_kernel(const plantos_t* h) {
+    return (h && h->last_kernel) ? h->last_kernel : "";
 }
 
 extern "C" int64_t plantos_state_bytes_per_env(const plantos_t* h) {

@@ -1,0 +1,426 @@
+// plantos_tile.cuh -- k_step_tile: the round-2 hot kernel.  ONE LANE PER ENV for the whole
+// simulation part of the step, the WHOLE WARP for the observation output.
+//
+// Same shape limits as k_step_fast (W == 1, VW == 4, G + R <= 32, R <= 7, C <= 16) plus: the LIDAR
+// sample offsets must be the reference's own (plantos_lidar_gen.cuh holds them as compile-time
+// tables, the host compares every uploaded table with them and routes to k_step_fast otherwise).
+//
+// Why a second specialised kernel: k_step_fast builds observations with one half-warp per env, which
+// costs ~75 warp instructions and ~31 load/store-pipe wavefronts per env and a three-round-trip
+// dependent fetch chain (record -> target words -> post-move windows) that every warp of the GPU walks
+// at the same time (profiles/r1_summary.md).  Here, per 32-env TILE of a warp:
+//   1. every lane loads its env's 32-byte record and action (coalesced);
+//   2. ONE window per env is copied cooperatively (cp.async, 8 lanes per env, 16-byte chunks): the type
+//      rows x-R-1 .. x+R+1 and the visit-nibble rows x-3 .. x+3 around the PRE-move position, i.e.
+//      everything the transition AND the observation can touch -- the target-word round trip is gone;
+//   3. lane-per-env: transition (plantos_env.py:160-222) out of the shared-memory window (patched in
+//      place, stored to HBM), then the rover-centred window words of the POST-move position go into
+//      registers, the LIDAR (plantos_env.py:251-292) is marched with compile-time offsets (two ALU
+//      instructions per sample, no shuffles), and the env's observation is emitted as a BYTE CODE:
+//      one byte per float = 4 * index into a 64-entry float table (0.0, 1.0, r/R, min(v,10)/10, x/G,
+//      all host-evaluated like every table of this library);
+//   4. the 32 byte rows form one flat image of the tile's [32, D] slice (32*D bytes, in the window
+//      buffer, which is dead by then); the whole warp expands it: per lane and iteration one code word,
+//      four byte-permutes that splice a code byte into the table's 256-byte aligned address, four table
+//      reads, one 128-bit streaming store -- fully coalesced, no float staging tile.
+// 28 warps per SM (4 blocks x 7 warps, 72 registers): at the benchmark size every warp owns exactly one
+// tile.  Auto-reset and the ragged tail reuse the generic warp routines, as in k_step_fast.
+#pragma once
+#include "plantos_fast.cuh"
+#include "plantos_lidar_gen.cuh"
+
+namespace plantos_dev {
+
+#ifndef PLANTOS_TILE_WARPS
+#define PLANTOS_TILE_WARPS 7
+#endif
+#ifndef PLANTOS_TILE_MINBLOCKS
+#define PLANTOS_TILE_MINBLOCKS 4
+#endif
+constexpr int kTileWarps = PLANTOS_TILE_WARPS;
+constexpr int kTileLutBytes = 512;    // 64 floats, placed on a 256-byte boundary inside this area
+
+// window of one env: R+2 chunks (16 B = two 8-byte type rows) + 7 chunks (visit-nibble rows); the env
+// stride is an odd number of chunks so that the lane-per-env reads spread over the banks
+__host__ __device__ constexpr int tile_type_chunks(int R) { return R + 2; }
+__host__ __device__ constexpr int tile_win_chunks(int R) { return R + 2 + 7; }
+__host__ __device__ constexpr int tile_win_stride(int R) { return (tile_win_chunks(R) | 1) * 16; }
+// per-warp scratch: 32 windows; reused as the flat byte code of the tile and as phase C's plane + row
+__host__ __device__ inline int tile_warp_scratch_bytes(int R, int G, int D) {
+    int b = 32 * tile_win_stride(R);
+    const int code = align_up(32 * D, 16), resetscratch = align_up(G * 8, 16) + align_up(D * 4, 16);
+    if (code > b) b = code;
+    if (resetscratch > b) b = resetscratch;
+    return b;
+}
+__host__ __device__ inline int tile_block_smem_bytes(int R, int G, int C) {
+    return kTileLutBytes + tables_bytes(G, R, C) + kTileWarps * tile_warp_scratch_bytes(R, G, 5 * C + 27);
+}
+
+__device__ __forceinline__ void sts_u32_v(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u64_v(uint32_t a, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" :: "r"(a), "l"(v) : "memory"); }
+
+// ---- byte-code emitters: OR five / one code bytes into the env's logical code words at a compile-time
+// byte offset (the words are registers: every index is a constant after unrolling)
+// ray group: B0 = db (a value < 256), B1..B4 = the bytes of kw
+template <int OFF, int NWORDS>
+__device__ __forceinline__ void emit_ray(uint32_t (&c)[NWORDS], uint32_t db, uint32_t kw) {
+    constexpr int i = OFF >> 2, sh = OFF & 3;
+    if (sh == 0) { c[i] |= __byte_perm(db, kw, 0x6540); c[i + 1] |= kw >> 24; }
+    if (sh == 1) { c[i] |= __byte_perm(db, kw, 0x5401); c[i + 1] |= __byte_perm(db, kw, 0x1176); }
+    if (sh == 2) { c[i] |= __byte_perm(db, kw, 0x4011); c[i + 1] |= __byte_perm(db, kw, 0x1765); }
+    if (sh == 3) { c[i] |= db << 24; c[i + 1] |= kw; }
+}
+// visit group: B0..B3 = the bytes of lo4, B4 = hi1 (a value < 256)
+template <int OFF, int NWORDS>
+__device__ __forceinline__ void emit_vis(uint32_t (&c)[NWORDS], uint32_t lo4, uint32_t hi1) {
+    constexpr int i = OFF >> 2, sh = OFF & 3;
+    if (sh == 0) { c[i] |= lo4; c[i + 1] |= hi1; }
+    if (sh == 1) { c[i] |= lo4 << 8; c[i + 1] |= __byte_perm(lo4, hi1, 0x5543); }
+    if (sh == 2) { c[i] |= lo4 << 16; c[i + 1] |= __byte_perm(lo4, hi1, 0x5432); }
+    if (sh == 3) { c[i] |= lo4 << 24; c[i + 1] |= __byte_perm(lo4, hi1, 0x4321); }
+}
+template <int OFF, int NWORDS>
+__device__ __forceinline__ void emit_byte(uint32_t (&c)[NWORDS], uint32_t b) { c[OFF >> 2] |= b << (8 * (OFF & 3)); }
+
+// Words FROM .. TO-1 of the env's code are complete: rotate them into the flat image (the env starts at
+// byte D*lane, i.e. s8 bits into word 0 of the lane's span) and store them.  Word 0 waits for the tail
+// of the previous env (see the end of the encode).
+template <int FROM, int TO, int NWORDS>
+__device__ __forceinline__ void flush_code(const uint32_t (&c)[NWORDS], uint32_t s_mycode, int s8, bool on) {
+#pragma unroll
+    for (int m = (FROM < 1 ? 1 : FROM); m < TO; ++m)
+        if (on) sts_u32_v(s_mycode + 4 * m, __funnelshift_l(c[m - 1], c[m], s8));
+}
+
+template <int R, int C>
+__global__ void __launch_bounds__(kTileWarps * 32, PLANTOS_TILE_MINBLOCKS)
+k_step_tile(const Params p, const StepIO io) {
+    using Gen = LidarGen<R, C>;
+    static_assert(Gen::ok, "no generated LIDAR offsets for this (R, C)");
+    constexpr int D = 5 * C + 27;
+    constexpr int NROW = 2 * R + 1;
+    constexpr int VW = 4;                 // nibble words per visit row (G + 4 <= 32)
+    constexpr int TP = R + 2;             // wall rows above the grid (== Params.TP)
+    constexpr int TCH = tile_type_chunks(R), NCHUNK = tile_win_chunks(R), WS = tile_win_stride(R);
+    constexpr int NW = (D + 3) / 4;       // logical code words per env
+    constexpr int TB = D & 3;             // bytes in the last logical word (0 = all four)
+    constexpr int LB_DIST = 2, LB_VIS = R + 4, LB_POS = R + 20;   // table sections: 0.0 | 1.0 | r/R (R+2) | nibble (16) | x/G (G)
+    constexpr int NVEC = 8 * D;           // float4 per full tile
+    constexpr int NIT = (NVEC + 31) / 32; // expansion iterations per full tile
+    constexpr unsigned FULL = 0xffffffffu;
+    static_assert(NROW <= 16 && C <= 16 && NCHUNK <= 16, "tile kernel shape limits");
+    static_assert(D >= 8, "flat code packing needs two logical words");
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    const PlainMem mem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int G = p.G, VE = p.VE, TS = p.TS;
+    const int tbytes = tables_bytes(G, R, C);
+    // the decode table sits on a 256-byte boundary: a code byte then IS the low address byte
+    const uint32_t s_smem = smem_u32(smem);
+    const uint32_t s_lut = (s_smem + 255u) & ~255u;
+    unsigned char* const tab_s = smem + kTileLutBytes;
+    unsigned char* const scratch = tab_s + tbytes + warp * tile_warp_scratch_bytes(R, G, D);
+    const uint32_t s_win = smem_u32(scratch);
+    const uint32_t s_code = s_win;                            // the code image reuses the window buffer
+    uint64_t* const plane = reinterpret_cast<uint64_t*>(scratch);                                 // phase C scratch
+    float* const row_s = reinterpret_cast<float*>(scratch + align_up(G * 8, 16));
+
+    // tiles of 32 envs; tile (round r, block b, warp w) = r * nwarps + w * nblocks + b, so every
+    // round of the persistent loop spreads evenly over the SMs
+    const int nwarps = gridDim.x * kTileWarps;
+    const int nfull = p.N & ~3;                             // envs in whole 4-env groups
+    const int ntiles = (nfull + 31) >> 5;
+
+    // Programmatic dependent launch (see k_step_fast): only immutable tables are read before the wait.
+    griddep_launch_dependents();
+    const int n16 = tbytes >> 4;                            // <= blockDim.x (checked on the host)
+    uint4 tab16 = make_uint4(0, 0, 0, 0);
+    if ((int)threadIdx.x < n16) tab16 = __ldg(p.table_blob + threadIdx.x);
+    // Window copy roles: 8 lanes per env, four envs per round, eight rounds per tile; lane c8 serves
+    // chunks c8 and c8 + 8 (chunks 0 .. TCH-1: type rows, TCH .. NCHUNK-1: nibble rows).  Per-lane
+    // constants: the source base of each chunk with the chunk's offset folded in.
+    const int cj = lane >> 3, c8 = lane & 7;
+    const bool cp0_type = c8 < TCH, cp1_type = c8 + 8 < TCH, cp1_on = c8 + 8 < NCHUNK;
+    const char* const cp0_base = cp0_type ? reinterpret_cast<const char*>(p.types) + 16 * c8
+                                          : reinterpret_cast<const char*>(p.vis4) + 16 * (c8 - TCH);
+    const char* const cp1_base = cp1_type ? reinterpret_cast<const char*>(p.types) + 16 * (c8 + 8)
+                                          : reinterpret_cast<const char*>(p.vis4) + 16 * (c8 + 8 - TCH);
+    const uint32_t s_cpdst = s_win + cj * WS + 16 * c8;
+    griddep_wait();
+    if ((int)threadIdx.x < n16) reinterpret_cast<uint4*>(tab_s)[threadIdx.x] = tab16;
+    __syncthreads();
+    const Tables tb = tables_at(tab_s, G, R);
+    if (threadIdx.x < 64) {                                 // the decode table
+        const int i = threadIdx.x;
+        float v = 0.0f;
+        if (i == 1) v = 1.0f;
+        else if (i >= LB_DIST && i < LB_VIS) v = tb.dist[min(i - LB_DIST, R)];      // entry R+1 repeats r = R: "no hit"
+        else if (i >= LB_VIS && i < LB_POS) v = tb.visit[i - LB_VIS];
+        else if (i >= LB_POS && i < LB_POS + G) v = tb.pos[i - LB_POS];
+        sts_u32_v(s_lut + 4 * i, __float_as_uint(v));
+    }
+    __syncthreads();
+    const uint32_t s_rw32 = smem_u32(tb.rw32), s_rw64 = smem_u32(tb.rw64);
+    constexpr uint64_t LOWPAD = kObstAll & ((1ull << (2 * R)) - 1ull);
+    // flat code image: env j's D bytes start at byte D*j; this lane owns words a_w .. a_w + M - 1
+    const int A = D * lane, s8 = 8 * (A & 3);
+    const uint32_t s_mycode = s_code + 4 * (A >> 2);
+    const bool own_last = (((A & 3) + D) >> 2) == NW;
+    const uint32_t s_mywin = s_win + lane * WS;
+
+    for (int t = warp * gridDim.x + blockIdx.x; t < ntiles; t += nwarps) {
+        const int e0 = t * 32;
+        const int ts = min(32, nfull - e0);                  // envs in this tile (a multiple of 4)
+        const bool act = lane < ts;
+        const unsigned e = (unsigned)(e0 + lane);            // 32-bit element offsets (host check)
+
+        // ---- records + actions, one lane per env
+        uint4 ra = make_uint4(0, 0, 0, 0), rbw = ra;
+        long long action = 0;
+        if (act) {
+            ra = mem.ld128(p.rec + 2 * e);
+            rbw = mem.ld128(p.rec + 2 * e + 1);
+            action = io.actions[e];
+        }
+        EnvRec r = unpack_rec(ra, rbw);
+        const int x0 = r.x;
+        // ---- cooperative window copy: lane j knows where env j's window starts; the eight lanes that
+        // copy env 4k + cj fetch those two offsets with shuffles.  Type rows: the even padded row at or
+        // just below x0+1 (grid row g = padded row g+TP); nibble rows: padded row x0 (grid row g = g+3).
+        {
+            const unsigned off_t = e * (unsigned)TS + (((unsigned)x0 + 1u) & ~1u);     // u64 elements
+            const unsigned off_v = e * (unsigned)VE + (unsigned)x0 * VW;               // u32 elements
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const unsigned ot = __shfl_sync(FULL, off_t, 4 * k + cj), ov = __shfl_sync(FULL, off_v, 4 * k + cj);
+                if (4 * k + cj < ts) {
+                    cp_async16(s_cpdst + 4 * k * WS, cp0_base + (cp0_type ? (size_t)ot * 8 : (size_t)ov * 4));
+                    if (cp1_on) cp_async16(s_cpdst + 4 * k * WS + 128, cp1_base + (cp1_type ? (size_t)ot * 8 : (size_t)ov * 4));
+                }
+            }
+            cp_async_commit();
+        }
+        cp_async_wait_all();
+        __syncwarp();
+
+        // ---- transition (plantos_env.py:160-222), one lane per env, out of the window
+        int done = 0, term = 0, trunc = 0;
+        if (act) {
+            int tx, ty; bool inb;
+            action_target(r, action, G, tx, ty, inb);
+            // the window holds padded type rows a .. a+2R+3 (a = x0+1 rounded down to even) and padded
+            // nibble rows x0 .. x0+6
+            const uint32_t s_tw = s_mywin + 8 * (tx + TP - ((x0 + 1) & ~1));
+            const uint32_t s_vw = s_mywin + 16 * (TCH + tx + 3 - x0) + 4 * ((ty + 2) >> 3);
+            const uint64_t word = lds_u64_v(s_tw);
+            const uint32_t vword = lds_u32_v(s_vw);
+            const int t_cell = inb ? cell_of(word, ty & 31) : kObstacle;
+            const int sh = nib_shift(ty);
+            int expl_fresh = -1;
+            if (p.cur_mode && inb && action < 4) {           // CurriculumWrapper: this episode's explored_map
+                const uint32_t ew = p.expl[e * G + tx], bit = 1u << (ty & 31);
+                expl_fresh = (ew & bit) ? 0 : 1;
+                if (t_cell != kObstacle) p.expl[e * G + tx] = ew | bit;
+            }
+            StepOut o = transition_core(r, action, tx, ty, t_cell, (vword >> sh) & 15u, p.max_steps, expl_fresh);
+            if (p.cur_mode) {                                // CurriculumWrapper.step, A2C_training.py:94-100
+                const double pct = ((double)r.explored / (double)r.total_free) * 100.0;
+                if (pct >= p.cur_thr[e]) {
+                    p.cur_cnt[e].y |= 1;
+                    if (p.cur_mode == 1) o.terminated = 1;
+                }
+            }
+            if (o.moved)
+                sts_u32_v(s_vw, bump_visit(p.vis4 + e * VE + nib_word(tx, ty, VW), vword, sh, p.visov + e * G * G + tx * G + ty, mem));
+            if (o.watered) {                                 // 3 -> 2
+                const uint64_t nw = word ^ (1ull << (2 * (ty & 31)));
+                mem.st64(p.types + e * TS + TP + tx, nw);
+                sts_u64_v(s_tw, nw);
+            }
+            r.ret += lds_f64(s_rw64 + 8 * o.ridx);
+            io.reward[e] = lds_f32(s_rw32 + 4 * o.ridx);
+            term = o.terminated; trunc = o.truncated; done = term | trunc;
+            io.done[e] = (uint8_t)done;
+            if (io.terminated) io.terminated[e] = (uint8_t)term;
+            if (io.truncated) io.truncated[e] = (uint8_t)trunc;
+            pack_rec(r, ra, rbw);
+            mem.st128(p.rec + 2 * e, ra);
+            mem.st128(p.rec + 2 * e + 1, rbw);
+            if (done) {
+                p.term_rec[2 * e] = ra;
+                p.term_rec[2 * e + 1] = rbw;
+            }
+        }
+        accumulate_stats(p, act && done, r, term, trunc, lane, (int)e);
+
+        // ---- the POST-move window into registers (idle lanes read their stale slot: harmless)
+        const int x1 = r.x, y1 = r.y, dxm = x1 - x0;
+        const int episode = r.episode;
+        unsigned w[NROW], sl[5];
+        {
+            // needed padded type rows x1+2 .. x1+2R+2; the window starts at padded row x0 + (x0 & 1)
+            const uint32_t s_rows = s_mywin + 8 * (2 + dxm - (x0 & 1));
+            const int sft = 2 * y1;
+            uint64_t raw[NROW];
+#pragma unroll
+            for (int i = 0; i < NROW; ++i) raw[i] = lds_u64_v(s_rows + 8 * i);
+            // needed padded nibble rows x1+1 .. x1+5, window nibble row 0 = padded row x0; grid column
+            // y1-2+k is nibble y1+k: the five nibbles sit in words y1>>3 and (one further, if any)
+            const int w0 = y1 >> 3;
+            const uint32_t s_vrows = s_mywin + 16 * (TCH + 1 + dxm) + 4 * w0;
+            const uint32_t w1off = w0 < 3 ? 4u : 0u;
+            const int vs = 4 * (y1 & 7);
+            uint32_t va[5], vb[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) { va[i] = lds_u32_v(s_vrows + 16 * i); vb[i] = lds_u32_v(s_vrows + 16 * i + w1off); }
+#pragma unroll
+            for (int i = 0; i < NROW; ++i) {
+                const uint64_t ext = (raw[i] << (2 * R)) | LOWPAD;
+                w[i] = (unsigned)((ext >> sft) | ((kObstAll << 1) << (63 - sft)));   // cells y1-R .. y1+R, walls outside
+            }
+#pragma unroll
+            for (int i = 0; i < 5; ++i) sl[i] = __funnelshift_r(va[i], vb[i], vs);
+        }
+        __syncwarp();                                        // every lane has read its window: the buffer becomes the code image
+
+        // ---- observation as a byte code (plantos_env.py:251-315); complete words are stored as soon as
+        // they are final so that they do not occupy registers
+        uint32_t c[NW + 1];
+#pragma unroll
+        for (int i = 0; i <= NW; ++i) c[i] = 0u;
+        // LIDAR (:260-292): sample rr of a ray lands at bits 2(R-rr), 2(R-rr)+1 of acc, so the nearest
+        // non-empty sample is the HIGHEST set bit; bit 0 is the "nothing hit" sentinel
+#define PLANTOS_TILE_RAY(ray)                                                                               \
+        if (ray < C) {                                                                                      \
+            constexpr int ry = ray < C ? ray : 0;                                                           \
+            unsigned acc = 1u;                                                                              \
+            _Pragma("unroll")                                                                               \
+            for (int rr = 0; rr < R; ++rr) {                                                                \
+                const int pos = 2 * (Gen::dy(ry, rr) + R), tgt = 2 * (R - rr);                              \
+                const unsigned wr = w[Gen::dx(ry, rr) + R];                                                 \
+                const unsigned al = pos > tgt ? wr >> (pos - tgt) : (pos < tgt ? wr << (tgt - pos) : wr);   \
+                acc |= al & (3u << tgt);                                                                    \
+            }                                                                                               \
+            const int g2 = (31 - __clz(acc)) & ~1;          /* 2(R-rr) of the hit, 0: none */                \
+            const unsigned kk = g2 ? acc >> g2 : 0u;        /* nearer samples are empty: the two bits alone */ \
+            const unsigned kw = __funnelshift_l(0u, 4u, kk << 3);      /* one-hot: byte `kind` = 4 -> 1.0 */ \
+            const unsigned db = (unsigned)(4 * (LB_DIST + R + 1) - 2 * g2);   /* r/R with r = R+1-g2/2 (R+1: the repeat of R) */ \
+            emit_ray<5 * ry>(c, db, kw);                                                                    \
+            flush_code<(5 * ry) / 4, (5 * ry + 5) / 4>(c, s_mycode, s8, act);                               \
+        }
+        PLANTOS_TILE_RAY(0) PLANTOS_TILE_RAY(1) PLANTOS_TILE_RAY(2) PLANTOS_TILE_RAY(3)
+        PLANTOS_TILE_RAY(4) PLANTOS_TILE_RAY(5) PLANTOS_TILE_RAY(6) PLANTOS_TILE_RAY(7)
+        PLANTOS_TILE_RAY(8) PLANTOS_TILE_RAY(9) PLANTOS_TILE_RAY(10) PLANTOS_TILE_RAY(11)
+        PLANTOS_TILE_RAY(12) PLANTOS_TILE_RAY(13) PLANTOS_TILE_RAY(14) PLANTOS_TILE_RAY(15)
+#undef PLANTOS_TILE_RAY
+        emit_byte<5 * C>(c, (unsigned)(4 * (LB_POS + x1)));          // :294-296
+        emit_byte<5 * C + 1>(c, (unsigned)(4 * (LB_POS + y1)));
+        flush_code<(5 * C) / 4, (5 * C + 2) / 4>(c, s_mycode, s8, act);
+        // 5x5 visit window (:298-313): nibble k -> byte 4 * (LB_VIS + k)
+#define PLANTOS_TILE_VIS(i)                                                                                 \
+        {                                                                                                   \
+            unsigned v = sl[i] & 0xffffu;                                                                   \
+            v = (v | (v << 8)) & 0x00ff00ffu;                                                               \
+            v = (v | (v << 4)) & 0x0f0f0f0fu;                                                               \
+            emit_vis<5 * C + 2 + 5 * i>(c, v * 4u + 0x01010101u * (4u * LB_VIS), ((sl[i] >> 16) & 15u) * 4u + 4u * LB_VIS); \
+            flush_code<(5 * C + 2 + 5 * i) / 4, (5 * C + 2 + 5 * i + 5) / 4>(c, s_mycode, s8, act);         \
+        }
+        PLANTOS_TILE_VIS(0) PLANTOS_TILE_VIS(1) PLANTOS_TILE_VIS(2) PLANTOS_TILE_VIS(3) PLANTOS_TILE_VIS(4)
+#undef PLANTOS_TILE_VIS
+        // the words that are still open: the last one (only if this lane owns it) and word 0, which also
+        // carries the last (A & 3) bytes of the previous env
+        {
+            static_assert((5 * C + 27) / 4 == NW - (TB ? 1 : 0), "flush bookkeeping");
+            const uint32_t tail = TB ? __funnelshift_r(c[NW - 2], c[NW - 1], 8 * TB) : c[NW - 1];
+            const uint32_t tprev = __shfl_up_sync(FULL, tail, 1);
+            if (act) {
+                sts_u32_v(s_mycode, __funnelshift_l(tprev, c[0], s8));
+                if (TB && own_last) sts_u32_v(s_mycode + 4 * (NW - 1), __funnelshift_l(c[NW - 2], c[NW - 1], s8));
+            }
+        }
+        __syncwarp();
+
+        // ---- expand: the whole warp, one float4 per lane and iteration, coalesced streaming stores
+        {
+            float4* const dst = reinterpret_cast<float4*>(io.obs) + ((size_t)e0 * D >> 2) + lane;
+            const uint32_t s_cw = s_code + 4 * lane;
+            if (ts == 32) {
+                constexpr int LASTN = NVEC - 32 * (NIT - 1);        // lanes of the last iteration
+#pragma unroll
+                for (int q0 = 0; q0 < NIT; q0 += 3) {
+                    uint32_t cw[3];
+                    float4 f[3];
+#pragma unroll
+                    for (int u = 0; u < 3; ++u)
+                        if (q0 + u < NIT) cw[u] = lds_u32_v(s_cw + 128 * (q0 + u));   // (beyond the image in the last one: unused)
+#pragma unroll
+                    for (int u = 0; u < 3; ++u)
+                        if (q0 + u < NIT) {
+                            f[u].x = lds_f32(__byte_perm(cw[u], s_lut, 0x7650));
+                            f[u].y = lds_f32(__byte_perm(cw[u], s_lut, 0x7651));
+                            f[u].z = lds_f32(__byte_perm(cw[u], s_lut, 0x7652));
+                            f[u].w = lds_f32(__byte_perm(cw[u], s_lut, 0x7653));
+                        }
+#pragma unroll
+                    for (int u = 0; u < 3; ++u)
+                        if (q0 + u < NIT && (q0 + u < NIT - 1 || LASTN == 32 || lane < LASTN)) __stcs(dst + (q0 + u) * 32, f[u]);
+                }
+            } else {
+                const int nvec = (ts * D) >> 2;
+#pragma unroll 1
+                for (int q = 0; q * 32 + lane < nvec; ++q) {
+                    const uint32_t cw = lds_u32_v(s_cw + 128 * q);
+                    float4 f;
+                    f.x = lds_f32(__byte_perm(cw, s_lut, 0x7650));
+                    f.y = lds_f32(__byte_perm(cw, s_lut, 0x7651));
+                    f.z = lds_f32(__byte_perm(cw, s_lut, 0x7652));
+                    f.w = lds_f32(__byte_perm(cw, s_lut, 0x7653));
+                    __stcs(dst + q * 32, f);
+                }
+            }
+        }
+        __syncwarp();                                        // the buffer may be reused
+
+        // ---- auto-reset of finished envs (rare; warp-cooperative generic code in the same buffer)
+        unsigned dmask = __ballot_sync(FULL, act && done);
+        while (dmask) {
+            const int j = __ffs(dmask) - 1;
+            dmask &= dmask - 1;
+            const size_t ej = (size_t)e0 + j;
+            const int ep = __shfl_sync(FULL, episode, j);
+            const int px = __shfl_sync(FULL, x1, j), py = __shfl_sync(FULL, y1, j);
+            const uint64_t* types_e = p.types + ej * TS + TP;
+            const uint32_t* vis_e = p.vis4 + ej * VE;
+            if (io.terminal_obs) {
+                for (int idx = lane; idx < G; idx += 32) plane[idx] = types_e[idx];
+                __syncwarp();
+                build_obs_warp(p, tb, plane, vis_e, px, py, row_s, lane);
+                store_obs_row(row_s, io.terminal_obs + ej * D, D, lane);
+                __syncwarp();
+            }
+            int keep = 0;
+            if (p.cur_mode) {                                // CurriculumWrapper.reset
+                if (lane == 0) keep = curriculum_on_reset(p, (int)ej) ? 1 : 0;
+                keep = __shfl_sync(FULL, keep, 0);
+            }
+            const EnvRec nr = reset_env_warp(p, (int)ej, ep, plane, lane, keep != 0);
+            build_obs_warp(p, tb, plane, vis_e, nr.x, nr.y, row_s, lane, keep != 0);
+            store_obs_row(row_s, io.obs + ej * D, D, lane);
+            if (lane == 0) {
+                uint4 qa, qb;
+                pack_rec(nr, qa, qb);
+                p.rec[2 * ej] = qa;
+                p.rec[2 * ej + 1] = qb;
+            }
+            __syncwarp();
+        }
+    }
+
+    // ragged tail: envs beyond the last 4-env group, one at a time
+    if (blockIdx.x == gridDim.x - 1 && warp == kTileWarps - 1)
+        for (int e = nfull; e < p.N; ++e) step_env_warp(p, tb, io, e, plane, row_s, lane);
+}
+
+}  // namespace plantos_dev

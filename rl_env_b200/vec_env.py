@@ -238,6 +238,11 @@ class PlantOSVecEnv:
         return self._lib.plantos_kernel_name(self._h).decode()
 
     @property
+    def last_step_kernel(self) -> str:
+        """The kernel the latest step launched (k_step_tile / k_step_fast / k_step_generic)."""
+        return self._lib.plantos_last_step_kernel(self._h).decode()
+
+    @property
     def launch_count(self) -> int:
         return int(self._lib.plantos_launch_count(self._h))
 

@@ -83,13 +83,17 @@ def test_lane_kernel_replays_reference(name, replicas, monkeypatch):
     assert res["bitexact_obs"] == 1 and res["bitexact_reward"] == 1
 
 
-@pytest.mark.parametrize("grid,replicas", [(1, 60), (2, 60), (1, 24), (5, 100)])
-def test_fast_kernel_buffer_reuse(grid, replicas, monkeypatch):
+@pytest.mark.parametrize("impl", ["tile", "trip"])
+@pytest.mark.parametrize("grid,replicas", [(1, 60), (2, 60), (1, 24), (5, 100), (1, 200), (2, 131)])
+def test_fast_kernel_buffer_reuse(grid, replicas, impl, monkeypatch):
     """Few persistent blocks => every warp walks several 32-env macro tiles (480 envs over 7
     warps = tiles of 32, 32, 8; over 14 warps = 32, 4), so the record / target-word buffers and
     both window buffers are reused and the next-tile prefetch path runs; (1, 24) and (5, 100)
     are single short macro tiles of 28 and 24 envs."""
+    # k_step_tile (16-warp blocks, 32-env tiles): (1, 200) = 50 tiles over 16 warps, three to four per warp
+    # (both record buffers and the window buffer are reused), (2, 131) ends in a short tile of 24 envs
     monkeypatch.setenv("PLANTOS_FAST_GRID", str(grid))
+    monkeypatch.setenv("PLANTOS_FAST_IMPL", impl)
     res = _run("replay_T_8env", "fast", replicas=replicas, steps=1100)
     assert res["bitexact_obs"] == 1
 
