@@ -92,6 +92,7 @@ struct plantos {
     FastLaunch tile;             // k_step_tile
     int impl;                    // 0: k_step_tile when possible, 1: k_step_fast, 2: k_step_lane (experiments)
     const char* last_kernel;     // name of the kernel the latest plantos_step launched
+    bool wrc_valid;              // the window ring cache mirrors the planes (k_step_tile keeps it so)
     bool lane_offsets_ok;        // the uploaded LIDAR offsets equal the lane kernel's compile-time table
     bool prefer_lane;
     bool use_pdl;
@@ -213,7 +214,7 @@ static void free_all(plantos_t* h) {
     cudaFree(h->d_tables); cudaFree(h->d_table_blob); cudaFree(h->d_lane_tab); cudaFree(h->p.stats); cudaFree(h->p.err);
     cudaFree(h->d_map_cells); cudaFree(h->d_map_rover);
     cudaFree(h->p.ep_log); cudaFree(h->p.ep_log_count);
-    cudaFree(h->p.cur_thr); cudaFree(h->p.cur_cnt); cudaFree(h->p.expl);
+    cudaFree(h->p.cur_thr); cudaFree(h->p.cur_cnt); cudaFree(h->p.expl); cudaFree(h->p.wrc);
     cudaFree(h->s_actions); cudaFree(h->s_obs); cudaFree(h->s_reward); cudaFree(h->s_done);
     delete h;
 }
@@ -373,6 +374,11 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
             L.grid = (int)(blocks < 1 ? 1 : blocks);
             L.threads = kTileWarps * 32; L.smem = tile_block_smem_bytes(p.R, p.G, p.C); L.q = 32;
             if (L.smem > (int)prop.sharedMemPerBlockOptin || (tables_bytes(p.G, p.R, p.C) >> 4) > kTileWarps * 32) L.fn = nullptr;
+            if (L.fn) {                                     // the window ring cache, one slice per 32-env tile
+                const size_t bytes = (size_t)((p.N + 31) / 32) * wrc_tile_bytes(p.R);
+                if (cudaMalloc((void**)&p.wrc, bytes) != cudaSuccess) { p.wrc = nullptr; L.fn = nullptr; cudaGetLastError(); }
+                else cudaMemset(p.wrc, 0x55, bytes);
+            }
         }
         h->prefer_lane = false;
         h->impl = 0;
@@ -460,6 +466,7 @@ extern "C" int plantos_reset(plantos_t* h, float* obs_dev, void* stream) {
     CUDA_TRY(cudaGetLastError());
     h->launches += 1;
     h->did_reset = true;
+    h->wrc_valid = false;
     return PLANTOS_OK;
 }
 
@@ -481,6 +488,13 @@ extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, fl
         cudaLaunchConfig_t lc = {};
         // (the experimental lane kernel has no curriculum path)
         const bool use_tile = h->impl == 0 && h->tile.fn && h->lane_offsets_ok;
+        if (use_tile && !h->wrc_valid) {                    // something else changed the state: rebuild the cache
+            const size_t threads = (size_t)h->p.N * 32;
+            k_wrc_build<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->p);
+            CUDA_TRY(cudaGetLastError());
+            h->launches += 1;
+        }
+        h->wrc_valid = use_tile;
         const bool use_lane = h->prefer_lane && h->lane.fn && h->lane_offsets_ok && !h->p.cur_mode;
         const FastLaunch& L = use_tile ? h->tile : (use_lane ? h->lane : h->trip);
         h->last_kernel = use_tile ? "k_step_tile" : (use_lane ? "k_step_lane" : "k_step_fast");
@@ -502,6 +516,7 @@ extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, fl
             return fail(PLANTOS_EINVAL, "PLANTOS_KERNEL_FAST needs a 16-byte aligned obs buffer");
         k_step_generic<<<h->generic_grid, kGenericWarps * 32, h->generic_smem, (cudaStream_t)stream>>>(h->p, io);
         h->last_kernel = "k_step_generic";
+        h->wrc_valid = false;
     }
     CUDA_TRY(cudaGetLastError());
     h->launches += 1;
@@ -573,6 +588,7 @@ extern "C" int plantos_set_state(plantos_t* h, const uint8_t* cells_dev, const i
     CUDA_TRY(cudaGetLastError());
     h->launches += 1;
     h->did_reset = true;
+    h->wrc_valid = false;
     return PLANTOS_OK;
 }
 

@@ -88,7 +88,24 @@ struct Params {
     double* cur_thr;            // [N] exploration_threshold
     int2* cur_cnt;              // [N] {episodes_on_current_maze, bit0 maze_completed | bit1 persistent_visit_counts is not None}
     uint32_t* expl;             // [N][G][W] explored_map > 0, one bit per cell (restarts every episode)
+    // window ring cache of k_step_tile (see wrc_* below); nullptr when the shape has no tile kernel
+    unsigned char* wrc;
 };
+
+// ------------------------------------------------------------ window ring cache (WRC)
+// k_step_tile reads, per env, only the rows of the two planes that one step can touch: the padded type
+// rows x+1 .. x+2R+3 (grid rows x-R-1 .. x+R+1) and the padded nibble rows x .. x+6 (grid rows
+// x-3 .. x+3) around the rover row x.  The WRC keeps exactly those rows in a second, tile-major array
+// whose address does not depend on x, so that a warp fetches its 32 envs' windows with ONE bulk copy
+// issued at kernel start (no record -> window dependency, no per-env address arithmetic):
+//   tile tt = env >> 5 owns wrc_tile_bytes(R) bytes: u64 planes [2R+3][32] (type row with padded index pr
+//   sits in ring slot pr % (2R+3), column = env & 31) followed by u32 planes [7][4][32] (word w of the
+//   nibble row with padded index pn sits in plane (pn % 7) * 4 + w).  Both are rings: a move of one row
+//   replaces exactly the slot of the row that left the window.
+// The planes stay the source of truth (every patch goes to both); the WRC is rebuilt from them by
+// k_wrc_build whenever something other than k_step_tile has changed the state.
+__host__ __device__ constexpr int wrc_type_slots(int R) { return 2 * R + 3; }
+__host__ __device__ constexpr int wrc_tile_bytes(int R) { return wrc_type_slots(R) * 256 + 7 * 4 * 128; }
 
 struct StepIO {
     const long long* actions;

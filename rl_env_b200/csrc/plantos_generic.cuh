@@ -190,6 +190,24 @@ __device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int epi
     return r;
 }
 
+// (Re)build env e's window-ring-cache entry from the planes in global memory for rover row x.
+// Warp-cooperative; the caller has made the planes' latest contents visible (__syncwarp after
+// reset_env_warp's stores).  No-op without a WRC.
+__device__ __forceinline__ void wrc_build_env_warp(const Params& p, size_t e, int x, int lane) {
+    if (!p.wrc) return;
+    const int ntr = wrc_type_slots(p.R);
+    unsigned char* tile = p.wrc + (e >> 5) * (size_t)wrc_tile_bytes(p.R);
+    const int j = (int)(e & 31);
+    for (int i = lane; i < ntr; i += 32) {                // padded type rows x+1 .. x+ntr (W == 1)
+        const int pr = x + 1 + i;
+        reinterpret_cast<uint64_t*>(tile)[(pr % ntr) * 32 + j] = p.types[e * p.TS + pr];
+    }
+    if (lane < 28) {                                      // padded nibble rows x .. x+6, four words each (VW == 4)
+        const int pn = x + (lane >> 2), w = lane & 3;
+        reinterpret_cast<uint32_t*>(tile + ntr * 256)[((pn % 7) * 4 + w) * 32 + j] = p.vis4[e * p.VE + pn * 4 + w];
+    }
+}
+
 // episode statistics of finished envs -> fixed-point accumulators (one atomic per warp)
 // and, when enabled, one episode-log entry per finished env (`env` = the lane's env index;
 // slots are handed out with one atomic per warp)
@@ -383,6 +401,15 @@ k_reset_all(const Params p, float* obs) {
         }
         __syncwarp();
     }
+}
+
+// one warp per env: the whole window ring cache from the planes (after reset / set_state / a step of
+// another kernel)
+__global__ void k_wrc_build(const Params p) {
+    const int lane = threadIdx.x & 31;
+    const size_t e = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    if (e >= (size_t)p.N) return;
+    wrc_build_env_warp(p, e, (int)(p.rec[2 * e].x & 0xffu), lane);
 }
 
 // --------------------------------------------------------------- state access

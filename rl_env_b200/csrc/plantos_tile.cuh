@@ -1,7 +1,8 @@
 // plantos_tile.cuh -- k_step_tile: the round-2 hot kernel.  ONE LANE PER ENV for the whole
-// simulation part of the step, the WHOLE WARP for the observation output.
+// simulation part of the step, the WHOLE WARP for the observation output, ONE BULK COPY per tile for
+// the state.
 //
-// Same shape limits as k_step_fast (W == 1, VW == 4, G + R <= 32, R <= 7, C <= 16) plus: the LIDAR
+// Same shape limits as k_step_fast (W == 1, VW == 4, G + R <= 32, C <= 16; R <= 6) plus: the LIDAR
 // sample offsets must be the reference's own (plantos_lidar_gen.cuh holds them as compile-time
 // tables, the host compares every uploaded table with them and routes to k_step_fast otherwise).
 //
@@ -9,20 +10,22 @@
 // costs ~75 warp instructions and ~31 load/store-pipe wavefronts per env and a three-round-trip
 // dependent fetch chain (record -> target words -> post-move windows) that every warp of the GPU walks
 // at the same time (profiles/r1_summary.md).  Here, per 32-env TILE of a warp:
-//   1. every lane loads its env's 32-byte record and action (coalesced);
-//   2. ONE window per env is copied cooperatively (cp.async, 8 lanes per env, 16-byte chunks): the type
-//      rows x-R-1 .. x+R+1 and the visit-nibble rows x-3 .. x+3 around the PRE-move position, i.e.
-//      everything the transition AND the observation can touch -- the target-word round trip is gone;
-//   3. lane-per-env: transition (plantos_env.py:160-222) out of the shared-memory window (patched in
-//      place, stored to HBM), then the rover-centred window words of the POST-move position go into
-//      registers, the LIDAR (plantos_env.py:251-292) is marched with compile-time offsets (two ALU
-//      instructions per sample, no shuffles), and the env's observation is emitted as a BYTE CODE:
-//      one byte per float = 4 * index into a 64-entry float table (0.0, 1.0, r/R, min(v,10)/10, x/G,
-//      all host-evaluated like every table of this library);
-//   4. the 32 byte rows form one flat image of the tile's [32, D] slice (32*D bytes, in the window
-//      buffer, which is dead by then); the whole warp expands it: per lane and iteration one code word,
-//      four byte-permutes that splice a code byte into the table's 256-byte aligned address, four table
-//      reads, one 128-bit streaming store -- fully coalesced, no float staging tile.
+//   1. one lane issues ONE cp.async.bulk (TMA, mbarrier completion) for the tile's slice of the window
+//      ring cache (plantos_common.cuh: the type rows x-R-1 .. x+R+1 and visit-nibble rows x-3 .. x+3 of
+//      all 32 envs, 7.4 KB, at an address that does not depend on the rover positions) while every lane
+//      loads its env's 32-byte record and action: a single round trip, no per-env address arithmetic;
+//   2. lane-per-env: transition (plantos_env.py:160-222) out of the shared-memory rings (patches go to
+//      shared memory, the plane and the cache), then the rover-centred window words of the POST-move
+//      position go into registers, the LIDAR (plantos_env.py:251-292) is marched with compile-time
+//      offsets (two ALU instructions per sample, no shuffles), and the env's observation is emitted as
+//      a BYTE CODE: one byte per float = 4 * index into a 64-entry float table (0.0, 1.0, r/R,
+//      min(v,10)/10, x/G, all host-evaluated like every table of this library);
+//   3. the 32 byte rows form one flat image of the tile's [32, D] slice (32*D bytes, in the ring buffer,
+//      which is dead by then); the whole warp expands it: per lane and iteration one code word, four
+//      byte-permutes that splice a code byte into the table's 256-byte aligned address, four table
+//      reads, one 128-bit streaming store -- fully coalesced, no float staging tile;
+//   4. a rover that changed rows pulls the one type row and the one nibble row that entered its window
+//      from the planes (loads issued before the expansion, stored into the cache after it).
 // 28 warps per SM (4 blocks x 7 warps, 72 registers): at the benchmark size every warp owns exactly one
 // tile.  Auto-reset and the ragged tail reuse the generic warp routines, as in k_step_fast.
 #pragma once
@@ -40,21 +43,42 @@ namespace plantos_dev {
 constexpr int kTileWarps = PLANTOS_TILE_WARPS;
 constexpr int kTileLutBytes = 512;    // 64 floats, placed on a 256-byte boundary inside this area
 
-// window of one env: R+2 chunks (16 B = two 8-byte type rows) + 7 chunks (visit-nibble rows); the env
-// stride is an odd number of chunks so that the lane-per-env reads spread over the banks
-__host__ __device__ constexpr int tile_type_chunks(int R) { return R + 2; }
-__host__ __device__ constexpr int tile_win_chunks(int R) { return R + 2 + 7; }
-__host__ __device__ constexpr int tile_win_stride(int R) { return (tile_win_chunks(R) | 1) * 16; }
-// per-warp scratch: 32 windows; reused as the flat byte code of the tile and as phase C's plane + row
+constexpr int kTileMbarBytes = 64;    // one 8-byte mbarrier per warp
+// per-warp scratch: the tile's window-ring-cache slice; reused as the flat byte code of the tile and as
+// phase C's plane + row
 __host__ __device__ inline int tile_warp_scratch_bytes(int R, int G, int D) {
-    int b = 32 * tile_win_stride(R);
+    int b = wrc_tile_bytes(R);
     const int code = align_up(32 * D, 16), resetscratch = align_up(G * 8, 16) + align_up(D * 4, 16);
     if (code > b) b = code;
     if (resetscratch > b) b = resetscratch;
     return b;
 }
 __host__ __device__ inline int tile_block_smem_bytes(int R, int G, int C) {
-    return kTileLutBytes + tables_bytes(G, R, C) + kTileWarps * tile_warp_scratch_bytes(R, G, 5 * C + 27);
+    return kTileLutBytes + kTileMbarBytes + tables_bytes(G, R, C) + kTileWarps * tile_warp_scratch_bytes(R, G, 5 * C + 27);
+}
+
+// ---- TMA (bulk async copy) + mbarrier
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    return ok;
+}
+// orders this thread's (and, after a __syncwarp, its warp's) earlier generic-proxy accesses to shared
+// memory before later async-proxy (TMA) writes to it
+__device__ __forceinline__ void fence_proxy_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_load(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(sdst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
 }
 
 __device__ __forceinline__ void sts_u32_v(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
@@ -93,6 +117,7 @@ __device__ __forceinline__ void flush_code(const uint32_t (&c)[NWORDS], uint32_t
         if (on) sts_u32_v(s_mycode + 4 * m, __funnelshift_l(c[m - 1], c[m], s8));
 }
 
+
 template <int R, int C>
 __global__ void __launch_bounds__(kTileWarps * 32, PLANTOS_TILE_MINBLOCKS)
 k_step_tile(const Params p, const StepIO io) {
@@ -102,28 +127,33 @@ k_step_tile(const Params p, const StepIO io) {
     constexpr int NROW = 2 * R + 1;
     constexpr int VW = 4;                 // nibble words per visit row (G + 4 <= 32)
     constexpr int TP = R + 2;             // wall rows above the grid (== Params.TP)
-    constexpr int TCH = tile_type_chunks(R), NCHUNK = tile_win_chunks(R), WS = tile_win_stride(R);
+    constexpr int NTR = wrc_type_slots(R), WRCB = wrc_tile_bytes(R);
     constexpr int NW = (D + 3) / 4;       // logical code words per env
     constexpr int TB = D & 3;             // bytes in the last logical word (0 = all four)
     constexpr int LB_DIST = 2, LB_VIS = R + 4, LB_POS = R + 20;   // table sections: 0.0 | 1.0 | r/R (R+2) | nibble (16) | x/G (G)
     constexpr int NVEC = 8 * D;           // float4 per full tile
     constexpr int NIT = (NVEC + 31) / 32; // expansion iterations per full tile
     constexpr unsigned FULL = 0xffffffffu;
-    static_assert(NROW <= 16 && C <= 16 && NCHUNK <= 16, "tile kernel shape limits");
+    static_assert(NROW <= 13 && C <= 16, "tile kernel shape limits");
     static_assert(D >= 8, "flat code packing needs two logical words");
 
     extern __shared__ __align__(16) unsigned char smem[];
     const PlainMem mem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#ifdef PLANTOS_EXP_TIMING
+    unsigned ts_[10] = {};
+#endif
+    TSTAMP(0);
     const int G = p.G, VE = p.VE, TS = p.TS;
     const int tbytes = tables_bytes(G, R, C);
     // the decode table sits on a 256-byte boundary: a code byte then IS the low address byte
     const uint32_t s_smem = smem_u32(smem);
     const uint32_t s_lut = (s_smem + 255u) & ~255u;
-    unsigned char* const tab_s = smem + kTileLutBytes;
+    const uint32_t s_mbar = s_smem + kTileLutBytes + 8 * warp;
+    unsigned char* const tab_s = smem + kTileLutBytes + kTileMbarBytes;
     unsigned char* const scratch = tab_s + tbytes + warp * tile_warp_scratch_bytes(R, G, D);
     const uint32_t s_win = smem_u32(scratch);
-    const uint32_t s_code = s_win;                            // the code image reuses the window buffer
+    const uint32_t s_code = s_win;                            // the code image reuses the ring buffer
     uint64_t* const plane = reinterpret_cast<uint64_t*>(scratch);                                 // phase C scratch
     float* const row_s = reinterpret_cast<float*>(scratch + align_up(G * 8, 16));
 
@@ -138,17 +168,16 @@ k_step_tile(const Params p, const StepIO io) {
     const int n16 = tbytes >> 4;                            // <= blockDim.x (checked on the host)
     uint4 tab16 = make_uint4(0, 0, 0, 0);
     if ((int)threadIdx.x < n16) tab16 = __ldg(p.table_blob + threadIdx.x);
-    // Window copy roles: 8 lanes per env, four envs per round, eight rounds per tile; lane c8 serves
-    // chunks c8 and c8 + 8 (chunks 0 .. TCH-1: type rows, TCH .. NCHUNK-1: nibble rows).  Per-lane
-    // constants: the source base of each chunk with the chunk's offset folded in.
-    const int cj = lane >> 3, c8 = lane & 7;
-    const bool cp0_type = c8 < TCH, cp1_type = c8 + 8 < TCH, cp1_on = c8 + 8 < NCHUNK;
-    const char* const cp0_base = cp0_type ? reinterpret_cast<const char*>(p.types) + 16 * c8
-                                          : reinterpret_cast<const char*>(p.vis4) + 16 * (c8 - TCH);
-    const char* const cp1_base = cp1_type ? reinterpret_cast<const char*>(p.types) + 16 * (c8 + 8)
-                                          : reinterpret_cast<const char*>(p.vis4) + 16 * (c8 + 8 - TCH);
-    const uint32_t s_cpdst = s_win + cj * WS + 16 * c8;
+    if (lane == 0) mbar_init(s_mbar, 1);
+    __syncwarp();
+    uint32_t parity = 0;
+    int t = warp * gridDim.x + blockIdx.x;
     griddep_wait();
+    TSTAMP(1);
+    if (t < ntiles && lane == 0) {                          // the first tile's rings are on their way at once
+        mbar_arrive_expect_tx(s_mbar, WRCB);
+        bulk_load(s_win, p.wrc + (size_t)t * WRCB, WRCB, s_mbar);
+    }
     if ((int)threadIdx.x < n16) reinterpret_cast<uint4*>(tab_s)[threadIdx.x] = tab16;
     __syncthreads();
     const Tables tb = tables_at(tab_s, G, R);
@@ -168,13 +197,20 @@ k_step_tile(const Params p, const StepIO io) {
     const int A = D * lane, s8 = 8 * (A & 3);
     const uint32_t s_mycode = s_code + 4 * (A >> 2);
     const bool own_last = (((A & 3) + D) >> 2) == NW;
-    const uint32_t s_mywin = s_win + lane * WS;
+    // this lane's column of the ring planes: u64 type planes, then u32 nibble planes
+    const uint32_t s_t8 = s_win + 8 * lane, s_n4 = s_win + NTR * 256 + 4 * lane;
 
-    for (int t = warp * gridDim.x + blockIdx.x; t < ntiles; t += nwarps) {
+    for (bool first = true; t < ntiles; t += nwarps, first = false) {
         const int e0 = t * 32;
         const int ts = min(32, nfull - e0);                  // envs in this tile (a multiple of 4)
         const bool act = lane < ts;
         const unsigned e = (unsigned)(e0 + lane);            // 32-bit element offsets (host check)
+        unsigned char* const g_tile = p.wrc + (size_t)t * WRCB;   // this tile's rings in global memory
+        if (!first && lane == 0) {                           // (the whole warp is past its last use of the buffer)
+            fence_proxy_async_shared();
+            mbar_arrive_expect_tx(s_mbar, WRCB);
+            bulk_load(s_win, g_tile, WRCB, s_mbar);
+        }
 
         // ---- records + actions, one lane per env
         uint4 ra = make_uint4(0, 0, 0, 0), rbw = ra;
@@ -186,36 +222,22 @@ k_step_tile(const Params p, const StepIO io) {
         }
         EnvRec r = unpack_rec(ra, rbw);
         const int x0 = r.x;
-        // ---- cooperative window copy: lane j knows where env j's window starts; the eight lanes that
-        // copy env 4k + cj fetch those two offsets with shuffles.  Type rows: the even padded row at or
-        // just below x0+1 (grid row g = padded row g+TP); nibble rows: padded row x0 (grid row g = g+3).
-        {
-            const unsigned off_t = e * (unsigned)TS + (((unsigned)x0 + 1u) & ~1u);     // u64 elements
-            const unsigned off_v = e * (unsigned)VE + (unsigned)x0 * VW;               // u32 elements
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const unsigned ot = __shfl_sync(FULL, off_t, 4 * k + cj), ov = __shfl_sync(FULL, off_v, 4 * k + cj);
-                if (4 * k + cj < ts) {
-                    cp_async16(s_cpdst + 4 * k * WS, cp0_base + (cp0_type ? (size_t)ot * 8 : (size_t)ov * 4));
-                    if (cp1_on) cp_async16(s_cpdst + 4 * k * WS + 128, cp1_base + (cp1_type ? (size_t)ot * 8 : (size_t)ov * 4));
-                }
-            }
-            cp_async_commit();
-        }
-        cp_async_wait_all();
-        __syncwarp();
+        if (x0 >= 0) TSTAMP(2);
+        while (!mbar_try_wait(s_mbar, parity)) {}
+        parity ^= 1u;
+        TSTAMP(4);
 
-        // ---- transition (plantos_env.py:160-222), one lane per env, out of the window
+        // ---- transition (plantos_env.py:160-222), one lane per env, out of the rings
         int done = 0, term = 0, trunc = 0;
         if (act) {
             int tx, ty; bool inb;
             action_target(r, action, G, tx, ty, inb);
-            // the window holds padded type rows a .. a+2R+3 (a = x0+1 rounded down to even) and padded
-            // nibble rows x0 .. x0+6
-            const uint32_t s_tw = s_mywin + 8 * (tx + TP - ((x0 + 1) & ~1));
-            const uint32_t s_vw = s_mywin + 16 * (TCH + tx + 3 - x0) + 4 * ((ty + 2) >> 3);
-            const uint64_t word = lds_u64_v(s_tw);
-            const uint32_t vword = lds_u32_v(s_vw);
+            // grid row g is padded type row g+TP and padded nibble row g+3; the rings hold padded type
+            // rows x0+1 .. x0+NTR and padded nibble rows x0 .. x0+6
+            const uint32_t o_tw = 256u * (unsigned)((tx + TP) % NTR);
+            const uint32_t o_vw = 128u * (unsigned)(((tx + 3) % 7) * 4 + ((ty + 2) >> 3));
+            const uint64_t word = lds_u64_v(s_t8 + o_tw);
+            const uint32_t vword = lds_u32_v(s_n4 + o_vw);
             const int t_cell = inb ? cell_of(word, ty & 31) : kObstacle;
             const int sh = nib_shift(ty);
             int expl_fresh = -1;
@@ -232,12 +254,16 @@ k_step_tile(const Params p, const StepIO io) {
                     if (p.cur_mode == 1) o.terminated = 1;
                 }
             }
-            if (o.moved)
-                sts_u32_v(s_vw, bump_visit(p.vis4 + e * VE + nib_word(tx, ty, VW), vword, sh, p.visov + e * G * G + tx * G + ty, mem));
+            if (o.moved) {                                   // visit count + 1: plane, ring (shared), ring (cache)
+                const uint32_t nw = bump_visit(p.vis4 + e * VE + nib_word(tx, ty, VW), vword, sh, p.visov + e * G * G + tx * G + ty, mem);
+                sts_u32_v(s_n4 + o_vw, nw);
+                *reinterpret_cast<uint32_t*>(g_tile + NTR * 256 + 4 * lane + o_vw) = nw;
+            }
             if (o.watered) {                                 // 3 -> 2
                 const uint64_t nw = word ^ (1ull << (2 * (ty & 31)));
                 mem.st64(p.types + e * TS + TP + tx, nw);
-                sts_u64_v(s_tw, nw);
+                sts_u64_v(s_t8 + o_tw, nw);
+                *reinterpret_cast<uint64_t*>(g_tile + 8 * lane + o_tw) = nw;
             }
             r.ret += lds_f64(s_rw64 + 8 * o.ridx);
             io.reward[e] = lds_f32(s_rw32 + 4 * o.ridx);
@@ -254,27 +280,32 @@ k_step_tile(const Params p, const StepIO io) {
             }
         }
         accumulate_stats(p, act && done, r, term, trunc, lane, (int)e);
+        TSTAMP(5);
 
-        // ---- the POST-move window into registers (idle lanes read their stale slot: harmless)
+        // ---- the POST-move window into registers (idle lanes read their stale column: harmless)
         const int x1 = r.x, y1 = r.y, dxm = x1 - x0;
         const int episode = r.episode;
         unsigned w[NROW], sl[5];
         {
-            // needed padded type rows x1+2 .. x1+2R+2; the window starts at padded row x0 + (x0 & 1)
-            const uint32_t s_rows = s_mywin + 8 * (2 + dxm - (x0 & 1));
+            // needed padded type rows x1+2 .. x1+2R+2: ring slots b, b+1, ... wrapping at NTR
+            const int b = (x1 + 2) % NTR, kwrap = NTR - b;
+            const uint32_t base_n = s_t8 + 256 * b, base_w = base_n - 256 * NTR;
             const int sft = 2 * y1;
             uint64_t raw[NROW];
 #pragma unroll
-            for (int i = 0; i < NROW; ++i) raw[i] = lds_u64_v(s_rows + 8 * i);
-            // needed padded nibble rows x1+1 .. x1+5, window nibble row 0 = padded row x0; grid column
-            // y1-2+k is nibble y1+k: the five nibbles sit in words y1>>3 and (one further, if any)
-            const int w0 = y1 >> 3;
-            const uint32_t s_vrows = s_mywin + 16 * (TCH + 1 + dxm) + 4 * w0;
-            const uint32_t w1off = w0 < 3 ? 4u : 0u;
+            for (int i = 0; i < NROW; ++i) raw[i] = lds_u64_v((i >= kwrap ? base_w : base_n) + 256 * i);
+            // needed padded nibble rows x1+1 .. x1+5; grid column y1-2+k is nibble y1+k: the five nibbles
+            // sit in words y1>>3 and (one further, if any)
+            const int bv = (x1 + 1) % 7, kv = 7 - bv, w0 = y1 >> 3;
+            const uint32_t vbase_n = s_n4 + 512 * bv + 128 * w0, vbase_w = vbase_n - 512 * 7;
+            const uint32_t w1off = w0 < 3 ? 128u : 0u;
             const int vs = 4 * (y1 & 7);
             uint32_t va[5], vb[5];
 #pragma unroll
-            for (int i = 0; i < 5; ++i) { va[i] = lds_u32_v(s_vrows + 16 * i); vb[i] = lds_u32_v(s_vrows + 16 * i + w1off); }
+            for (int i = 0; i < 5; ++i) {
+                const uint32_t a = (i >= kv ? vbase_w : vbase_n) + 512 * i;
+                va[i] = lds_u32_v(a); vb[i] = lds_u32_v(a + w1off);
+            }
 #pragma unroll
             for (int i = 0; i < NROW; ++i) {
                 const uint64_t ext = (raw[i] << (2 * R)) | LOWPAD;
@@ -283,7 +314,8 @@ k_step_tile(const Params p, const StepIO io) {
 #pragma unroll
             for (int i = 0; i < 5; ++i) sl[i] = __funnelshift_r(va[i], vb[i], vs);
         }
-        __syncwarp();                                        // every lane has read its window: the buffer becomes the code image
+        __syncwarp();                                        // every lane has read its rings: the buffer becomes the code image
+        if (w[0] != 0xdeadbeefu) TSTAMP(6);
 
         // ---- observation as a byte code (plantos_env.py:251-315); complete words are stored as soon as
         // they are final so that they do not occupy registers
@@ -340,7 +372,18 @@ k_step_tile(const Params p, const StepIO io) {
                 if (TB && own_last) sts_u32_v(s_mycode + 4 * (NW - 1), __funnelshift_l(c[NW - 2], c[NW - 1], s8));
             }
         }
+        // a rover that changed rows: the type row and the nibble row that entered its window come from
+        // the planes (loads in flight during the expansion) and replace the rows that left the rings
+        const bool newrow = act && !done && dxm != 0;
+        const int pr_new = dxm > 0 ? x1 + NTR : x1 + 1, pn_new = dxm > 0 ? x1 + 6 : x1;
+        uint64_t trow_new = 0;
+        uint4 nrow_new = make_uint4(0, 0, 0, 0);
+        if (newrow) {
+            trow_new = mem.ld64(p.types + e * TS + pr_new);
+            nrow_new = mem.ld128(reinterpret_cast<const uint4*>(p.vis4 + e * VE + pn_new * VW));
+        }
         __syncwarp();
+        TSTAMP(7);
 
         // ---- expand: the whole warp, one float4 per lane and iteration, coalesced streaming stores
         {
@@ -381,7 +424,22 @@ k_step_tile(const Params p, const StepIO io) {
                 }
             }
         }
+        if (newrow) {
+            *reinterpret_cast<uint64_t*>(g_tile + 256 * (pr_new % NTR) + 8 * lane) = trow_new;
+            uint32_t* const gn = reinterpret_cast<uint32_t*>(g_tile + NTR * 256 + 512 * (pn_new % 7) + 4 * lane);
+            gn[0] = nrow_new.x; gn[32] = nrow_new.y; gn[64] = nrow_new.z; gn[96] = nrow_new.w;
+        }
         __syncwarp();                                        // the buffer may be reused
+        TSTAMP(8);
+#ifdef PLANTOS_EXP_TIMING
+        { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); ts_[9] = sm; }
+        if (lane == 0 && ts >= 8)
+            for (int k = 0; k < 5; ++k) {
+                uint4 v = p.term_rec[2 * ((size_t)e0 + k) + 1];
+                v.z = ts_[2 * k]; v.w = ts_[2 * k + 1];
+                p.term_rec[2 * ((size_t)e0 + k) + 1] = v;
+            }
+#endif
 
         // ---- auto-reset of finished envs (rare; warp-cooperative generic code in the same buffer)
         unsigned dmask = __ballot_sync(FULL, act && done);
@@ -408,6 +466,7 @@ k_step_tile(const Params p, const StepIO io) {
             const EnvRec nr = reset_env_warp(p, (int)ej, ep, plane, lane, keep != 0);
             build_obs_warp(p, tb, plane, vis_e, nr.x, nr.y, row_s, lane, keep != 0);
             store_obs_row(row_s, io.obs + ej * D, D, lane);
+            wrc_build_env_warp(p, ej, nr.x, lane);           // the new episode's rings
             if (lane == 0) {
                 uint4 qa, qb;
                 pack_rec(nr, qa, qb);
@@ -418,7 +477,7 @@ k_step_tile(const Params p, const StepIO io) {
         }
     }
 
-    // ragged tail: envs beyond the last 4-env group, one at a time
+    // ragged tail: envs beyond the last 4-env group, one at a time (they are never part of a tile)
     if (blockIdx.x == gridDim.x - 1 && warp == kTileWarps - 1)
         for (int e = nfull; e < p.N; ++e) step_env_warp(p, tb, io, e, plane, row_s, lane);
 }

@@ -13,7 +13,7 @@ lo = (r & 0xffffffff).astype(np.int64); hi = ((r >> 32) & 0xffffffff).astype(np.
 # macro tiles start at multiples of fast_q; find rows with non-zero data at k=0
 T = []
 q = 28
-for e0 in range(0, N - 8, 4):
+for e0 in range(0, N - 8, 32 if os.environ.get('PLANTOS_FAST_IMPL', 'tile') == 'tile' else 4):
     if lo[e0] != 0 and hi[e0] != 0 and lo[e0+4] != 0:
         T.append([lo[e0], hi[e0], lo[e0+1], hi[e0+1], lo[e0+2], hi[e0+2], lo[e0+3], hi[e0+3], lo[e0+4], hi[e0+4]])
 T = np.array(T, dtype=np.int64)
@@ -21,7 +21,7 @@ print("warps", len(T))
 base = T[:, 1].max()  # last griddep_wait return ~ previous kernel end
 t0 = T[:, 0].min()
 rel = T - t0
-names = ["entry", "after griddep wait", "tables staged", "rec landed", "target landed", "phase A done", "trip0 windows landed", "trip0 done", "all trips done", "-"]
+names = (["entry", "after griddep wait", "rec landed", "windows issued", "windows landed", "phase A done", "window regs built", "encode done", "expand done", "-"] if os.environ.get("PLANTOS_FAST_IMPL", "tile") == "tile" else ["entry", "after griddep wait", "tables staged", "rec landed", "target landed", "phase A done", "trip0 windows landed", "trip0 done", "all trips done", "-"])
 for k in range(9):
     c = rel[:, k]
     print(f"{names[k]:24s} min {c.min():7d} p50 {int(np.median(c)):7d} p90 {int(np.percentile(c,90)):7d} max {c.max():7d} ns")
