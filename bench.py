@@ -273,8 +273,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # observation / reward / done / terminal buffers) and steps the remainder eagerly; --no-graph steps
     # eagerly throughout.
     roll = None
+    pipelined = not args.no_pipeline
+    env.set_pipelining(pipelined)          # eager steps too (the obs ring gives every step its own buffer)
     if not args.no_graph:
-        roll = env.make_rollout(ACTION_RING, with_flags=True)
+        roll = env.make_rollout(ACTION_RING, with_flags=True, pipelined=pipelined)
         roll.actions.copy_(torch.stack(actions))
 
     def maybe_stats(i):
@@ -369,7 +371,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        "kernel": kernel_name, "maps": "philox seed 0", "state_bytes_per_env": state_bytes,
                        "l2": f"inputs larger than L2: per-GPU state {n * state_bytes / 1e6:.0f} MB + obs ring "
                              f"{ACTION_RING if roll is not None else OBS_RING}x{n * OBS_DIM * 4 / 1e6:.0f} MB vs 126 MB L2; no explicit flush",
-                       "launch": ("CUDA graph of %d single-step launches, replayed" % ACTION_RING) if roll is not None else "eager, one launch per step",
+                       "launch": (("CUDA graph of %d single-step launches, replayed" % ACTION_RING) if roll is not None else "eager, one launch per step")
+                                 + ("; consecutive steps pipelined on the device (plantos_set_pipelining: per-tile step counters instead of a "
+                                    "grid-wide dependency, every step still one launch with its own actions and outputs)" if pipelined else ""),
                        "stats_allreduce_every": args.stats_every if world > 1 else 0},
             "e2e": {"value": total_envs * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * (4 * OBS_DIM + 4 + 1),
@@ -415,6 +419,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-terminal-obs", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="step eagerly instead of replaying a CUDA graph of 16 steps")
+    ap.add_argument("--no-pipeline", action="store_true", help="full grid-wide dependency between consecutive step launches")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0"))

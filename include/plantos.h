@@ -223,6 +223,15 @@ int plantos_check(plantos_t* h, void* stream);
 int64_t plantos_launch_count(const plantos_t* h);
 /* Kernel family the handle selected at create ("generic" / "fast"). */
 const char* plantos_kernel_name(const plantos_t* h);
+/* Pipelined stepping for OPEN-LOOP sequences (rollouts with pre-generated actions, benchmarks): with
+ * enable != 0 a plantos_step that directly follows another plantos_step of this handle on the same
+ * stream, writing a DIFFERENT obs buffer, no longer waits for the previous launch as a whole; per-tile
+ * counters on the device order the two steps env by env, so the next step's loads and simulation
+ * overlap the previous step's observation stores.  Results are identical.  Contract: `actions` of such a
+ * step must not be produced by work enqueued after the previous plantos_step (anything else enqueued
+ * on the stream in between must not touch the step's inputs).  Default off; the reference has no
+ * counterpart (its DummyVecEnv steps synchronously, A2C_training.py:218). */
+int plantos_set_pipelining(plantos_t* h, int enable);
 /* The kernel the latest plantos_step actually launched: "k_step_tile", "k_step_fast" (both are the
  * "fast" family: lane-per-env tiles resp. the table-driven half-warp kernel used when a caller uploads
  * LIDAR offsets other than the reference's), "k_step_generic" (also what a fast handle falls back to

@@ -71,6 +71,7 @@ SIGNATURES = {
     "plantos_launch_count": (C.c_int64, [_vp]),
     "plantos_kernel_name": (C.c_char_p, [_vp]),
     "plantos_last_step_kernel": (C.c_char_p, [_vp]),
+    "plantos_set_pipelining": (C.c_int, [_vp, C.c_int]),
     "plantos_state_bytes_per_env": (C.c_int64, [_vp]),
     "plantos_last_error": (C.c_char_p, []),
     "plantos_abi_version": (C.c_int, []),

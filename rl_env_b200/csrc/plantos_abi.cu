@@ -93,6 +93,11 @@ struct plantos {
     int impl;                    // 0: k_step_tile when possible, 1: k_step_fast, 2: k_step_lane (experiments)
     const char* last_kernel;     // name of the kernel the latest plantos_step launched
     bool wrc_valid;              // the window ring cache mirrors the planes (k_step_tile keeps it so)
+    void* d_sync;                // tickets (8 B) + per-tile step flags of k_step_tile
+    bool pipelining;             // plantos_set_pipelining
+    bool prev_tile_step;         // the handle's latest enqueued operation was a k_step_tile launch ...
+    const float* prev_obs;       // ... that wrote this observation buffer on this stream
+    void* prev_stream;
     bool lane_offsets_ok;        // the uploaded LIDAR offsets equal the lane kernel's compile-time table
     bool prefer_lane;
     bool use_pdl;
@@ -103,6 +108,9 @@ struct plantos {
     int64_t launches;
     int64_t steps;               // plantos_step calls so far (episode log's step_seq)
 };
+
+// every enqueued kernel other than a step launch ends a pipelined sequence of steps
+static void note_launch(plantos_t* h) { h->launches += 1; h->prev_tile_step = false; }
 
 // ------------------------------------------------------------------ host tables
 extern "C" int plantos_default_config(plantos_config_t* cfg) {
@@ -214,7 +222,7 @@ static void free_all(plantos_t* h) {
     cudaFree(h->d_tables); cudaFree(h->d_table_blob); cudaFree(h->d_lane_tab); cudaFree(h->p.stats); cudaFree(h->p.err);
     cudaFree(h->d_map_cells); cudaFree(h->d_map_rover);
     cudaFree(h->p.ep_log); cudaFree(h->p.ep_log_count);
-    cudaFree(h->p.cur_thr); cudaFree(h->p.cur_cnt); cudaFree(h->p.expl); cudaFree(h->p.wrc);
+    cudaFree(h->p.cur_thr); cudaFree(h->p.cur_cnt); cudaFree(h->p.expl); cudaFree(h->p.wrc); cudaFree(h->d_sync);
     cudaFree(h->s_actions); cudaFree(h->s_obs); cudaFree(h->s_reward); cudaFree(h->s_done);
     delete h;
 }
@@ -373,11 +381,17 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
             if (const char* s = std::getenv("PLANTOS_FAST_GRID")) { const int v = std::atoi(s); if (v > 0 && v < blocks) blocks = v; }
             L.grid = (int)(blocks < 1 ? 1 : blocks);
             L.threads = kTileWarps * 32; L.smem = tile_block_smem_bytes(p.R, p.G, p.C); L.q = 32;
-            if (L.smem > (int)prop.sharedMemPerBlockOptin || (tables_bytes(p.G, p.R, p.C) >> 4) > kTileWarps * 32) L.fn = nullptr;
+            if (L.smem > (int)prop.sharedMemPerBlockOptin) L.fn = nullptr;
             if (L.fn) {                                     // the window ring cache, one slice per 32-env tile
                 const size_t bytes = (size_t)((p.N + 31) / 32) * wrc_tile_bytes(p.R);
                 if (cudaMalloc((void**)&p.wrc, bytes) != cudaSuccess) { p.wrc = nullptr; L.fn = nullptr; cudaGetLastError(); }
                 else cudaMemset(p.wrc, 0x55, bytes);
+                const size_t sb = ((size_t)L.grid + (size_t)((p.N + 31) / 32)) * 4;   // per-block launch counters | per-tile step flags
+                if (L.fn && cudaMalloc(&h->d_sync, sb) == cudaSuccess) {
+                    cudaMemset(h->d_sync, 0, sb);
+                    p.tickets = (unsigned int*)h->d_sync;
+                    p.tile_flags = (unsigned int*)h->d_sync + L.grid;
+                } else { L.fn = nullptr; cudaGetLastError(); }
             }
         }
         h->prefer_lane = false;
@@ -464,7 +478,7 @@ extern "C" int plantos_reset(plantos_t* h, float* obs_dev, void* stream) {
     CUDA_TRY(cudaSetDevice(h->device));
     k_reset_all<<<h->generic_grid, kGenericWarps * 32, h->generic_smem, (cudaStream_t)stream>>>(h->p, obs_dev);
     CUDA_TRY(cudaGetLastError());
-    h->launches += 1;
+    note_launch(h);
     h->did_reset = true;
     h->wrc_valid = false;
     return PLANTOS_OK;
@@ -495,6 +509,16 @@ extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, fl
             h->launches += 1;
         }
         h->wrc_valid = use_tile;
+        // Pipelined launch (plantos_set_pipelining): allowed when the handle's previous operation was a
+        // k_step_tile launch on this stream into a DIFFERENT observation buffer (the expansion stores of
+        // consecutive steps are not ordered) and there is no ragged tail (its envs bypass the tile flags).
+        const size_t obs_bytes = (size_t)h->p.N * h->p.D * sizeof(float);
+        const bool disjoint = h->prev_obs && ((const char*)obs + obs_bytes <= (const char*)h->prev_obs ||
+                                              (const char*)h->prev_obs + obs_bytes <= (const char*)obs);
+        h->p.pipelined = (use_tile && h->pipelining && h->use_pdl && h->prev_tile_step && disjoint &&
+                          h->prev_stream == stream && (h->p.N & 3) == 0) ? 1 : 0;
+        h->p.release = h->pipelining ? 1 : 0;
+        h->prev_tile_step = use_tile; h->prev_obs = obs; h->prev_stream = stream;
         const bool use_lane = h->prefer_lane && h->lane.fn && h->lane_offsets_ok && !h->p.cur_mode;
         const FastLaunch& L = use_tile ? h->tile : (use_lane ? h->lane : h->trip);
         h->last_kernel = use_tile ? "k_step_tile" : (use_lane ? "k_step_lane" : "k_step_fast");
@@ -509,7 +533,7 @@ extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, fl
         // launches gain 1.1 us from PDL)
         cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing((cudaStream_t)stream, &capturing);
-        lc.attrs = at; lc.numAttrs = (h->use_pdl && capturing == cudaStreamCaptureStatusNone) ? 1 : 0;
+        lc.attrs = at; lc.numAttrs = (h->use_pdl && (capturing == cudaStreamCaptureStatusNone || h->p.pipelined)) ? 1 : 0;
         CUDA_TRY(cudaLaunchKernelEx(&lc, L.fn, h->p, io));
     } else {
         if (h->cfg.kernel == PLANTOS_KERNEL_FAST)
@@ -517,6 +541,7 @@ extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, fl
         k_step_generic<<<h->generic_grid, kGenericWarps * 32, h->generic_smem, (cudaStream_t)stream>>>(h->p, io);
         h->last_kernel = "k_step_generic";
         h->wrc_valid = false;
+        h->prev_tile_step = false;
     }
     CUDA_TRY(cudaGetLastError());
     h->launches += 1;
@@ -552,7 +577,7 @@ extern "C" int plantos_get_scalars(plantos_t* h, int which, int32_t* out_dev, vo
     CUDA_TRY(cudaSetDevice(h->device));
     k_get_scalars<<<(h->p.N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->p, which, out_dev);
     CUDA_TRY(cudaGetLastError());
-    h->launches += 1;
+    note_launch(h);
     return PLANTOS_OK;
 }
 
@@ -561,7 +586,7 @@ extern "C" int plantos_get_returns(plantos_t* h, int which, double* out_dev, voi
     CUDA_TRY(cudaSetDevice(h->device));
     k_get_returns<<<(h->p.N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->p, which, out_dev);
     CUDA_TRY(cudaGetLastError());
-    h->launches += 1;
+    note_launch(h);
     return PLANTOS_OK;
 }
 
@@ -574,7 +599,7 @@ extern "C" int plantos_get_state(plantos_t* h, uint8_t* cells_dev, int32_t* visi
     if (blocks > (size_t)h->num_sms * 32) blocks = (size_t)h->num_sms * 32;
     k_get_state<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(h->p, cells_dev, visits_dev);
     CUDA_TRY(cudaGetLastError());
-    h->launches += 1;
+    note_launch(h);
     return PLANTOS_OK;
 }
 
@@ -586,7 +611,7 @@ extern "C" int plantos_set_state(plantos_t* h, const uint8_t* cells_dev, const i
     const size_t threads = (size_t)h->p.N * 32;
     k_set_state<<<(int)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->p, cells_dev, visits_dev, scalars_dev);
     CUDA_TRY(cudaGetLastError());
-    h->launches += 1;
+    note_launch(h);
     h->did_reset = true;
     h->wrc_valid = false;
     return PLANTOS_OK;
@@ -597,7 +622,7 @@ extern "C" int plantos_stats(plantos_t* h, double* out_dev, int clear, void* str
     CUDA_TRY(cudaSetDevice(h->device));
     k_stats_out<<<1, 32, 0, (cudaStream_t)stream>>>(h->p.stats, out_dev, clear);
     CUDA_TRY(cudaGetLastError());
-    h->launches += 1;
+    note_launch(h);
     return PLANTOS_OK;
 }
 
@@ -660,7 +685,7 @@ extern "C" int plantos_rollout_policy(plantos_t* h, const float* uniforms_dev, i
     CUDA_TRY(cudaSetDevice(h->device));
     k_policy_heuristic<<<(h->p.N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->p, uniforms_dev, (long long*)actions_dev);
     CUDA_TRY(cudaGetLastError());
-    h->launches += 1;
+    note_launch(h);
     return PLANTOS_OK;
 }
 
@@ -705,6 +730,13 @@ extern "C" const char* plantos_kernel_name(const plantos_t* h) {
     if (!h) return "";
     if (!h->use_fast) return "generic";
     return "fast";
+}
+
+extern "C" int plantos_set_pipelining(plantos_t* h, int enable) {
+    if (!h) return fail(PLANTOS_EINVAL, "handle is NULL");
+    h->pipelining = enable != 0;
+    h->prev_tile_step = false;
+    return PLANTOS_OK;
 }
 
 extern "C" const char* plantos_last_step_kernel(const plantos_t* h) {

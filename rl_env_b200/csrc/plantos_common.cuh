@@ -90,6 +90,14 @@ struct Params {
     uint32_t* expl;             // [N][G][W] explored_map > 0, one bit per cell (restarts every episode)
     // window ring cache of k_step_tile (see wrc_* below); nullptr when the shape has no tile kernel
     unsigned char* wrc;
+    // cross-launch ordering of k_step_tile (plantos_tile.cuh): tickets[b] counts the launches of block b
+    // (= the launch's ordinal, the same for every block), tile_flags[t] the steps tile t has completed.
+    // pipelined = 1: the launch does not wait for the previous grid (no griddepcontrol.wait); a warp
+    // starts tile t when tile_flags[t] == ordinal.
+    unsigned int* tickets;
+    unsigned int* tile_flags;
+    int pipelined;
+    int release;                // the handle may overlap launches (plantos_set_pipelining): publish tile flags with release semantics
 };
 
 // ------------------------------------------------------------ window ring cache (WRC)

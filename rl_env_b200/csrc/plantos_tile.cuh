@@ -35,26 +35,35 @@
 namespace plantos_dev {
 
 #ifndef PLANTOS_TILE_WARPS
-#define PLANTOS_TILE_WARPS 7
+#define PLANTOS_TILE_WARPS 2          // small blocks: a finished block's slot goes to the next launch at once
 #endif
 #ifndef PLANTOS_TILE_MINBLOCKS
-#define PLANTOS_TILE_MINBLOCKS 4
+#define PLANTOS_TILE_MINBLOCKS 14     // 28 warps per SM (72 registers, 15.2 KB of shared memory per block)
 #endif
 constexpr int kTileWarps = PLANTOS_TILE_WARPS;
-constexpr int kTileLutBytes = 512;    // 64 floats, placed on a 256-byte boundary inside this area
+// -DPLANTOS_TILE_SKIP=<mask> builds timing-only variants that leave work out (tools/gpu_bisect.sh; wrong
+// results): 1 no observation stores, 2 no expansion, 4 no encode, 8 no ring maintenance, 16 no phase A
+// stores.  Never defined in the shipped build.
+#ifndef PLANTOS_TILE_SKIP
+#define PLANTOS_TILE_SKIP 0
+#endif
+constexpr int kTileLutBytes = 256;    // 64 floats on a 256-byte boundary: the first bytes of the dynamic shared memory
 
 constexpr int kTileMbarBytes = 64;    // one 8-byte mbarrier per warp
 // per-warp scratch: the tile's window-ring-cache slice; reused as the flat byte code of the tile and as
 // phase C's plane + row
+// offset of the new-row staging area (32 B per lane) inside the scratch: beyond everything the expansion reads
+__host__ __device__ constexpr int tile_stage_off(int D) { return ((8 * D + 31) / 32) * 128; }
 __host__ __device__ inline int tile_warp_scratch_bytes(int R, int G, int D) {
     int b = wrc_tile_bytes(R);
+    if (tile_stage_off(D) + 1024 > b) b = tile_stage_off(D) + 1024;
     const int code = align_up(32 * D, 16), resetscratch = align_up(G * 8, 16) + align_up(D * 4, 16);
     if (code > b) b = code;
     if (resetscratch > b) b = resetscratch;
     return b;
 }
 __host__ __device__ inline int tile_block_smem_bytes(int R, int G, int C) {
-    return kTileLutBytes + kTileMbarBytes + tables_bytes(G, R, C) + kTileWarps * tile_warp_scratch_bytes(R, G, 5 * C + 27);
+    return kTileLutBytes + kTileMbarBytes + kTileWarps * tile_warp_scratch_bytes(R, G, 5 * C + 27);
 }
 
 // ---- TMA (bulk async copy) + mbarrier
@@ -79,6 +88,21 @@ __device__ __forceinline__ void fence_proxy_async_shared() { asm volatile("fence
 __device__ __forceinline__ void bulk_load(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t mbar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(sdst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* q) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(q) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* q, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(q), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds_u128_v(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
 }
 
 __device__ __forceinline__ void sts_u32_v(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
@@ -137,7 +161,7 @@ k_step_tile(const Params p, const StepIO io) {
     static_assert(NROW <= 13 && C <= 16, "tile kernel shape limits");
     static_assert(D >= 8, "flat code packing needs two logical words");
 
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(256) unsigned char smem[];
     const PlainMem mem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #ifdef PLANTOS_EXP_TIMING
@@ -145,13 +169,15 @@ k_step_tile(const Params p, const StepIO io) {
 #endif
     TSTAMP(0);
     const int G = p.G, VE = p.VE, TS = p.TS;
-    const int tbytes = tables_bytes(G, R, C);
-    // the decode table sits on a 256-byte boundary: a code byte then IS the low address byte
+    // the decode table sits on a 256-byte boundary (checked below): a code byte then IS the low address byte
     const uint32_t s_smem = smem_u32(smem);
-    const uint32_t s_lut = (s_smem + 255u) & ~255u;
+    const uint32_t s_lut = s_smem;
     const uint32_t s_mbar = s_smem + kTileLutBytes + 8 * warp;
-    unsigned char* const tab_s = smem + kTileLutBytes + kTileMbarBytes;
-    unsigned char* const scratch = tab_s + tbytes + warp * tile_warp_scratch_bytes(R, G, D);
+    unsigned char* const scratch = smem + kTileLutBytes + kTileMbarBytes + warp * tile_warp_scratch_bytes(R, G, D);
+    // the tables stay in global memory (the host-packed image, plantos_common.cuh: tables_at): the hot
+    // loop only needs the two reward tables (L1 hits), the rare generic paths read them as they are
+    // (recomputed at every use: seven pointers are not worth registers)
+    auto tabs = [&]() { return tables_at(const_cast<unsigned char*>(reinterpret_cast<const unsigned char*>(p.table_blob)), G, R); };
     const uint32_t s_win = smem_u32(scratch);
     const uint32_t s_code = s_win;                            // the code image reuses the ring buffer
     uint64_t* const plane = reinterpret_cast<uint64_t*>(scratch);                                 // phase C scratch
@@ -163,35 +189,56 @@ k_step_tile(const Params p, const StepIO io) {
     const int nfull = p.N & ~3;                             // envs in whole 4-env groups
     const int ntiles = (nfull + 31) >> 5;
 
-    // Programmatic dependent launch (see k_step_fast): only immutable tables are read before the wait.
-    griddep_launch_dependents();
-    const int n16 = tbytes >> 4;                            // <= blockDim.x (checked on the host)
-    uint4 tab16 = make_uint4(0, 0, 0, 0);
-    if ((int)threadIdx.x < n16) tab16 = __ldg(p.table_blob + threadIdx.x);
-    if (lane == 0) mbar_init(s_mbar, 1);
-    __syncwarp();
-    uint32_t parity = 0;
+    // Launch ordinal: block b counts its own launches in tickets[b], and it does so BEFORE it lets the next
+    // launch start (the next launch's block b can only exist after every block of this one has passed
+    // this point), so the value it reads numbers the launches without any contention.
     int t = warp * gridDim.x + blockIdx.x;
-    griddep_wait();
-    TSTAMP(1);
-    if (t < ntiles && lane == 0) {                          // the first tile's rings are on their way at once
-        mbar_arrive_expect_tx(s_mbar, WRCB);
-        bulk_load(s_win, p.wrc + (size_t)t * WRCB, WRCB, s_mbar);
-    }
-    if ((int)threadIdx.x < n16) reinterpret_cast<uint4*>(tab_s)[threadIdx.x] = tab16;
-    __syncthreads();
-    const Tables tb = tables_at(tab_s, G, R);
-    if (threadIdx.x < 64) {                                 // the decode table
+    unsigned ticket = 0, flag0 = 0;
+    if (threadIdx.x == 0) ticket = atomicAdd(p.tickets + blockIdx.x, 1u);
+    // (pipelined launches: a first look at the first tile's flag travels together with the ticket)
+    if (lane == 0 && t < ntiles && p.pipelined) flag0 = ld_acquire_u32(p.tile_flags + t);
+    if (lane == 0) mbar_init(s_mbar, 1);
+    if (threadIdx.x < 64) {                                 // the decode table (immutable inputs)
+        const Tables tb = tabs();
         const int i = threadIdx.x;
         float v = 0.0f;
         if (i == 1) v = 1.0f;
-        else if (i >= LB_DIST && i < LB_VIS) v = tb.dist[min(i - LB_DIST, R)];      // entry R+1 repeats r = R: "no hit"
-        else if (i >= LB_VIS && i < LB_POS) v = tb.visit[i - LB_VIS];
-        else if (i >= LB_POS && i < LB_POS + G) v = tb.pos[i - LB_POS];
+        else if (i >= LB_DIST && i < LB_VIS) v = __ldg(tb.dist + min(i - LB_DIST, R));      // entry R+1 repeats r = R: "no hit"
+        else if (i >= LB_VIS && i < LB_POS) v = __ldg(tb.visit + (i - LB_VIS));
+        else if (i >= LB_POS && i < LB_POS + G) v = __ldg(tb.pos + (i - LB_POS));
         sts_u32_v(s_lut + 4 * i, __float_as_uint(v));
     }
+    if (threadIdx.x == 0) {
+        sts_u32_v(s_smem + kTileLutBytes + 8 * kTileWarps, ticket);
+        if ((s_lut & 255u) != 0u) atomicExch(p.err, -6);    // (the launch configuration guarantees the alignment)
+    }
     __syncthreads();
-    const uint32_t s_rw32 = smem_u32(tb.rw32), s_rw64 = smem_u32(tb.rw64);
+    const unsigned ordinal = lds_u32_v(s_smem + kTileLutBytes + 8 * kTileWarps);
+    // Programmatic dependent launch (see k_step_fast): nothing mutable but the ticket is touched before the wait.
+    griddep_launch_dependents();
+    uint32_t parity = 0;
+    // Pipelined launches (plantos_set_pipelining) do NOT wait for the previous grid: the per-tile flags
+    // below order a tile's steps, so this launch's loads and simulation overlap the previous launch's
+    // observation stores.  Otherwise the usual full dependency.
+    if (!p.pipelined) griddep_wait();
+    TSTAMP(1);
+    auto wait_tile = [&](int tile, unsigned seen) {         // lane 0: until the previous step of this tile is complete
+        if (p.pipelined) {
+            const unsigned* f = p.tile_flags + tile;
+            unsigned spins = 0;
+            while (seen != ordinal) {
+                __nanosleep(64);
+                if (++spins > (1u << 24)) { atomicExch(p.err, -5); break; }   // never hang the GPU on a protocol error
+                seen = ld_acquire_u32(f);
+            }
+            fence_proxy_async_global();                     // the bulk copy below reads what other SMs stored
+        }
+    };
+    if (t < ntiles && lane == 0) {                          // the first tile's rings are on their way at once
+        wait_tile(t, flag0);
+        mbar_arrive_expect_tx(s_mbar, WRCB);
+        bulk_load(s_win, p.wrc + (size_t)t * WRCB, WRCB, s_mbar);
+    }
     constexpr uint64_t LOWPAD = kObstAll & ((1ull << (2 * R)) - 1ull);
     // flat code image: env j's D bytes start at byte D*j; this lane owns words a_w .. a_w + M - 1
     const int A = D * lane, s8 = 8 * (A & 3);
@@ -207,18 +254,20 @@ k_step_tile(const Params p, const StepIO io) {
         const unsigned e = (unsigned)(e0 + lane);            // 32-bit element offsets (host check)
         unsigned char* const g_tile = p.wrc + (size_t)t * WRCB;   // this tile's rings in global memory
         if (!first && lane == 0) {                           // (the whole warp is past its last use of the buffer)
+            wait_tile(t, p.pipelined ? ld_acquire_u32(p.tile_flags + t) : 0u);
             fence_proxy_async_shared();
             mbar_arrive_expect_tx(s_mbar, WRCB);
             bulk_load(s_win, g_tile, WRCB, s_mbar);
         }
 
-        // ---- records + actions, one lane per env
+        __syncwarp();                                        // (lane 0 has seen the tile's flag)
+        // ---- records + actions, one lane per env (L2 loads: another SM may have just written the record)
         uint4 ra = make_uint4(0, 0, 0, 0), rbw = ra;
         long long action = 0;
         if (act) {
-            ra = mem.ld128(p.rec + 2 * e);
-            rbw = mem.ld128(p.rec + 2 * e + 1);
-            action = io.actions[e];
+            ra = __ldcg(p.rec + 2 * e);
+            rbw = __ldcg(p.rec + 2 * e + 1);
+            action = __ldcg(io.actions + e);
         }
         EnvRec r = unpack_rec(ra, rbw);
         const int x0 = r.x;
@@ -265,15 +314,17 @@ k_step_tile(const Params p, const StepIO io) {
                 sts_u64_v(s_t8 + o_tw, nw);
                 *reinterpret_cast<uint64_t*>(g_tile + 8 * lane + o_tw) = nw;
             }
-            r.ret += lds_f64(s_rw64 + 8 * o.ridx);
-            io.reward[e] = lds_f32(s_rw32 + 4 * o.ridx);
+            r.ret += __ldg(tabs().rw64 + o.ridx);
             term = o.terminated; trunc = o.truncated; done = term | trunc;
+            pack_rec(r, ra, rbw);
+            if (!(PLANTOS_TILE_SKIP & 16) || r.step == 54321) {
+            io.reward[e] = __ldg(tabs().rw32 + o.ridx);
             io.done[e] = (uint8_t)done;
             if (io.terminated) io.terminated[e] = (uint8_t)term;
             if (io.truncated) io.truncated[e] = (uint8_t)trunc;
-            pack_rec(r, ra, rbw);
             mem.st128(p.rec + 2 * e, ra);
             mem.st128(p.rec + 2 * e + 1, rbw);
+            }
             if (done) {
                 p.term_rec[2 * e] = ra;
                 p.term_rec[2 * e + 1] = rbw;
@@ -316,6 +367,16 @@ k_step_tile(const Params p, const StepIO io) {
         }
         __syncwarp();                                        // every lane has read its rings: the buffer becomes the code image
         if (w[0] != 0xdeadbeefu) TSTAMP(6);
+        // a rover that changed rows: the type row and the nibble row that entered its window come from
+        // the planes, by cp.async into a staging area behind the code image while the encode runs
+        const bool newrow = act && !done && dxm != 0 && !(PLANTOS_TILE_SKIP & 8);
+        const int pr_new = dxm > 0 ? x1 + NTR : x1 + 1, pn_new = dxm > 0 ? x1 + 6 : x1;
+        const uint32_t s_stage = s_win + tile_stage_off(D) + 32 * lane;
+        if (newrow) {
+            cp_async16(s_stage, p.vis4 + e * VE + pn_new * VW);
+            cp_async8(s_stage + 16, p.types + e * TS + pr_new);
+        }
+        cp_async_commit();
 
         // ---- observation as a byte code (plantos_env.py:251-315); complete words are stored as soon as
         // they are final so that they do not occupy registers
@@ -342,10 +403,19 @@ k_step_tile(const Params p, const StepIO io) {
             emit_ray<5 * ry>(c, db, kw);                                                                    \
             flush_code<(5 * ry) / 4, (5 * ry + 5) / 4>(c, s_mycode, s8, act);                               \
         }
+        if (PLANTOS_TILE_SKIP & 4) {
+            unsigned xs = 0;
+#pragma unroll
+            for (int i = 0; i < NROW; ++i) xs ^= w[i];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) xs ^= sl[i];
+            c[0] = xs;
+        } else {
         PLANTOS_TILE_RAY(0) PLANTOS_TILE_RAY(1) PLANTOS_TILE_RAY(2) PLANTOS_TILE_RAY(3)
         PLANTOS_TILE_RAY(4) PLANTOS_TILE_RAY(5) PLANTOS_TILE_RAY(6) PLANTOS_TILE_RAY(7)
         PLANTOS_TILE_RAY(8) PLANTOS_TILE_RAY(9) PLANTOS_TILE_RAY(10) PLANTOS_TILE_RAY(11)
         PLANTOS_TILE_RAY(12) PLANTOS_TILE_RAY(13) PLANTOS_TILE_RAY(14) PLANTOS_TILE_RAY(15)
+        }
 #undef PLANTOS_TILE_RAY
         emit_byte<5 * C>(c, (unsigned)(4 * (LB_POS + x1)));          // :294-296
         emit_byte<5 * C + 1>(c, (unsigned)(4 * (LB_POS + y1)));
@@ -359,7 +429,9 @@ k_step_tile(const Params p, const StepIO io) {
             emit_vis<5 * C + 2 + 5 * i>(c, v * 4u + 0x01010101u * (4u * LB_VIS), ((sl[i] >> 16) & 15u) * 4u + 4u * LB_VIS); \
             flush_code<(5 * C + 2 + 5 * i) / 4, (5 * C + 2 + 5 * i + 5) / 4>(c, s_mycode, s8, act);         \
         }
+        if (!(PLANTOS_TILE_SKIP & 4)) {
         PLANTOS_TILE_VIS(0) PLANTOS_TILE_VIS(1) PLANTOS_TILE_VIS(2) PLANTOS_TILE_VIS(3) PLANTOS_TILE_VIS(4)
+        }
 #undef PLANTOS_TILE_VIS
         // the words that are still open: the last one (only if this lane owns it) and word 0, which also
         // carries the last (A & 3) bytes of the previous env
@@ -372,15 +444,21 @@ k_step_tile(const Params p, const StepIO io) {
                 if (TB && own_last) sts_u32_v(s_mycode + 4 * (NW - 1), __funnelshift_l(c[NW - 2], c[NW - 1], s8));
             }
         }
-        // a rover that changed rows: the type row and the nibble row that entered its window come from
-        // the planes (loads in flight during the expansion) and replace the rows that left the rings
-        const bool newrow = act && !done && dxm != 0;
-        const int pr_new = dxm > 0 ? x1 + NTR : x1 + 1, pn_new = dxm > 0 ? x1 + 6 : x1;
-        uint64_t trow_new = 0;
-        uint4 nrow_new = make_uint4(0, 0, 0, 0);
+        // the fetched rows of the rovers that changed rows go from the staging area into the cache rings,
+        // replacing the rows that left the windows; then the tile's state is complete
+        cp_async_wait_all();
         if (newrow) {
-            trow_new = mem.ld64(p.types + e * TS + pr_new);
-            nrow_new = mem.ld128(reinterpret_cast<const uint4*>(p.vis4 + e * VE + pn_new * VW));
+            const uint4 nrow_new = lds_u128_v(s_stage);
+            const uint64_t trow_new = lds_u64_v(s_stage + 16);
+            *reinterpret_cast<uint64_t*>(g_tile + 256 * (pr_new % NTR) + 8 * lane) = trow_new;
+            uint32_t* const gn = reinterpret_cast<uint32_t*>(g_tile + NTR * 256 + 512 * (pn_new % 7) + 4 * lane);
+            gn[0] = nrow_new.x; gn[32] = nrow_new.y; gn[64] = nrow_new.z; gn[96] = nrow_new.w;
+        }
+        const unsigned dmask0 = __ballot_sync(FULL, act && done);
+        __syncwarp();                                        // orders every lane's state stores before lane 0's release
+        if (dmask0 == 0u && lane == 0) {                     // the tile's state is complete: the next step may start
+            if (p.release) st_release_u32(p.tile_flags + t, ordinal + 1u);
+            else p.tile_flags[t] = ordinal + 1u;             // (nobody overlaps launches on this handle: the kernel end publishes it)
         }
         __syncwarp();
         TSTAMP(7);
@@ -389,7 +467,8 @@ k_step_tile(const Params p, const StepIO io) {
         {
             float4* const dst = reinterpret_cast<float4*>(io.obs) + ((size_t)e0 * D >> 2) + lane;
             const uint32_t s_cw = s_code + 4 * lane;
-            if (ts == 32) {
+            if ((PLANTOS_TILE_SKIP & 2) && ts >= 0) {
+            } else if (ts == 32) {
                 constexpr int LASTN = NVEC - 32 * (NIT - 1);        // lanes of the last iteration
 #pragma unroll
                 for (int q0 = 0; q0 < NIT; q0 += 3) {
@@ -397,7 +476,11 @@ k_step_tile(const Params p, const StepIO io) {
                     float4 f[3];
 #pragma unroll
                     for (int u = 0; u < 3; ++u)
-                        if (q0 + u < NIT) cw[u] = lds_u32_v(s_cw + 128 * (q0 + u));   // (beyond the image in the last one: unused)
+                        if (q0 + u < NIT) {
+                            cw[u] = lds_u32_v(s_cw + 128 * (q0 + u));
+                            // lanes beyond the image in the last iteration read stale bytes: make them a valid code
+                            if (q0 + u == NIT - 1 && LASTN != 32 && lane >= LASTN) cw[u] = 0u;
+                        }
 #pragma unroll
                     for (int u = 0; u < 3; ++u)
                         if (q0 + u < NIT) {
@@ -408,7 +491,8 @@ k_step_tile(const Params p, const StepIO io) {
                         }
 #pragma unroll
                     for (int u = 0; u < 3; ++u)
-                        if (q0 + u < NIT && (q0 + u < NIT - 1 || LASTN == 32 || lane < LASTN)) __stcs(dst + (q0 + u) * 32, f[u]);
+                        if (q0 + u < NIT && (q0 + u < NIT - 1 || LASTN == 32 || lane < LASTN) &&
+                            (!(PLANTOS_TILE_SKIP & 1) || f[u].x == 123.0f)) __stcs(dst + (q0 + u) * 32, f[u]);
                 }
             } else {
                 const int nvec = (ts * D) >> 2;
@@ -424,11 +508,6 @@ k_step_tile(const Params p, const StepIO io) {
                 }
             }
         }
-        if (newrow) {
-            *reinterpret_cast<uint64_t*>(g_tile + 256 * (pr_new % NTR) + 8 * lane) = trow_new;
-            uint32_t* const gn = reinterpret_cast<uint32_t*>(g_tile + NTR * 256 + 512 * (pn_new % 7) + 4 * lane);
-            gn[0] = nrow_new.x; gn[32] = nrow_new.y; gn[64] = nrow_new.z; gn[96] = nrow_new.w;
-        }
         __syncwarp();                                        // the buffer may be reused
         TSTAMP(8);
 #ifdef PLANTOS_EXP_TIMING
@@ -442,7 +521,7 @@ k_step_tile(const Params p, const StepIO io) {
 #endif
 
         // ---- auto-reset of finished envs (rare; warp-cooperative generic code in the same buffer)
-        unsigned dmask = __ballot_sync(FULL, act && done);
+        unsigned dmask = dmask0;
         while (dmask) {
             const int j = __ffs(dmask) - 1;
             dmask &= dmask - 1;
@@ -454,7 +533,7 @@ k_step_tile(const Params p, const StepIO io) {
             if (io.terminal_obs) {
                 for (int idx = lane; idx < G; idx += 32) plane[idx] = types_e[idx];
                 __syncwarp();
-                build_obs_warp(p, tb, plane, vis_e, px, py, row_s, lane);
+                build_obs_warp(p, tabs(), plane, vis_e, px, py, row_s, lane);
                 store_obs_row(row_s, io.terminal_obs + ej * D, D, lane);
                 __syncwarp();
             }
@@ -464,7 +543,7 @@ k_step_tile(const Params p, const StepIO io) {
                 keep = __shfl_sync(FULL, keep, 0);
             }
             const EnvRec nr = reset_env_warp(p, (int)ej, ep, plane, lane, keep != 0);
-            build_obs_warp(p, tb, plane, vis_e, nr.x, nr.y, row_s, lane, keep != 0);
+            build_obs_warp(p, tabs(), plane, vis_e, nr.x, nr.y, row_s, lane, keep != 0);
             store_obs_row(row_s, io.obs + ej * D, D, lane);
             wrc_build_env_warp(p, ej, nr.x, lane);           // the new episode's rings
             if (lane == 0) {
@@ -475,11 +554,15 @@ k_step_tile(const Params p, const StepIO io) {
             }
             __syncwarp();
         }
+        if (dmask0 != 0u && lane == 0) {                     // tiles with resets complete here
+            if (p.release) st_release_u32(p.tile_flags + t, ordinal + 1u);
+            else p.tile_flags[t] = ordinal + 1u;
+        }
     }
 
     // ragged tail: envs beyond the last 4-env group, one at a time (they are never part of a tile)
     if (blockIdx.x == gridDim.x - 1 && warp == kTileWarps - 1)
-        for (int e = nfull; e < p.N; ++e) step_env_warp(p, tb, io, e, plane, row_s, lane);
+        for (int e = nfull; e < p.N; ++e) step_env_warp(p, tabs(), io, e, plane, row_s, lane);
 }
 
 }  // namespace plantos_dev

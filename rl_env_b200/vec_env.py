@@ -309,12 +309,21 @@ class PlantOSVecEnv:
         return self.step_wait()
 
     # ------------------------------------------------------------------ step_many
-    def make_rollout(self, k: int, with_flags: bool = False) -> "GraphRollout":
+    def make_rollout(self, k: int, with_flags: bool = False, pipelined: bool = True) -> "GraphRollout":
         """K open-loop steps as ONE CUDA-graph launch: `rollout(actions[K, N])` returns the K
         observation / reward / done tensors (static buffers, overwritten by the next call).  For
         MCTS-style rollouts (mcts_custom_trainer.py:168-243 steps a copied env with a fixed action
-        sequence) and for small batches, where the per-step host launch cost dominates."""
-        return GraphRollout(self, k, with_flags)
+        sequence) and for small batches, where the per-step host launch cost dominates.
+        `pipelined`: consecutive steps of the rollout overlap (plantos_set_pipelining: the actions of
+        all K steps are resident before the launch, every step writes its own observation buffer)."""
+        return GraphRollout(self, k, with_flags, pipelined)
+
+    def set_pipelining(self, enable: bool) -> None:
+        """Let back-to-back `step_async` calls overlap on the device (open-loop stepping only: the
+        actions of a step must not be computed from the previous step's results, and `obs_ring >= 2`
+        so that consecutive steps write different observation buffers).  See plantos_set_pipelining."""
+        nat.check(self._lib.plantos_set_pipelining(self._h, int(bool(enable))))
+        self._pipelining = bool(enable)
 
     def rollout_policy(self, uniforms: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None) -> torch.Tensor:
         """Actions of the reference's MCTS rollout policy (mcts_custom_trainer.py:168-216) for the
@@ -499,7 +508,7 @@ class GraphRollout:
     not produced (read `env.scalars()` afterwards if needed); the device episode log would stamp
     every replay with the step numbers of the capture."""
 
-    def __init__(self, env: "PlantOSVecEnv", k: int, with_flags: bool = False):
+    def __init__(self, env: "PlantOSVecEnv", k: int, with_flags: bool = False, pipelined: bool = True):
         """`with_flags`: also write the env's terminated / truncated / terminal-observation buffers
         every step, like a single step does (they hold the last step's values afterwards)."""
         if k < 1:
@@ -515,6 +524,15 @@ class GraphRollout:
         self.graph = torch.cuda.CUDAGraph()
         lib, h = env._lib, env._h
         torch.cuda.synchronize(dev)
+        was = getattr(env, "_pipelining", False)
+        nat.check(lib.plantos_set_pipelining(h, int(bool(pipelined))))   # baked into the captured launches
+        try:
+            self._capture(env, with_flags)
+        finally:
+            nat.check(lib.plantos_set_pipelining(h, int(was)))
+
+    def _capture(self, env: "PlantOSVecEnv", with_flags: bool) -> None:
+        lib, h, dev = env._lib, env._h, env.device
         with torch.cuda.graph(self.graph):
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             term = env._terminated.data_ptr() if with_flags else None

@@ -146,8 +146,9 @@ def test_episode_log_and_monitor_csv_match_the_oracle_monitor(kernel, tmp_path):
         assert int(e["flags"]) in (1, 2, 3)
 
 
-@pytest.mark.parametrize("n,kernel", [(4096, "fast"), (515, "fast"), (300, "generic")])
-def test_graph_rollout_equals_single_steps(n, kernel):
+@pytest.mark.parametrize("pipelined", [True, False])
+@pytest.mark.parametrize("n,kernel", [(4096, "fast"), (8192, "fast"), (515, "fast"), (300, "generic")])
+def test_graph_rollout_equals_single_steps(n, kernel, pipelined):
     """make_rollout(K): K steps captured in one CUDA graph (incl. the programmatic-dependent-launch
     edges of the fast kernel) give exactly what K single steps give, replay after replay."""
     import torch
@@ -156,7 +157,7 @@ def test_graph_rollout_equals_single_steps(n, kernel):
     a, b = PlantOSVecEnv(n, **kw), PlantOSVecEnv(n, **kw)
     assert torch.equal(a.reset(), b.reset())
     K = 12
-    roll = b.make_rollout(K)
+    roll = b.make_rollout(K, pipelined=pipelined)   # pipelined: steps ordered tile by tile on the device (no-op with a ragged tail / generic)
     g = torch.Generator(device="cuda"); g.manual_seed(3)
     for rep in range(5):                                   # 60 steps: every env auto-resets at least once
         acts = torch.randint(0, 5, (K, n), device="cuda", generator=g)
@@ -166,6 +167,41 @@ def test_graph_rollout_equals_single_steps(n, kernel):
             assert torch.equal(obs, obs_k[t]) and torch.equal(rew, rew_k[t]) and torch.equal(done, done_k[t]), (rep, t)
     sa, sb = a.get_state(), b.get_state()
     assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    a.check(); b.check()
+    a.close(); b.close()
+
+
+def test_pipelined_eager_steps_equal_plain_steps():
+    """plantos_set_pipelining on eager launches: back-to-back step_async calls into an observation ring
+    overlap on the device (per-tile counters order them) and give exactly the plain results; every
+    observation of the ring is checked after the burst."""
+    import torch
+    from rl_env_b200 import PlantOSVecEnv, PRESETS
+    n, ring, steps = 16384, 6, 90
+    kw = dict(PRESETS["training"], max_steps=29, seed=5, kernel="fast", full_infos=False)
+    a, b = PlantOSVecEnv(n, **kw), PlantOSVecEnv(n, obs_ring=ring, **kw)
+    b.set_pipelining(True)
+    assert torch.equal(a.reset(), b.reset())
+    g = torch.Generator(device="cuda"); g.manual_seed(4)
+    acts = torch.randint(0, 5, (steps, n), device="cuda", generator=g)
+    want = []
+    for t in range(steps):
+        obs, rew, done, _ = a.step(acts[t])
+        want.append((obs.clone(), rew.clone(), done.clone()))
+    for t0 in range(0, steps, ring - 1):                   # bursts of ring-1 steps without a host sync
+        got = []
+        for t in range(t0, min(steps, t0 + ring - 1)):
+            b.step_async(acts[t])
+            obs, rew, done, _ = b.step_wait()
+            got.append((t, obs))
+        torch.cuda.synchronize()
+        for t, obs in got:
+            assert torch.equal(obs, want[t][0]), t
+        assert torch.equal(b._rewards, want[t][1]) and torch.equal(b._dones, want[t][2])
+    assert b.last_step_kernel == "k_step_tile"
+    sa, sb = a.get_state(), b.get_state()
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    a.check(); b.check()
     a.close(); b.close()
 
 
