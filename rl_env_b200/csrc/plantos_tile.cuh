@@ -49,7 +49,8 @@ constexpr int kTileWarps = PLANTOS_TILE_WARPS;
 #endif
 constexpr int kTileLutBytes = 256;    // 64 floats on a 256-byte boundary: the first bytes of the dynamic shared memory
 
-constexpr int kTileMbarBytes = 64;    // one 8-byte mbarrier per warp
+constexpr int kTileMbarBytes = 64;    // one 8-byte mbarrier per warp, then the launch ordinal
+constexpr int kTileRwBytes = 160;     // the two reward tables (12 f64 + 12 f32), read in the transition
 // per-warp scratch: the tile's window-ring-cache slice; reused as the flat byte code of the tile and as
 // phase C's plane + row
 // offset of the new-row staging area (32 B per lane) inside the scratch: beyond everything the expansion reads
@@ -63,7 +64,7 @@ __host__ __device__ inline int tile_warp_scratch_bytes(int R, int G, int D) {
     return b;
 }
 __host__ __device__ inline int tile_block_smem_bytes(int R, int G, int C) {
-    return kTileLutBytes + kTileMbarBytes + kTileWarps * tile_warp_scratch_bytes(R, G, 5 * C + 27);
+    return kTileLutBytes + kTileMbarBytes + kTileRwBytes + kTileWarps * tile_warp_scratch_bytes(R, G, 5 * C + 27);
 }
 
 // ---- TMA (bulk async copy) + mbarrier
@@ -97,6 +98,15 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* q) {
 }
 __device__ __forceinline__ void st_release_u32(unsigned* q, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(q), "r"(v) : "memory");
+}
+// one 32-byte record = one 256-bit access (sm_100: LDG/STG.E.ENL2.256), L2-coherent
+__device__ __forceinline__ void ld_rec256(const uint4* q, uint4& a, uint4& b) {
+    asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(q) : "memory");
+}
+__device__ __forceinline__ void st_rec256(uint4* q, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(q), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ uint4 lds_u128_v(uint32_t a) {
@@ -173,7 +183,8 @@ k_step_tile(const Params p, const StepIO io) {
     const uint32_t s_smem = smem_u32(smem);
     const uint32_t s_lut = s_smem;
     const uint32_t s_mbar = s_smem + kTileLutBytes + 8 * warp;
-    unsigned char* const scratch = smem + kTileLutBytes + kTileMbarBytes + warp * tile_warp_scratch_bytes(R, G, D);
+    const uint32_t s_rw64 = s_smem + kTileLutBytes + kTileMbarBytes, s_rw32 = s_rw64 + 96;
+    unsigned char* const scratch = smem + kTileLutBytes + kTileMbarBytes + kTileRwBytes + warp * tile_warp_scratch_bytes(R, G, D);
     // the tables stay in global memory (the host-packed image, plantos_common.cuh: tables_at): the hot
     // loop only needs the two reward tables (L1 hits), the rare generic paths read them as they are
     // (recomputed at every use: seven pointers are not worth registers)
@@ -207,6 +218,12 @@ k_step_tile(const Params p, const StepIO io) {
         else if (i >= LB_VIS && i < LB_POS) v = __ldg(tb.visit + (i - LB_VIS));
         else if (i >= LB_POS && i < LB_POS + G) v = __ldg(tb.pos + (i - LB_POS));
         sts_u32_v(s_lut + 4 * i, __float_as_uint(v));
+        // (acquire loads invalidate the SM's L1 all the time in pipelined mode: the reward tables live in shared memory too)
+        if (i < 2 * kRwCount) {
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(tb.rw64) + i);
+            sts_u64_v(s_rw64 + 8 * i, (uint64_t)q.x | ((uint64_t)q.y << 32));
+            sts_u32_v(s_rw32 + 4 * i, __float_as_uint(__ldg(tb.rw32 + i)));
+        }
     }
     if (threadIdx.x == 0) {
         sts_u32_v(s_smem + kTileLutBytes + 8 * kTileWarps, ticket);
@@ -234,11 +251,25 @@ k_step_tile(const Params p, const StepIO io) {
             fence_proxy_async_global();                     // the bulk copy below reads what other SMs stored
         }
     };
-    if (t < ntiles && lane == 0) {                          // the first tile's rings are on their way at once
-        wait_tile(t, flag0);
-        mbar_arrive_expect_tx(s_mbar, WRCB);
-        bulk_load(s_win, p.wrc + (size_t)t * WRCB, WRCB, s_mbar);
-    }
+#ifndef PLANTOS_TILE_RINGCOPY
+#define PLANTOS_TILE_RINGCOPY 0       // 0: one TMA bulk copy per tile; 1: 16-byte cp.async copies by all lanes (experiment)
+#endif
+    auto fetch_rings = [&](int tile, unsigned seen) {
+        if (PLANTOS_TILE_RINGCOPY) {
+            if (lane == 0) wait_tile(tile, seen);
+            __syncwarp();
+            const unsigned char* src = p.wrc + (size_t)tile * WRCB + 16 * lane;
+#pragma unroll
+            for (int k = 0; k < (WRCB + 511) / 512; ++k)
+                if (512 * k + 16 * lane < WRCB) cp_async16(s_win + 512 * k + 16 * lane, src + 512 * k);
+            cp_async_commit();
+        } else if (lane == 0) {
+            wait_tile(tile, seen);
+            mbar_arrive_expect_tx(s_mbar, WRCB);
+            bulk_load(s_win, p.wrc + (size_t)tile * WRCB, WRCB, s_mbar);
+        }
+    };
+    if (t < ntiles) fetch_rings(t, flag0);                  // the first tile's rings are on their way at once
     constexpr uint64_t LOWPAD = kObstAll & ((1ull << (2 * R)) - 1ull);
     // flat code image: env j's D bytes start at byte D*j; this lane owns words a_w .. a_w + M - 1
     const int A = D * lane, s8 = 8 * (A & 3);
@@ -253,11 +284,9 @@ k_step_tile(const Params p, const StepIO io) {
         const bool act = lane < ts;
         const unsigned e = (unsigned)(e0 + lane);            // 32-bit element offsets (host check)
         unsigned char* const g_tile = p.wrc + (size_t)t * WRCB;   // this tile's rings in global memory
-        if (!first && lane == 0) {                           // (the whole warp is past its last use of the buffer)
-            wait_tile(t, p.pipelined ? ld_acquire_u32(p.tile_flags + t) : 0u);
-            fence_proxy_async_shared();
-            mbar_arrive_expect_tx(s_mbar, WRCB);
-            bulk_load(s_win, g_tile, WRCB, s_mbar);
+        if (!first) {                                        // (the whole warp is past its last use of the buffer)
+            if (lane == 0) fence_proxy_async_shared();
+            fetch_rings(t, (p.pipelined && lane == 0) ? ld_acquire_u32(p.tile_flags + t) : 0u);
         }
 
         __syncwarp();                                        // (lane 0 has seen the tile's flag)
@@ -265,15 +294,14 @@ k_step_tile(const Params p, const StepIO io) {
         uint4 ra = make_uint4(0, 0, 0, 0), rbw = ra;
         long long action = 0;
         if (act) {
-            ra = __ldcg(p.rec + 2 * e);
-            rbw = __ldcg(p.rec + 2 * e + 1);
+            ld_rec256(p.rec + 2 * e, ra, rbw);
             action = __ldcg(io.actions + e);
         }
         EnvRec r = unpack_rec(ra, rbw);
         const int x0 = r.x;
         if (x0 >= 0) TSTAMP(2);
-        while (!mbar_try_wait(s_mbar, parity)) {}
-        parity ^= 1u;
+        if (PLANTOS_TILE_RINGCOPY) { cp_async_wait_all(); __syncwarp(); }
+        else { while (!mbar_try_wait(s_mbar, parity)) {} parity ^= 1u; }
         TSTAMP(4);
 
         // ---- transition (plantos_env.py:160-222), one lane per env, out of the rings
@@ -314,21 +342,17 @@ k_step_tile(const Params p, const StepIO io) {
                 sts_u64_v(s_t8 + o_tw, nw);
                 *reinterpret_cast<uint64_t*>(g_tile + 8 * lane + o_tw) = nw;
             }
-            r.ret += __ldg(tabs().rw64 + o.ridx);
+            r.ret += lds_f64(s_rw64 + 8 * o.ridx);
             term = o.terminated; trunc = o.truncated; done = term | trunc;
             pack_rec(r, ra, rbw);
             if (!(PLANTOS_TILE_SKIP & 16) || r.step == 54321) {
-            io.reward[e] = __ldg(tabs().rw32 + o.ridx);
+            io.reward[e] = lds_f32(s_rw32 + 4 * o.ridx);
             io.done[e] = (uint8_t)done;
             if (io.terminated) io.terminated[e] = (uint8_t)term;
             if (io.truncated) io.truncated[e] = (uint8_t)trunc;
-            mem.st128(p.rec + 2 * e, ra);
-            mem.st128(p.rec + 2 * e + 1, rbw);
+            st_rec256(p.rec + 2 * e, ra, rbw);
             }
-            if (done) {
-                p.term_rec[2 * e] = ra;
-                p.term_rec[2 * e + 1] = rbw;
-            }
+            if (done) st_rec256(p.term_rec + 2 * e, ra, rbw);
         }
         accumulate_stats(p, act && done, r, term, trunc, lane, (int)e);
         TSTAMP(5);
@@ -512,11 +536,12 @@ k_step_tile(const Params p, const StepIO io) {
         TSTAMP(8);
 #ifdef PLANTOS_EXP_TIMING
         { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); ts_[9] = sm; }
-        if (lane == 0 && ts >= 8)
+        if (lane == 0 && ts == 32)                            // the stamps of the last four launches, side by side
             for (int k = 0; k < 5; ++k) {
-                uint4 v = p.term_rec[2 * ((size_t)e0 + k) + 1];
+                const size_t slot = (size_t)e0 + 5 * (ordinal & 3u) + k;
+                uint4 v = p.term_rec[2 * slot + 1];
                 v.z = ts_[2 * k]; v.w = ts_[2 * k + 1];
-                p.term_rec[2 * ((size_t)e0 + k) + 1] = v;
+                p.term_rec[2 * slot + 1] = v;
             }
 #endif
 

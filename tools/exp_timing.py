@@ -4,6 +4,7 @@ from rl_env_b200.vec_env import PlantOSVecEnv, PRESETS
 N = 131072
 env = PlantOSVecEnv(N, device="cuda:0", seed=1, obs_ring=5, **PRESETS["training"])
 env.reset()
+if os.environ.get("PIPE", "0") == "1": env.set_pipelining(True)
 acts = [torch.randint(0, 5, (N,), device="cuda") for _ in range(16)]
 for i in range(200):
     env.step(acts[i % 16])
@@ -17,6 +18,8 @@ for e0 in range(0, N - 8, 32 if os.environ.get('PLANTOS_FAST_IMPL', 'tile') == '
     if lo[e0] != 0 and hi[e0] != 0 and lo[e0+4] != 0:
         T.append([lo[e0], hi[e0], lo[e0+1], hi[e0+1], lo[e0+2], hi[e0+2], lo[e0+3], hi[e0+3], lo[e0+4], hi[e0+4]])
 T = np.array(T, dtype=np.int64)
+os.makedirs("gpurun_out/r2", exist_ok=True)
+np.save("gpurun_out/r2/stamps_%s.npy" % ("pipe" if os.environ.get("PIPE", "0") == "1" else "plain"), T)
 print("warps", len(T))
 base = T[:, 1].max()  # last griddep_wait return ~ previous kernel end
 t0 = T[:, 0].min()
