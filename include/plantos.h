@@ -223,6 +223,18 @@ int plantos_check(plantos_t* h, void* stream);
 int64_t plantos_launch_count(const plantos_t* h);
 /* Kernel family the handle selected at create ("generic" / "fast"). */
 const char* plantos_kernel_name(const plantos_t* h);
+/* num_steps consecutive steps with pre-generated actions in ONE call -- the open-loop rollout the
+ * reference's MCTS planner runs on a copied env (mcts_custom_trainer.py:139-166: `_rollout` steps
+ * `sim_env` up to max_depth with no learner in between).  actions [num_steps][N]; step k writes
+ * obs + k * obs_step_stride (floats; >= N * obs_dim, a multiple of 4), reward / done / terminated /
+ * truncated + k * N (the last two may be NULL); terminal_obs as in plantos_step.  Auto-reset applies
+ * inside the rollout exactly as in single steps; the result is bit-identical to num_steps plantos_step
+ * calls.  On the fast presets this is one launch of the state-resident kernel (each warp keeps its 32
+ * envs' window rings and records on the SM for all num_steps steps); otherwise num_steps launches. */
+int plantos_rollout(plantos_t* h, int num_steps, const int64_t* actions_dev, float* obs_dev, int64_t obs_step_stride,
+                    float* reward_dev, uint8_t* done_dev, uint8_t* terminated_dev, uint8_t* truncated_dev,
+                    float* terminal_obs_dev, void* stream);
+
 /* Pipelined stepping for OPEN-LOOP sequences (rollouts with pre-generated actions, benchmarks): with
  * enable != 0 a plantos_step that directly follows another plantos_step of this handle on the same
  * stream, writing a DIFFERENT obs buffer, no longer waits for the previous launch as a whole; per-tile

@@ -56,6 +56,7 @@ SIGNATURES = {
     "plantos_push_maps": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "plantos_reset": (C.c_int, [_vp, _vp, _vp]),
     "plantos_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "plantos_rollout": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "plantos_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "plantos_get_scalars": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "plantos_get_returns": (C.c_int, [_vp, C.c_int, _vp, _vp]),

@@ -32,6 +32,7 @@ int fail(int code, const std::string& msg) {
     } while (0)
 
 typedef void (*fast_kernel_t)(const Params, const StepIO);
+typedef void (*tile_kernel_t)(const Params, const RollIO);
 
 struct FastVariant { int R, C, keep; fast_kernel_t fn; };
 
@@ -47,8 +48,9 @@ const FastVariant kFastVariants[] = {
 const FastVariant kLaneVariants[] = { LANE_ROW(6, 16), LANE_ROW(2, 10), LANE_ROW(4, 16), LANE_ROW(4, 8) };
 
 // k_step_tile (plantos_tile.cuh): lane-per-env simulation + byte-coded observation output
-#define TILE_ROW(R_, C_) {R_, C_, 0, k_step_tile<R_, C_>}
-const FastVariant kTileVariants[] = { TILE_ROW(6, 16), TILE_ROW(2, 10), TILE_ROW(4, 16), TILE_ROW(4, 8) };
+struct TileVariant { int R, C; tile_kernel_t step, rollout; };
+#define TILE_ROW(R_, C_) {R_, C_, k_tile<R_, C_, false>, k_tile<R_, C_, true>}
+const TileVariant kTileVariants[] = { TILE_ROW(6, 16), TILE_ROW(2, 10), TILE_ROW(4, 16), TILE_ROW(4, 8) };
 
 // Does a LIDAR offset table equal the compile-time one the lane kernel was built with?
 template <int R, int C>
@@ -89,7 +91,9 @@ struct plantos {
     bool use_fast;               // a specialised kernel exists for this shape
     FastLaunch trip;             // k_step_fast (fn == nullptr: none)
     FastLaunch lane;             // k_step_lane
-    FastLaunch tile;             // k_step_tile
+    FastLaunch tile;             // k_step_tile = k_tile<R, C, false> (fn unused: see tile_step)
+    tile_kernel_t tile_step, tile_rollout;   // k_tile<R, C, false / true>
+    int rollout_grid, rollout_smem;
     int impl;                    // 0: k_step_tile when possible, 1: k_step_fast, 2: k_step_lane (experiments)
     const char* last_kernel;     // name of the kernel the latest plantos_step launched
     bool wrc_valid;              // the window ring cache mirrors the planes (k_step_tile keeps it so)
@@ -346,8 +350,11 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
             if (v.R == p.R && v.C == p.C && v.keep == keep) { h->use_fast = true; h->trip.fn = v.fn; }
         for (const FastVariant& v : kLaneVariants)
             if (v.R == p.R && v.C == p.C && v.keep == keep) h->lane.fn = v.fn;
-        for (const FastVariant& v : kTileVariants)
-            if (v.R == p.R && v.C == p.C && h->use_fast) h->tile.fn = v.fn;
+        for (const TileVariant& v : kTileVariants)
+            if (v.R == p.R && v.C == p.C && h->use_fast) {
+                h->tile.fn = h->trip.fn;                    // (non-null marks the tile path as available)
+                h->tile_step = v.step; h->tile_rollout = v.rollout;
+            }
     }
     if (cfg->kernel == PLANTOS_KERNEL_FAST && !h->use_fast) {
         free_all(h);
@@ -381,7 +388,8 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
             if (const char* s = std::getenv("PLANTOS_FAST_GRID")) { const int v = std::atoi(s); if (v > 0 && v < blocks) blocks = v; }
             L.grid = (int)(blocks < 1 ? 1 : blocks);
             L.threads = kTileWarps * 32; L.smem = tile_block_smem_bytes(p.R, p.G, p.C); L.q = 32;
-            if (L.smem > (int)prop.sharedMemPerBlockOptin) L.fn = nullptr;
+            h->rollout_smem = tile_block_smem_bytes_multi(p.R, p.G, p.C);
+            if (L.smem > (int)prop.sharedMemPerBlockOptin || h->rollout_smem > (int)prop.sharedMemPerBlockOptin) L.fn = nullptr;
             if (L.fn) {                                     // the window ring cache, one slice per 32-env tile
                 const size_t bytes = (size_t)((p.N + 31) / 32) * wrc_tile_bytes(p.R);
                 if (cudaMalloc((void**)&p.wrc, bytes) != cudaSuccess) { p.wrc = nullptr; L.fn = nullptr; cudaGetLastError(); }
@@ -415,10 +423,18 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     const long long want = ((long long)p.N + kGenericWarps - 1) / kGenericWarps;
     const long long cap = (long long)h->num_sms * occ;
     h->generic_grid = (int)(want < cap ? want : cap);
-    for (FastLaunch* L : {&h->trip, &h->lane, &h->tile}) {
+    for (FastLaunch* L : {&h->trip, &h->lane}) {
         if (!h->use_fast || !L->fn) continue;
         cudaError_t e3 = cudaFuncSetAttribute(L->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, L->smem);
         if (e3 != cudaSuccess) { free_all(h); return fail(PLANTOS_ECUDA, std::string("cudaFuncSetAttribute(fast): ") + cudaGetErrorString(e3)); }
+    }
+    if (h->use_fast && h->tile.fn) {
+        cudaError_t e3 = cudaFuncSetAttribute(h->tile_step, cudaFuncAttributeMaxDynamicSharedMemorySize, h->tile.smem);
+        cudaError_t e4 = cudaFuncSetAttribute(h->tile_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, h->rollout_smem);
+        if (e3 != cudaSuccess || e4 != cudaSuccess) {
+            free_all(h);
+            return fail(PLANTOS_ECUDA, std::string("cudaFuncSetAttribute(tile): ") + cudaGetErrorString(e3 != cudaSuccess ? e3 : e4));
+        }
     }
     cudaError_t es = cudaDeviceSynchronize();
     if (es != cudaSuccess) { free_all(h); return fail(PLANTOS_ECUDA, std::string("create: ") + cudaGetErrorString(es)); }
@@ -484,26 +500,32 @@ extern "C" int plantos_reset(plantos_t* h, float* obs_dev, void* stream) {
     return PLANTOS_OK;
 }
 
-extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, float* reward, uint8_t* done,
-                            uint8_t* terminated, uint8_t* truncated, float* terminal_obs, void* stream) {
-    if (!h || !actions || !obs || !reward || !done) return fail(PLANTOS_EINVAL, "handle/actions/obs/reward/done is NULL");
-    if (!h->did_reset) return fail(PLANTOS_ESTATE, "plantos_step before plantos_reset");
-    StepIO io;
-    io.actions = (const long long*)actions; io.obs = obs; io.reward = reward; io.done = done;
-    io.terminated = terminated; io.truncated = truncated; io.terminal_obs = terminal_obs;
+// K consecutive steps (K = 1: plantos_step).  The tile kernels take them in one launch (K > 1: the
+// state-resident k_tile<R, C, true>); every other configuration steps K times.
+static int launch_steps(plantos_t* h, int K, const int64_t* actions, float* obs, size_t obs_stride, float* reward,
+                        uint8_t* done, uint8_t* terminated, uint8_t* truncated, float* terminal_obs, void* stream) {
     CUDA_TRY(cudaSetDevice(h->device));
+    const size_t N = (size_t)h->p.N;
+    const bool aligned = (((uintptr_t)obs) & 15u) == 0 && (K == 1 || (obs_stride & 3u) == 0);
+    const bool use_tile = h->use_fast && aligned && h->impl == 0 && h->tile.fn && h->lane_offsets_ok;
+    if (!use_tile && K > 1) {                               // no multi-step kernel for this configuration
+        for (int k = 0; k < K; ++k) {
+            int rc = launch_steps(h, 1, actions + k * N, obs + k * obs_stride, 0, reward + k * N, done + k * N,
+                                  terminated ? terminated + k * N : nullptr, truncated ? truncated + k * N : nullptr,
+                                  terminal_obs, stream);
+            if (rc) return rc;
+        }
+        return PLANTOS_OK;
+    }
     h->p.step_seq = (unsigned)h->steps;
-    h->steps += 1;
-    const bool aligned = (((uintptr_t)obs) & 15u) == 0;
+    h->steps += K;
     if (h->use_fast && aligned) {
         // launched with programmatic stream serialization so that back-to-back steps overlap the
         // next step's prologue with this step's tail (the kernel waits on griddepcontrol before it
         // touches any state); PLANTOS_PDL=0 falls back to a plain launch
         cudaLaunchConfig_t lc = {};
-        // (the experimental lane kernel has no curriculum path)
-        const bool use_tile = h->impl == 0 && h->tile.fn && h->lane_offsets_ok;
         if (use_tile && !h->wrc_valid) {                    // something else changed the state: rebuild the cache
-            const size_t threads = (size_t)h->p.N * 32;
+            const size_t threads = N * 32;
             k_wrc_build<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->p);
             CUDA_TRY(cudaGetLastError());
             h->launches += 1;
@@ -512,32 +534,47 @@ extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, fl
         // Pipelined launch (plantos_set_pipelining): allowed when the handle's previous operation was a
         // k_step_tile launch on this stream into a DIFFERENT observation buffer (the expansion stores of
         // consecutive steps are not ordered) and there is no ragged tail (its envs bypass the tile flags).
-        const size_t obs_bytes = (size_t)h->p.N * h->p.D * sizeof(float);
+        const size_t obs_bytes = N * h->p.D * sizeof(float);
         const bool disjoint = h->prev_obs && ((const char*)obs + obs_bytes <= (const char*)h->prev_obs ||
                                               (const char*)h->prev_obs + obs_bytes <= (const char*)obs);
-        h->p.pipelined = (use_tile && h->pipelining && h->use_pdl && h->prev_tile_step && disjoint &&
+        h->p.pipelined = (use_tile && K == 1 && h->pipelining && h->use_pdl && h->prev_tile_step && disjoint &&
                           h->prev_stream == stream && (h->p.N & 3) == 0) ? 1 : 0;
         h->p.release = h->pipelining ? 1 : 0;
-        h->prev_tile_step = use_tile; h->prev_obs = obs; h->prev_stream = stream;
+        h->prev_tile_step = use_tile && K == 1; h->prev_obs = obs; h->prev_stream = stream;
+        // (the experimental lane kernel has no curriculum path)
         const bool use_lane = h->prefer_lane && h->lane.fn && h->lane_offsets_ok && !h->p.cur_mode;
         const FastLaunch& L = use_tile ? h->tile : (use_lane ? h->lane : h->trip);
-        h->last_kernel = use_tile ? "k_step_tile" : (use_lane ? "k_step_lane" : "k_step_fast");
+        h->last_kernel = use_tile ? (K > 1 ? "k_rollout_tile" : "k_step_tile") : (use_lane ? "k_step_lane" : "k_step_fast");
         h->p.fast_q = L.q;
         lc.gridDim = dim3((unsigned)L.grid); lc.blockDim = dim3((unsigned)L.threads);
-        lc.dynamicSmemBytes = (size_t)L.smem; lc.stream = (cudaStream_t)stream;
+        lc.dynamicSmemBytes = (size_t)((use_tile && K > 1) ? h->rollout_smem : L.smem); lc.stream = (cudaStream_t)stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         // (not while the stream is being captured into a CUDA graph: measured, graph kernel nodes
         // with programmatic edges run 0.8 us per step slower than plain graph edges, while eager
-        // launches gain 1.1 us from PDL)
+        // launches gain 1.1 us from PDL -- unless the launch is pipelined, which needs the edge)
         cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing((cudaStream_t)stream, &capturing);
         lc.attrs = at; lc.numAttrs = (h->use_pdl && (capturing == cudaStreamCaptureStatusNone || h->p.pipelined)) ? 1 : 0;
-        CUDA_TRY(cudaLaunchKernelEx(&lc, L.fn, h->p, io));
+        if (use_tile) {
+            RollIO ro;
+            ro.actions = (const long long*)actions; ro.obs = obs; ro.obs_stride = obs_stride; ro.reward = reward;
+            ro.done = done; ro.terminated = terminated; ro.truncated = truncated; ro.terminal_obs = terminal_obs; ro.K = K;
+            CUDA_TRY(cudaLaunchKernelEx(&lc, K > 1 ? h->tile_rollout : h->tile_step, h->p, ro));
+        } else {
+            StepIO io;
+            io.actions = (const long long*)actions; io.obs = obs; io.reward = reward; io.done = done;
+            io.terminated = terminated; io.truncated = truncated; io.terminal_obs = terminal_obs;
+            CUDA_TRY(cudaLaunchKernelEx(&lc, L.fn, h->p, io));
+            h->wrc_valid = false;
+        }
     } else {
         if (h->cfg.kernel == PLANTOS_KERNEL_FAST)
             return fail(PLANTOS_EINVAL, "PLANTOS_KERNEL_FAST needs a 16-byte aligned obs buffer");
+        StepIO io;
+        io.actions = (const long long*)actions; io.obs = obs; io.reward = reward; io.done = done;
+        io.terminated = terminated; io.truncated = truncated; io.terminal_obs = terminal_obs;
         k_step_generic<<<h->generic_grid, kGenericWarps * 32, h->generic_smem, (cudaStream_t)stream>>>(h->p, io);
         h->last_kernel = "k_step_generic";
         h->wrc_valid = false;
@@ -546,6 +583,23 @@ extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, fl
     CUDA_TRY(cudaGetLastError());
     h->launches += 1;
     return PLANTOS_OK;
+}
+
+extern "C" int plantos_step(plantos_t* h, const int64_t* actions, float* obs, float* reward, uint8_t* done,
+                            uint8_t* terminated, uint8_t* truncated, float* terminal_obs, void* stream) {
+    if (!h || !actions || !obs || !reward || !done) return fail(PLANTOS_EINVAL, "handle/actions/obs/reward/done is NULL");
+    if (!h->did_reset) return fail(PLANTOS_ESTATE, "plantos_step before plantos_reset");
+    return launch_steps(h, 1, actions, obs, 0, reward, done, terminated, truncated, terminal_obs, stream);
+}
+
+extern "C" int plantos_rollout(plantos_t* h, int num_steps, const int64_t* actions, float* obs, int64_t obs_step_stride,
+                               float* reward, uint8_t* done, uint8_t* terminated, uint8_t* truncated,
+                               float* terminal_obs, void* stream) {
+    if (!h || !actions || !obs || !reward || !done) return fail(PLANTOS_EINVAL, "handle/actions/obs/reward/done is NULL");
+    if (num_steps < 1) return fail(PLANTOS_EINVAL, "num_steps must be >= 1");
+    if (obs_step_stride < (int64_t)h->p.N * h->p.D) return fail(PLANTOS_EINVAL, "obs_step_stride must be >= num_envs * obs_dim");
+    if (!h->did_reset) return fail(PLANTOS_ESTATE, "plantos_rollout before plantos_reset");
+    return launch_steps(h, num_steps, actions, obs, (size_t)obs_step_stride, reward, done, terminated, truncated, terminal_obs, stream);
 }
 
 extern "C" int plantos_step_host(plantos_t* h, const int64_t* actions_host, float* obs_host, float* reward_host,

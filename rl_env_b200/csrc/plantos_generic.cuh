@@ -212,7 +212,7 @@ __device__ __forceinline__ void wrc_build_env_warp(const Params& p, size_t e, in
 // and, when enabled, one episode-log entry per finished env (`env` = the lane's env index;
 // slots are handed out with one atomic per warp)
 __device__ __forceinline__ void accumulate_stats(const Params& p, bool done, const EnvRec& r, int terminated,
-                                                 int truncated, int lane, int env) {
+                                                 int truncated, int lane, int env, unsigned seq_add = 0u) {
     const unsigned dm = __ballot_sync(0xffffffffu, done);
     if (dm == 0u) return;
     if (p.ep_log) {
@@ -222,7 +222,7 @@ __device__ __forceinline__ void accumulate_stats(const Params& p, bool done, con
         const unsigned slot = base + (unsigned)__popc(dm & ((1u << lane) - 1u));
         if (done && slot < (unsigned)p.ep_log_cap) {
             const unsigned long long rb = (unsigned long long)__double_as_longlong(r.ret);
-            p.ep_log[2 * (size_t)slot] = make_uint4((unsigned)env, (unsigned)r.step, p.step_seq,
+            p.ep_log[2 * (size_t)slot] = make_uint4((unsigned)env, (unsigned)r.step, p.step_seq + seq_add,
                                                      (unsigned)(terminated | (truncated << 1)));
             p.ep_log[2 * (size_t)slot + 1] = make_uint4((unsigned)rb, (unsigned)(rb >> 32), (unsigned)r.collisions,
                                                          (unsigned)r.watered);

@@ -66,6 +66,16 @@ __host__ __device__ inline int tile_warp_scratch_bytes(int R, int G, int D) {
 __host__ __device__ inline int tile_block_smem_bytes(int R, int G, int C) {
     return kTileLutBytes + kTileMbarBytes + kTileRwBytes + kTileWarps * tile_warp_scratch_bytes(R, G, 5 * C + 27);
 }
+// the multi-step kernel keeps the rings and has the code image (+ phase C scratch) behind them
+__host__ __device__ inline int tile_warp_scratch_bytes_multi(int R, int G, int D) {
+    int b = tile_stage_off(D);
+    const int resetscratch = align_up(G * 8, 16) + align_up(D * 4, 16);
+    if (resetscratch > b) b = resetscratch;
+    return wrc_tile_bytes(R) + b;
+}
+__host__ __device__ inline int tile_block_smem_bytes_multi(int R, int G, int C) {
+    return kTileLutBytes + kTileMbarBytes + kTileRwBytes + kTileWarps * tile_warp_scratch_bytes_multi(R, G, 5 * C + 27);
+}
 
 // ---- TMA (bulk async copy) + mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
@@ -152,9 +162,29 @@ __device__ __forceinline__ void flush_code(const uint32_t (&c)[NWORDS], uint32_t
 }
 
 
-template <int R, int C>
-__global__ void __launch_bounds__(kTileWarps * 32, PLANTOS_TILE_MINBLOCKS)
-k_step_tile(const Params p, const StepIO io) {
+// Outputs of K consecutive steps (K = 1: one plantos_step): step k reads actions + k * N and writes
+// obs + k * obs_stride, reward / done / terminated / truncated + k * N; terminal_obs is one [N, D] buffer.
+struct RollIO {
+    const long long* actions;
+    float* obs;
+    size_t obs_stride;      // floats between the observation buffers of consecutive steps
+    float* reward;
+    uint8_t* done;
+    uint8_t* terminated;
+    uint8_t* truncated;
+    float* terminal_obs;
+    int K;
+};
+
+// MULTI = false: k_step_tile, one step per launch (plantos_step).
+// MULTI = true:  k_rollout_tile, K steps per launch with the tile's rings and records RESIDENT on the SM
+//                (plantos_rollout; the state-resident multi-step kernel of SURVEY 8f row 4): the rings are
+//                fetched once, patched in place for K steps (visit-count patches also go to the plane, the
+//                source of the rows that enter a window), and written back once; the code image has its own
+//                buffer; half as many warps per SM, each walking its tiles one after the other.
+template <int R, int C, bool MULTI>
+__global__ void __launch_bounds__(kTileWarps * 32, MULTI ? PLANTOS_TILE_MINBLOCKS / 2 : PLANTOS_TILE_MINBLOCKS)
+k_tile(const Params p, const RollIO io) {
     using Gen = LidarGen<R, C>;
     static_assert(Gen::ok, "no generated LIDAR offsets for this (R, C)");
     constexpr int D = 5 * C + 27;
@@ -184,15 +214,19 @@ k_step_tile(const Params p, const StepIO io) {
     const uint32_t s_lut = s_smem;
     const uint32_t s_mbar = s_smem + kTileLutBytes + 8 * warp;
     const uint32_t s_rw64 = s_smem + kTileLutBytes + kTileMbarBytes, s_rw32 = s_rw64 + 96;
-    unsigned char* const scratch = smem + kTileLutBytes + kTileMbarBytes + kTileRwBytes + warp * tile_warp_scratch_bytes(R, G, D);
+    unsigned char* const scratch = smem + kTileLutBytes + kTileMbarBytes + kTileRwBytes +
+                                   warp * (MULTI ? tile_warp_scratch_bytes_multi(R, G, D) : tile_warp_scratch_bytes(R, G, D));
     // the tables stay in global memory (the host-packed image, plantos_common.cuh: tables_at): the hot
     // loop only needs the two reward tables (L1 hits), the rare generic paths read them as they are
     // (recomputed at every use: seven pointers are not worth registers)
     auto tabs = [&]() { return tables_at(const_cast<unsigned char*>(reinterpret_cast<const unsigned char*>(p.table_blob)), G, R); };
     const uint32_t s_win = smem_u32(scratch);
-    const uint32_t s_code = s_win;                            // the code image reuses the ring buffer
-    uint64_t* const plane = reinterpret_cast<uint64_t*>(scratch);                                 // phase C scratch
-    float* const row_s = reinterpret_cast<float*>(scratch + align_up(G * 8, 16));
+    // the code image reuses the ring buffer (single step) or sits behind the resident rings (multi-step)
+    constexpr int CODE_OFF = MULTI ? WRCB : 0;
+    const uint32_t s_code = s_win + CODE_OFF;
+    uint64_t* const plane = reinterpret_cast<uint64_t*>(scratch + CODE_OFF);                      // phase C scratch
+    float* const row_s = reinterpret_cast<float*>(scratch + CODE_OFF + align_up(G * 8, 16));
+    const int K = MULTI ? io.K : 1;
 
     // tiles of 32 envs; tile (round r, block b, warp w) = r * nwarps + w * nblocks + b, so every
     // round of the persistent loop spreads evenly over the SMs
@@ -298,12 +332,19 @@ k_step_tile(const Params p, const StepIO io) {
             action = __ldcg(io.actions + e);
         }
         EnvRec r = unpack_rec(ra, rbw);
-        const int x0 = r.x;
-        if (x0 >= 0) TSTAMP(2);
+        if (r.x >= 0) TSTAMP(2);
         if (PLANTOS_TILE_RINGCOPY) { cp_async_wait_all(); __syncwarp(); }
         else { while (!mbar_try_wait(s_mbar, parity)) {} parity ^= 1u; }
         TSTAMP(4);
 
+      for (int k = 0; k < K; ++k) {                          // (one pass for k_step_tile)
+        const size_t ko = (size_t)k * (size_t)p.N;           // offset of step k in the [K, N] outputs
+        long long action_next = 0;
+        if (MULTI) {
+            if (act && k + 1 < K) action_next = __ldcg(io.actions + ko + p.N + e);   // in flight during this step
+            cp_async_wait_all();                             // the rows the previous step pulled into this lane's rings
+        }
+        const int x0 = r.x;
         // ---- transition (plantos_env.py:160-222), one lane per env, out of the rings
         int done = 0, term = 0, trunc = 0;
         if (act) {
@@ -334,27 +375,27 @@ k_step_tile(const Params p, const StepIO io) {
             if (o.moved) {                                   // visit count + 1: plane, ring (shared), ring (cache)
                 const uint32_t nw = bump_visit(p.vis4 + e * VE + nib_word(tx, ty, VW), vword, sh, p.visov + e * G * G + tx * G + ty, mem);
                 sts_u32_v(s_n4 + o_vw, nw);
-                *reinterpret_cast<uint32_t*>(g_tile + NTR * 256 + 4 * lane + o_vw) = nw;
+                if (!MULTI) *reinterpret_cast<uint32_t*>(g_tile + NTR * 256 + 4 * lane + o_vw) = nw;   // (MULTI: rings written back at the end)
             }
             if (o.watered) {                                 // 3 -> 2
                 const uint64_t nw = word ^ (1ull << (2 * (ty & 31)));
                 mem.st64(p.types + e * TS + TP + tx, nw);
                 sts_u64_v(s_t8 + o_tw, nw);
-                *reinterpret_cast<uint64_t*>(g_tile + 8 * lane + o_tw) = nw;
+                if (!MULTI) *reinterpret_cast<uint64_t*>(g_tile + 8 * lane + o_tw) = nw;
             }
             r.ret += lds_f64(s_rw64 + 8 * o.ridx);
             term = o.terminated; trunc = o.truncated; done = term | trunc;
             pack_rec(r, ra, rbw);
             if (!(PLANTOS_TILE_SKIP & 16) || r.step == 54321) {
-            io.reward[e] = lds_f32(s_rw32 + 4 * o.ridx);
-            io.done[e] = (uint8_t)done;
-            if (io.terminated) io.terminated[e] = (uint8_t)term;
-            if (io.truncated) io.truncated[e] = (uint8_t)trunc;
-            st_rec256(p.rec + 2 * e, ra, rbw);
+            io.reward[ko + e] = lds_f32(s_rw32 + 4 * o.ridx);
+            io.done[ko + e] = (uint8_t)done;
+            if (io.terminated) io.terminated[ko + e] = (uint8_t)term;
+            if (io.truncated) io.truncated[ko + e] = (uint8_t)trunc;
+            if (!MULTI) st_rec256(p.rec + 2 * e, ra, rbw);   // (MULTI: the record stays in registers until the last step)
             }
             if (done) st_rec256(p.term_rec + 2 * e, ra, rbw);
         }
-        accumulate_stats(p, act && done, r, term, trunc, lane, (int)e);
+        accumulate_stats(p, act && done, r, term, trunc, lane, (int)e, (unsigned)k);
         TSTAMP(5);
 
         // ---- the POST-move window into registers (idle lanes read their stale column: harmless)
@@ -397,8 +438,15 @@ k_step_tile(const Params p, const StepIO io) {
         const int pr_new = dxm > 0 ? x1 + NTR : x1 + 1, pn_new = dxm > 0 ? x1 + 6 : x1;
         const uint32_t s_stage = s_win + tile_stage_off(D) + 32 * lane;
         if (newrow) {
-            cp_async16(s_stage, p.vis4 + e * VE + pn_new * VW);
-            cp_async8(s_stage + 16, p.types + e * TS + pr_new);
+            if (MULTI) {                                     // straight into the ring slots of the rows that left (resident rings)
+                cp_async8(s_t8 + 256 * (pr_new % NTR), p.types + e * TS + pr_new);
+                const uint32_t* vsrc = p.vis4 + e * VE + pn_new * VW;
+                const uint32_t sd = s_n4 + 512 * (pn_new % 7);
+                cp_async4(sd, vsrc); cp_async4(sd + 128, vsrc + 1); cp_async4(sd + 256, vsrc + 2); cp_async4(sd + 384, vsrc + 3);
+            } else {
+                cp_async16(s_stage, p.vis4 + e * VE + pn_new * VW);
+                cp_async8(s_stage + 16, p.types + e * TS + pr_new);
+            }
         }
         cp_async_commit();
 
@@ -470,8 +518,8 @@ k_step_tile(const Params p, const StepIO io) {
         }
         // the fetched rows of the rovers that changed rows go from the staging area into the cache rings,
         // replacing the rows that left the windows; then the tile's state is complete
-        cp_async_wait_all();
-        if (newrow) {
+        if (!MULTI) cp_async_wait_all();
+        if (!MULTI && newrow) {
             const uint4 nrow_new = lds_u128_v(s_stage);
             const uint64_t trow_new = lds_u64_v(s_stage + 16);
             *reinterpret_cast<uint64_t*>(g_tile + 256 * (pr_new % NTR) + 8 * lane) = trow_new;
@@ -480,7 +528,7 @@ k_step_tile(const Params p, const StepIO io) {
         }
         const unsigned dmask0 = __ballot_sync(FULL, act && done);
         __syncwarp();                                        // orders every lane's state stores before lane 0's release
-        if (dmask0 == 0u && lane == 0) {                     // the tile's state is complete: the next step may start
+        if (!MULTI && dmask0 == 0u && lane == 0) {           // the tile's state is complete: the next step may start
             if (p.release) st_release_u32(p.tile_flags + t, ordinal + 1u);
             else p.tile_flags[t] = ordinal + 1u;             // (nobody overlaps launches on this handle: the kernel end publishes it)
         }
@@ -489,7 +537,8 @@ k_step_tile(const Params p, const StepIO io) {
 
         // ---- expand: the whole warp, one float4 per lane and iteration, coalesced streaming stores
         {
-            float4* const dst = reinterpret_cast<float4*>(io.obs) + ((size_t)e0 * D >> 2) + lane;
+            float* const obs_k = io.obs + (size_t)k * io.obs_stride;
+            float4* const dst = reinterpret_cast<float4*>(obs_k) + ((size_t)e0 * D >> 2) + lane;
             const uint32_t s_cw = s_code + 4 * lane;
             if ((PLANTOS_TILE_SKIP & 2) && ts >= 0) {
             } else if (ts == 32) {
@@ -569,9 +618,17 @@ k_step_tile(const Params p, const StepIO io) {
             }
             const EnvRec nr = reset_env_warp(p, (int)ej, ep, plane, lane, keep != 0);
             build_obs_warp(p, tabs(), plane, vis_e, nr.x, nr.y, row_s, lane, keep != 0);
-            store_obs_row(row_s, io.obs + ej * D, D, lane);
+            store_obs_row(row_s, io.obs + (size_t)k * io.obs_stride + ej * D, D, lane);
             wrc_build_env_warp(p, ej, nr.x, lane);           // the new episode's rings
-            if (lane == 0) {
+            if (MULTI) {                                     // ... and into the resident copy; the lane's record restarts
+                __syncwarp();
+                const uint32_t* gsrc = reinterpret_cast<const uint32_t*>(g_tile);
+                for (int q = lane; q < 2 * NTR; q += 32)     // type planes: two words per slot and env
+                    sts_u32_v(s_win + 256 * (q >> 1) + 8 * j + 4 * (q & 1), __ldcg(gsrc + 64 * (q >> 1) + 2 * j + (q & 1)));
+                if (lane < 28) sts_u32_v(s_win + NTR * 256 + 128 * lane + 4 * j, __ldcg(gsrc + NTR * 64 + 32 * lane + j));
+                if (lane == j) r = nr;
+            }
+            if (!MULTI && lane == 0) {
                 uint4 qa, qb;
                 pack_rec(nr, qa, qb);
                 p.rec[2 * ej] = qa;
@@ -579,15 +636,41 @@ k_step_tile(const Params p, const StepIO io) {
             }
             __syncwarp();
         }
-        if (dmask0 != 0u && lane == 0) {                     // tiles with resets complete here
+        if (!MULTI && dmask0 != 0u && lane == 0) {           // tiles with resets complete here
             if (p.release) st_release_u32(p.tile_flags + t, ordinal + 1u);
             else p.tile_flags[t] = ordinal + 1u;
+        }
+        action = action_next;
+      }   // steps of the tile
+        if (MULTI) {
+            // the K steps of this tile are done: records and rings go back to global memory once
+            cp_async_wait_all();
+            if (act) {
+                pack_rec(r, ra, rbw);
+                st_rec256(p.rec + 2 * e, ra, rbw);
+            }
+            __syncwarp();
+            for (int q = lane; q < WRCB / 16; q += 32)
+                reinterpret_cast<uint4*>(g_tile)[q] = lds_u128_v(s_win + 16 * q);
+            __syncwarp();
+            if (lane == 0) {
+                if (p.release) st_release_u32(p.tile_flags + t, ordinal + 1u);
+                else p.tile_flags[t] = ordinal + 1u;
+            }
+            __syncwarp();
         }
     }
 
     // ragged tail: envs beyond the last 4-env group, one at a time (they are never part of a tile)
     if (blockIdx.x == gridDim.x - 1 && warp == kTileWarps - 1)
-        for (int e = nfull; e < p.N; ++e) step_env_warp(p, tabs(), io, e, plane, row_s, lane);
+        for (int k = 0; k < K; ++k) {
+            StepIO sio;
+            const size_t ko = (size_t)k * (size_t)p.N;
+            sio.actions = io.actions + ko; sio.obs = io.obs + (size_t)k * io.obs_stride; sio.reward = io.reward + ko;
+            sio.done = io.done + ko; sio.terminated = io.terminated ? io.terminated + ko : nullptr;
+            sio.truncated = io.truncated ? io.truncated + ko : nullptr; sio.terminal_obs = io.terminal_obs;
+            for (int e = nfull; e < p.N; ++e) step_env_warp(p, tabs(), sio, e, plane, row_s, lane);
+        }
 }
 
 }  // namespace plantos_dev

@@ -318,6 +318,40 @@ class PlantOSVecEnv:
         all K steps are resident before the launch, every step writes its own observation buffer)."""
         return GraphRollout(self, k, with_flags, pipelined)
 
+    def step_many(self, actions, with_flags: bool = False):
+        """K open-loop steps in ONE call (plantos_rollout): `actions` int64 [K, N] -> obs [K, N, D],
+        rewards [K, N], dones [K, N] (+ terminated, truncated [K, N] with `with_flags`); the tensors
+        are reused by the next call with the same K.  Bit-identical to K `step` calls, auto-resets
+        included.  On the fast presets the K steps are one launch of the state-resident kernel (the
+        envs' window rings and records never leave the SM between steps) -- the GPU form of the
+        reference's MCTS rollout loop (mcts_custom_trainer.py:139-166)."""
+        if not isinstance(actions, torch.Tensor):
+            actions = torch.as_tensor(np.asarray(actions), dtype=torch.int64)
+        actions = actions.to(device=self.device, dtype=torch.int64, non_blocking=True).contiguous()
+        if actions.dim() != 2 or actions.shape[1] != self.num_envs:
+            raise ValueError(f"expected actions of shape [K, {self.num_envs}], got {tuple(actions.shape)}")
+        k, n, d, dev = int(actions.shape[0]), self.num_envs, self.obs_dim, self.device
+        buf = getattr(self, "_many", None)
+        if buf is None or buf["k"] != k:
+            stride = (n * d + 3) // 4 * 4                  # per-step stride padded to 16 bytes
+            buf = {"k": k, "stride": stride,
+                   "obs": torch.empty(k * stride, dtype=torch.float32, device=dev),
+                   "rew": torch.empty((k, n), dtype=torch.float32, device=dev),
+                   "done": torch.zeros((k, n), dtype=torch.bool, device=dev),
+                   "term": torch.zeros((k, n), dtype=torch.bool, device=dev),
+                   "trunc": torch.zeros((k, n), dtype=torch.bool, device=dev)}
+            self._many = buf
+        tobs = self._terminal_obs.data_ptr() if self._terminal_obs is not None else None
+        nat.check(self._lib.plantos_rollout(
+            self._h, k, actions.data_ptr(), buf["obs"].data_ptr(), buf["stride"], buf["rew"].data_ptr(),
+            buf["done"].data_ptr(), buf["term"].data_ptr() if with_flags else None,
+            buf["trunc"].data_ptr() if with_flags else None, tobs, self._stream()))
+        self._actions = actions                            # keep alive until the launch has consumed it
+        obs = buf["obs"].as_strided((k, n, d), (buf["stride"], d, 1))
+        if with_flags:
+            return obs, buf["rew"], buf["done"], buf["term"], buf["trunc"]
+        return obs, buf["rew"], buf["done"]
+
     def set_pipelining(self, enable: bool) -> None:
         """Let back-to-back `step_async` calls overlap on the device (open-loop stepping only: the
         actions of a step must not be computed from the previous step's results, and `obs_ring >= 2`

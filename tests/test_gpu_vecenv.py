@@ -171,6 +171,43 @@ def test_graph_rollout_equals_single_steps(n, kernel, pipelined):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("n,kernel,preset,cur", [(4096, "fast", "training", None), (1027, "fast", "training", None),
+                                                 (2048, "fast", "default", None), (96, "fast", "training", "a2c"),
+                                                 (200, "generic", "training", None)])
+def test_step_many_equals_single_steps(n, kernel, preset, cur):
+    """plantos_rollout / env.step_many: K steps in one call (one launch of the state-resident multi-step
+    kernel on the fast presets) give exactly what K single steps give -- observations, rewards, flags,
+    terminal observations, episode statistics and the full state afterwards -- with auto-resets inside the
+    rollouts, a ragged tail (1027), the curriculum wrapper, and single steps mixed in between."""
+    import torch
+    from rl_env_b200 import PlantOSVecEnv, PRESETS
+    kw = dict(PRESETS[preset], max_steps=23, seed=21, kernel=kernel, full_infos=False, curriculum=cur)
+    a, b = PlantOSVecEnv(n, **kw), PlantOSVecEnv(n, **kw)
+    assert torch.equal(a.reset(), b.reset())
+    g = torch.Generator(device="cuda"); g.manual_seed(8)
+    for rep, K in enumerate((7, 1, 16, 5, 16, 16)):
+        acts = torch.randint(0, 5, (K, n), device="cuda", generator=g)
+        obs_k, rew_k, done_k, term_k, trunc_k = b.step_many(acts, with_flags=True)
+        for t in range(K):
+            obs, rew, done, _ = a.step(acts[t])
+            assert torch.equal(obs, obs_k[t]), (rep, t)
+            assert torch.equal(rew, rew_k[t]) and torch.equal(done, done_k[t]), (rep, t)
+            assert torch.equal(a.terminated, term_k[t]) and torch.equal(a.truncated, trunc_k[t]), (rep, t)
+        assert torch.equal(a.terminal_observation, b.terminal_observation)
+        if rep == 2:                                       # single steps between rollouts
+            x = torch.randint(0, 5, (n,), device="cuda", generator=g)
+            oa, ra, da, _ = a.step(x)
+            ob, rb, db, _ = b.step(x)
+            assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)
+    if kernel == "fast":
+        assert b.last_step_kernel == "k_rollout_tile"
+    sa, sb = a.get_state(), b.get_state()
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    assert a.episode_stats() == b.episode_stats()
+    a.check(); b.check()
+    a.close(); b.close()
+
+
 def test_pipelined_eager_steps_equal_plain_steps():
     """plantos_set_pipelining on eager launches: back-to-back step_async calls into an observation ring
     overlap on the device (per-tile counters order them) and give exactly the plain results; every
