@@ -4,10 +4,19 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one VecEnv.step over all envs (one fused kernel launch per GPU: transition +
-LIDAR observation + auto-reset).  Workload (BASELINE.json configs[3], the one the metric is
-quoted on): training preset G25/P10/O12/R6/C16 (D=107), 131 072 envs per GPU -- 1 048 576
-envs on 8 GPUs -- weak scaling, Philox maps, i.i.d. uniform actions.
+One "step" = one VecEnv.step over all envs (transition + LIDAR observation + auto-reset, fused).
+Workload (BASELINE.json configs[3], the one the metric is quoted on): training preset
+G25/P10/O12/R6/C16 (D=107), 131 072 envs per GPU -- 1 048 576 envs on 8 GPUs -- weak scaling,
+Philox maps, i.i.d. uniform actions; the envs start at staggered episode phases
+(step_count = hash(env id) mod max_steps), so about N / 1000 envs truncate and are regenerated in EVERY
+step of the timed region.
+
+Timed loop (`--loop`): `rollout` (default) = env.step_many, 16 steps per plantos_rollout call with
+pre-generated actions: every step reads its own action vector and writes its own observation / reward /
+done buffers, the K steps of a call are one launch of the state-resident kernel; `graph` = a replayed
+CUDA graph of 16 single-step plantos_step launches (round 1's loop; consecutive launches pipelined on
+the device unless --no-pipeline); `eager` = one plantos_step call per step.  The line always carries
+the single-launch-per-step numbers next to the headline (`step_launch`).
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events, max over
 ranks); `e2e` = the same metric through plantos_step_host with pinned HOST buffers (H2D
@@ -34,7 +43,8 @@ ENVS_PER_GPU = 131072
 PRESET = dict(grid_size=25, num_plants=10, num_obstacles=12, lidar_range=6, lidar_channels=16)
 OBS_DIM = 5 * PRESET["lidar_channels"] + 27
 B_ALG = 4 * OBS_DIM + 4 + 1 + 8          # obs f32[D] + reward f32 + done u8 + action i64
-ACTION_RING = 16
+ACTION_RING = 16                          # steps per rollout call / per replayed graph
+ACTION_POOL = 4                           # distinct [16, N] action blocks the timed loop cycles through (64 i.i.d. vectors)
 OBS_RING = 5                              # rollout-buffer depth (A2C n_steps=5, A2C_training.py:229-247)
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
@@ -42,7 +52,7 @@ UNIT = "env-steps/s"
 
 def workload_name(n_gpus: int) -> str:
     return (f"PlantOS training preset G25/P10/O12/R6/C16 (D=107), {ENVS_PER_GPU} envs/GPU x {n_gpus} GPU "
-            f"= {ENVS_PER_GPU * n_gpus} envs, fused step+LIDAR obs+auto-reset, random actions")
+            f"= {ENVS_PER_GPU * n_gpus} envs, fused step+LIDAR obs+auto-reset, random actions, staggered episode phases")
 
 
 def measured_peak_gbs():
@@ -53,17 +63,18 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def measured_traffic(envs_per_gpu: int, kernel_name: str):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture; only valid
-    for the workload it was captured on (131 072 envs, fast kernel), else null."""
+def measured_traffic(envs_per_gpu: int, kernel: str):
+    """Steady-state DRAM bytes per STEP of the dominant kernel from the committed ncu capture
+    (profiles/r2_traffic.json: application replay, no cache flush); only valid for the workload and
+    kernel it was captured on, else null."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             t = json.load(f)
-        if envs_per_gpu == ENVS_PER_GPU and kernel_name == "fast":
-            return int(t["dram_bytes_per_launch"])
+        if envs_per_gpu == int(t.get("envs", 0)) and kernel in t.get("kernels", {}):
+            return int(t["kernels"][kernel]["dram_bytes_per_step"]), t["kernels"][kernel].get("source", "")
     except Exception:
         pass
-    return None
+    return None, ""
 
 
 # ------------------------------------------------------------------ CPU baseline (oracle port)
@@ -125,11 +136,11 @@ class CpuPool:
 
 
 def cpu_baseline(seconds: float = 12.0):
-    pool = CpuPool(envs_per_worker=8)
+    pool = CpuPool(envs_per_worker=REF_ENVS_PER_WORKER)
     pool.run(20)  # warm-up
     t0 = time.perf_counter()
     steps = 0
-    chunk = 100
+    chunk = 10
     while time.perf_counter() - t0 < seconds:
         steps += pool.run(chunk)
     dt = time.perf_counter() - t0
@@ -137,36 +148,34 @@ def cpu_baseline(seconds: float = 12.0):
     n_envs = pool.num_envs
     pool.close()
     return {"value": steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{steps} env-steps in {dt:.1f} s: {n_envs} envs (8 per process, {cores} processes, "
+            "sample": f"{steps} env-steps in {dt:.1f} s: {n_envs} envs ({REF_ENVS_PER_WORKER} per process, {cores} processes, "
                       f"no IPC on the step path) of the same preset, oracle/plantos_oracle.py"}
 
 
+REF_ENVS_PER_WORKER = 64      # fixed sample: 64 envs per host core
+REF_SECONDS = 10.0            # CPU time the K timed steps of the reference arm add up to
+
+
 def run_reference(args, rank: int):
-    """`--impl reference`: the reference's CPU implementation (oracle port) on all host cores."""
+    """`--impl reference`: the reference's CPU implementation (oracle port) on all host cores.  The
+    sample is FIXED (64 envs per core); one bench "step" = `reps` VecEnv steps over it, with reps
+    calibrated so that the K timed steps take about REF_SECONDS (short timings were +-40 % noisy)."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    # calibrate, then size the per-step sample so the K timed steps are ~20 s of CPU work
-    # (at least 8 envs per core) and bound the whole run to ~90 s
-    pool = CpuPool(envs_per_worker=8, workers=cores)
-    pool.run(5)
-    t0 = time.perf_counter()
-    done = pool.run(25)
-    rate = done / (time.perf_counter() - t0)
-    pool.close()
-    per_worker = int(min(256, max(8, rate * 20 / (max(1, args.steps) * cores))))
-    pool = CpuPool(envs_per_worker=per_worker, workers=cores)
+    pool = CpuPool(envs_per_worker=REF_ENVS_PER_WORKER, workers=cores)
     n_envs = pool.num_envs
-    budget_steps = max(1, int(rate * 90 / n_envs))
-    total = args.steps + args.warmup
-    reps = 1
-    steps, warmup = args.steps, args.warmup
-    if total > budget_steps:  # each bench "step" = one VecEnv step of the sample; cap their number
-        scale = budget_steps / total
-        steps, warmup = max(1, int(args.steps * scale)), max(1, int(args.warmup * scale))
-    pool.run(warmup)
+    pool.run(3)                                   # warm the interpreters
     t0 = time.perf_counter()
-    n = pool.run(steps * reps)
+    done = pool.run(10)
+    rate = done / (time.perf_counter() - t0)      # env-steps/s, calibration only
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    reps = max(1, int(round(REF_SECONDS * rate / (steps * n_envs))))
+    pool.run(min(warmup * reps, max(1, int(2.0 * rate / n_envs))))      # W warm-up steps, at most ~2 s
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(steps):
+        n += pool.run(reps)
     dt = time.perf_counter() - t0
     pool.close()
     value = n / dt
@@ -174,11 +183,12 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "python float64 / int", "data": "synthetic",
-        "config": {"workload": workload_name(args.gpus), "sample_envs": n_envs,
-                   "note": "CPU port of plantos_env.py (oracle/plantos_oracle.py), one process per host core; "
-                           "each step is one VecEnv step over the sample"},
+        "config": {"workload": workload_name(args.gpus), "sample_envs": n_envs, "vec_steps_per_bench_step": reps,
+                   "note": "CPU port of plantos_env.py (oracle/plantos_oracle.py), one process per host core, no IPC "
+                           "on the step path; each bench step is `vec_steps_per_bench_step` VecEnv steps over the "
+                           "fixed sample (64 envs per core)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n} env-steps in {dt:.1f} s over {n_envs} envs"},
+                         "sample": f"{n} env-steps in {dt:.1f} s over {n_envs} envs ({REF_ENVS_PER_WORKER} per core)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -259,8 +269,17 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        obs_ring=OBS_RING, track_terminal_obs=not args.no_terminal_obs, full_infos=False, **PRESET)
     assert env.num_envs == n and env.obs_dim == OBS_DIM
     gen = torch.Generator(device=dev).manual_seed(rank)
-    actions = [torch.randint(0, 5, (n,), device=dev, dtype=torch.int64, generator=gen) for _ in range(ACTION_RING)]
+    # ACTION_POOL blocks of ACTION_RING i.i.d. action vectors (the timed loop cycles through the blocks)
+    pool = [torch.randint(0, 5, (ACTION_RING, n), device=dev, dtype=torch.int64, generator=gen) for _ in range(ACTION_POOL)]
     env.reset()
+    # staggered episode phases: env i starts with step_count = global id mod max_steps, so ~N / max_steps
+    # envs hit the 1000-step truncation (terminal observation, Philox map, fresh observation) in EVERY step
+    if not args.no_stagger:
+        # (a multiplicative hash of the global env id: neighbouring envs must not truncate in neighbouring
+        # steps, or the 32 envs of one tile would reset 32 steps in a row)
+        gid = torch.arange(n, device=dev, dtype=torch.int64) + env.env_id_base
+        phase = ((gid * 2654435761) % 4294967296) % env.max_steps
+        env.set_state(scalars={"step_count": phase.to(torch.int32)})
     torch.cuda.synchronize()
 
     def barrier():
@@ -268,32 +287,42 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # The timed loop replays a CUDA graph of ACTION_RING single-step launches (PlantOSVecEnv.make_rollout:
-    # the same plantos_step calls, captured once; every step still reads its actions and writes its own
-    # observation / reward / done / terminal buffers) and steps the remainder eagerly; --no-graph steps
-    # eagerly throughout.
-    roll = None
     pipelined = not args.no_pipeline
-    env.set_pipelining(pipelined)          # eager steps too (the obs ring gives every step its own buffer)
-    if not args.no_graph:
+    loop = args.loop
+    roll = None
+    if loop != "rollout":
+        env.set_pipelining(pipelined)      # eager steps too (the obs ring gives every step its own buffer)
+    if loop == "graph":
         roll = env.make_rollout(ACTION_RING, with_flags=True, pipelined=pipelined)
-        roll.actions.copy_(torch.stack(actions))
 
-    def maybe_stats(i):
-        if world > 1 and args.stats_every and (i + 1) % args.stats_every < (ACTION_RING if roll else 1) and i + 1 >= args.stats_every:
-            env.episode_stats_tensor(all_reduce=True)   # NCCL all-reduce of 8 doubles, no host sync
+    # the optional NCCL all-reduce of the 8 episode statistics lands INSIDE the timed window whatever K is
+    stats_every = 0
+    if world > 1 and args.stats_every:
+        stats_every = max(ACTION_RING, min(args.stats_every, max(1, args.steps // 2)) // ACTION_RING * ACTION_RING)
+    counters = {"stats": 0, "launches": 0}
 
     def run_steps(k, start):
+        """k consecutive steps, numbered from `start` (the block of actions follows the step number)."""
         i, end = start, start + k
         while i < end:
-            if roll is not None and end - i >= ACTION_RING:
+            blk, off = pool[(i // ACTION_RING) % ACTION_POOL], i % ACTION_RING
+            m = min(ACTION_RING - off, end - i)
+            if loop == "rollout":
+                env.step_many(blk[off:off + m], with_flags=True)   # ONE plantos_rollout call: m steps
+                counters["launches"] += 1
+            elif loop == "graph" and m == ACTION_RING:
+                roll.actions.copy_(blk, non_blocking=True)           # (1 MB device copy per 16 steps, inside the timed region)
                 roll.graph.replay()
-                i += ACTION_RING
+                counters["launches"] += ACTION_RING
             else:
-                env.step_async(actions[i % ACTION_RING])
-                env.step_wait()
-                i += 1
-            maybe_stats(i - 1)
+                for t in range(off, off + m):
+                    env.step_async(blk[t])
+                    env.step_wait()
+                counters["launches"] += m
+            i += m
+            if stats_every and i % stats_every < m and i >= stats_every:
+                env.episode_stats_tensor(all_reduce=True)   # NCCL all-reduce of 8 doubles, no host sync
+                counters["stats"] += 1
 
     # untimed extra steps before the W warm-up steps: first launches, graph instantiation and the
     # first NCCL collective on every rank (a cold rank once made a whole 4-GPU run 30 % slower)
@@ -301,38 +330,63 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         env.episode_stats_tensor(all_reduce=True)
     barrier()
-    run_steps(args.warmup, 0)
+    run_steps(args.warmup, 2 * ACTION_RING)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.sample()
     sampler.start()
-    launches0 = env.launch_count
+    counters["stats"] = counters["launches"] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    run_steps(args.steps, args.warmup)
+    run_steps(args.steps, 2 * ACTION_RING + args.warmup)
     e1.record()
     barrier()
     sampler.stop()
     ms = e0.elapsed_time(e1)
-    launches = (env.launch_count - launches0) if roll is None else args.steps   # graph replays launch the same kernels
+    launches, stats_in_window = counters["launches"], counters["stats"]
+    kernel_of_loop = env.last_step_kernel
     env.check()
 
-    # isolated duration of the step kernel: event pair around single launches
-    iso = []
-    for i in range(min(200, max(20, args.steps))):
+    def timed(fn, reps):
+        fn(); fn()
+        torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        env.step_async(actions[i % ACTION_RING])
+        for _ in range(reps):
+            fn()
         b.record()
-        env.step_wait()
-        iso.append((a, b))
-    torch.cuda.synchronize()
-    iso_us = sorted(a.elapsed_time(b) * 1e3 for a, b in iso)
-    iso_med_us = iso_us[len(iso_us) // 2]
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e3 / reps
 
-    # end to end through the host-buffer entry point (plantos_step_host)
-    import numpy as np
-    host_actions = [a.cpu().numpy() for a in actions[:4]]
+    # the single-launch-per-step numbers, always reported next to the headline: (a) one launch alone between
+    # two events (isolated duration), (b) 16-step graphs of plantos_step launches, pipelined and with a
+    # grid-wide dependency between consecutive launches
+    step_launch = {}
+    if not args.no_step_launch:
+        env.set_pipelining(False)
+        iso = []
+        for i in range(64):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            env.step_async(pool[0][i % ACTION_RING])
+            b.record()
+            env.step_wait()
+            iso.append((a, b))
+        torch.cuda.synchronize()
+        iso_us = sorted(a.elapsed_time(b) * 1e3 for a, b in iso)
+        step_launch["isolated_launch_us_median"] = iso_us[len(iso_us) // 2]
+        for label, pl in (("graph16_pipelined_us_per_step", True), ("graph16_plain_us_per_step", False)):
+            g = env.make_rollout(ACTION_RING, with_flags=True, pipelined=pl)
+            g.actions.copy_(pool[1])
+            step_launch[label] = timed(g.graph.replay, 12) / ACTION_RING
+            del g
+        step_launch["kernel"] = env.last_step_kernel
+        step_launch["frac_pipelined"] = n * B_ALG / step_launch["graph16_pipelined_us_per_step"] / 1e3 / measured_peak_gbs()[0]
+        step_launch["frac_plain"] = n * B_ALG / step_launch["graph16_plain_us_per_step"] / 1e3 / measured_peak_gbs()[0]
+
+    # end to end through the host-buffer entry point (plantos_step_host): numpy in / numpy out, pinned host
+    # buffers, H2D actions + D2H obs / reward / done inside the timed region, one call per step
+    host_actions = [pool[0][i].cpu().numpy() for i in range(4)]
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
     for i in range(3):
         env.step_host(host_actions[i % 4])
@@ -345,11 +399,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     stats = env.episode_stats_tensor(all_reduce=True).cpu().tolist()
     t_ms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    per_rank_ms = [ms]
+    per_rank_ms, per_rank_e2e = [ms], [e2e_s * 1e3]
     if world > 1:
         gathered = [torch.zeros_like(t_ms) for _ in range(world)]
         dist.all_gather(gathered, t_ms)
         per_rank_ms = [float(g[0]) for g in gathered]     # the timed region of every rank (value uses the max)
+        per_rank_e2e = [float(g[1]) for g in gathered]
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms, e2e_ms = t_ms.tolist()
     kernel_name = env.kernel_name
@@ -362,29 +417,41 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         peak, peak_src = measured_peak_gbs()
         step_s = ms * 1e-3 / args.steps
         achieved = n * B_ALG / step_s / 1e9
+        traffic, traffic_src = measured_traffic(n, kernel_of_loop)
+        launch_desc = {
+            "rollout": "env.step_many: %d steps per plantos_rollout call (one launch of the state-resident kernel %s per call; "
+                       "every step reads its own action vector and writes its own obs/reward/done buffers)" % (ACTION_RING, kernel_of_loop),
+            "graph": "CUDA graph of %d single-step plantos_step launches, replayed" % ACTION_RING
+                     + ("; consecutive launches pipelined on the device (plantos_set_pipelining)" if pipelined else ""),
+            "eager": "eager, one plantos_step launch per step" + ("; pipelined (plantos_set_pipelining)" if pipelined else ""),
+        }[loop]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "int (2-bit cells, 4-bit/u16 visit counts) + f32 table-driven obs/reward", "data": "synthetic",
             "config": {"workload": workload_name(world), "envs_per_gpu": n, "obs_dim": OBS_DIM,
-                       "kernel": kernel_name, "maps": "philox seed 0", "state_bytes_per_env": state_bytes,
-                       "l2": f"inputs larger than L2: per-GPU state {n * state_bytes / 1e6:.0f} MB + obs ring "
-                             f"{ACTION_RING if roll is not None else OBS_RING}x{n * OBS_DIM * 4 / 1e6:.0f} MB vs 126 MB L2; no explicit flush",
-                       "launch": (("CUDA graph of %d single-step launches, replayed" % ACTION_RING) if roll is not None else "eager, one launch per step")
-                                 + ("; consecutive steps pipelined on the device (plantos_set_pipelining: per-tile step counters instead of a "
-                                    "grid-wide dependency, every step still one launch with its own actions and outputs)" if pipelined else ""),
-                       "stats_allreduce_every": args.stats_every if world > 1 else 0},
+                       "kernel": kernel_name, "loop_kernel": kernel_of_loop, "maps": "philox seed 0", "state_bytes_per_env": state_bytes,
+                       "actions": f"{ACTION_POOL * ACTION_RING} pre-generated i.i.d. uniform vectors, cycled",
+                       "episode_phases": "all envs start at step 0" if args.no_stagger else "staggered: step_count = hash(env id) mod 1000 (about N/1000 auto-resets in every step)",
+                       "l2": f"outputs larger than L2: {ACTION_RING if loop != 'eager' else OBS_RING} observation buffers x {n * OBS_DIM * 4 / 1e6:.0f} MB "
+                             f"written round-robin vs 126 MB L2 (per-GPU state {n * state_bytes / 1e6:.0f} MB); no explicit flush",
+                       "launch": launch_desc,
+                       "stats_allreduce_every": stats_every, "stats_allreduces_in_timed_window": stats_in_window},
             "e2e": {"value": total_envs * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * (4 * OBS_DIM + 4 + 1),
-                    "steps": e2e_steps, "api": "plantos_step_host (pinned host buffers), per GPU"},
+                    "steps": e2e_steps, "api": "plantos_step_host (pinned host buffers), one call per step and GPU; bytes are per GPU, "
+                                               "value is the aggregate over all GPUs (max over ranks of the wall time)",
+                    "ms_per_step_by_rank": [round(m / e2e_steps, 4) for m in per_rank_e2e]},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic(n, kernel_name),
-                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1_traffic.json)",
-                         "peak_source": peak_src,
-                         "alg_bytes_per_env_step": B_ALG, "kernel": f"k_step_{kernel_name}",
-                         "avg_launch_us": step_s * 1e6, "isolated_launch_us_median": iso_med_us},
+                         "frac": achieved / peak, "traffic": traffic,
+                         "traffic_unit": "steady-state DRAM bytes per step (ncu dram read+write, " + traffic_src + ")" if traffic else None,
+                         "peak_source": peak_src, "basis": "algorithmic bytes (obs + reward + done + action = 441 B per env-step)",
+                         "alg_bytes_per_env_step": B_ALG, "kernel": kernel_of_loop,
+                         "steps_per_launch": ACTION_RING if loop == "rollout" else 1,
+                         "avg_launch_us": step_s * 1e6 * (ACTION_RING if loop == "rollout" else 1)},
+            "step_launch": step_launch,
             "clocks": sampler.summary(),
             "ms_per_step_by_rank": [round(m / args.steps, 6) for m in per_rank_ms],
             "episode_stats": dict(zip(("episodes", "return_sum", "length_sum", "exploration_pct_sum",
@@ -403,9 +470,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
 
 def main():
-    # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # (NCCL_DEBUG is left as the caller set it: run_ours moves fd 1 to stderr while libraries may print)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3000)
@@ -418,10 +483,16 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-terminal-obs", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="step eagerly instead of replaying a CUDA graph of 16 steps")
-    ap.add_argument("--no-pipeline", action="store_true", help="full grid-wide dependency between consecutive step launches")
+    ap.add_argument("--loop", default="rollout", choices=["rollout", "graph", "eager"],
+                    help="timed loop: step_many (16 steps per rollout launch), replayed graph of 16 step launches, or eager steps")
+    ap.add_argument("--no-graph", action="store_true", help="same as --loop eager")
+    ap.add_argument("--no-pipeline", action="store_true", help="full grid-wide dependency between consecutive step launches (graph / eager loops)")
+    ap.add_argument("--no-stagger", action="store_true", help="all envs start at step 0 (no auto-reset before step 1000)")
+    ap.add_argument("--no-step-launch", action="store_true", help="skip the single-launch-per-step side measurements")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
+    if args.no_graph:
+        args.loop = "eager"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -120,34 +120,45 @@ __device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int epi
                 }
         }
         __syncwarp();
-        if (lane == 0) {
-            // plants: uniform sample without replacement from the free cells (:366) by
-            // rejection, thirsty with probability thirsty_plant_prob (:368)
-            uint32_t j = 0;
+        // plants: uniform sample without replacement from the free cells (:366) by rejection, thirsty with
+        // probability thirsty_plant_prob (:368).  Draw j of stream 1 is candidate j; candidates are taken in
+        // draw order while their cell is free.  32 candidates are drawn at once (one Philox block per lane):
+        // a candidate is taken iff its cell is empty in the map so far and no EARLIER candidate of the batch
+        // names the same cell (that one took it, or found it occupied) -- exactly the sequential rule.
+        {
             const uint32_t ncell = (uint32_t)(G * G);
-            for (int placed = 0; placed < p.P && j < (1u << 20); ++j) {
+            int placed = 0;
+            for (uint32_t j0 = 0; placed < p.P && j0 < (1u << 20); j0 += 32) {
                 uint32_t d[4];
-                map_draw(p, genv, episode, 1, j, d);
+                map_draw(p, genv, episode, 1, j0 + (uint32_t)lane, d);
                 const int cell = (int)bounded(d[0], ncell);
                 const int cx = cell / G, cy = cell - cx * G;
-                uint64_t& word = plane[cx * W + (cy >> 5)];
-                if (cell_of(word, cy & 31) == kEmpty) {
+                const bool empty = cell_of(plane[cx * W + (cy >> 5)], cy & 31) == kEmpty;
+                const unsigned same = __match_any_sync(0xffffffffu, cell);
+                const bool cand = empty && (same & ((1u << lane) - 1u)) == 0u;
+                const unsigned cmask = __ballot_sync(0xffffffffu, cand);
+                if (cand && placed + __popc(cmask & ((1u << lane) - 1u)) < p.P) {
                     const uint64_t code = ((unsigned long long)d[1] < p.thirsty_thresh) ? kThirsty : kHydrated;
-                    word |= code << (2 * (cy & 31));
-                    ++placed;
+                    atomicOr(reinterpret_cast<unsigned long long*>(&plane[cx * W + (cy >> 5)]), code << (2 * (cy & 31)));
+                }
+                placed = min(p.P, placed + __popc(cmask));
+                __syncwarp();
+            }
+            // rover: uniform over free cells that hold no plant (:372): the first candidate of stream 2 on an empty cell
+            for (uint32_t j0 = 0; j0 < (1u << 20); j0 += 32) {
+                uint32_t d[4];
+                map_draw(p, genv, episode, 2, j0 + (uint32_t)lane, d);
+                const int cell = (int)bounded(d[0], ncell);
+                const int cx = cell / G, cy = cell - cx * G;
+                const unsigned emask = __ballot_sync(0xffffffffu, cell_of(plane[cx * W + (cy >> 5)], cy & 31) == kEmpty);
+                if (emask) {
+                    const int src = __ffs(emask) - 1;
+                    rx = __shfl_sync(0xffffffffu, cx, src);
+                    ry = __shfl_sync(0xffffffffu, cy, src);
+                    break;
                 }
             }
-            // rover: uniform over free cells that hold no plant (:372)
-            for (j = 0; j < (1u << 20); ++j) {
-                uint32_t d[4];
-                map_draw(p, genv, episode, 2, j, d);
-                const int cell = (int)bounded(d[0], ncell);
-                const int cx = cell / G, cy = cell - cx * G;
-                if (cell_of(plane[cx * W + (cy >> 5)], cy & 31) == kEmpty) { rx = cx; ry = cy; break; }
-            }
         }
-        rx = __shfl_sync(0xffffffffu, rx, 0);
-        ry = __shfl_sync(0xffffffffu, ry, 0);
         __syncwarp();
     }
     // counts + write-out of the G grid rows (the wall rows above/below were set at create)
@@ -205,6 +216,42 @@ __device__ __forceinline__ void wrc_build_env_warp(const Params& p, size_t e, in
     if (lane < 28) {                                      // padded nibble rows x .. x+6, four words each (VW == 4)
         const int pn = x + (lane >> 2), w = lane & 3;
         reinterpret_cast<uint32_t*>(tile + ntr * 256)[((pn % 7) * 4 + w) * 32 + j] = p.vis4[e * p.VE + pn * 4 + w];
+    }
+}
+
+// The same entry right after reset_env_warp, without reading the planes back: the type rows come from the
+// shared-memory `plane` the reset has just built (grid rows; every padded row outside the grid is a wall
+// row), the nibble rows are the fresh ones (0, rover cell 1, border 15) unless the visit counts were kept
+// (curriculum), in which case they are read from the plane in global memory.  `s_ring` != 0: also store the
+// entry into the caller's resident copy of the tile's rings (shared-memory byte address of the tile image).
+__device__ __forceinline__ void wrc_build_env_fresh_warp(const Params& p, size_t e, int x, int y, const uint64_t* plane,
+                                                         bool keep_visits, int lane, uint32_t s_ring) {
+    if (!p.wrc) return;
+    const int ntr = wrc_type_slots(p.R), G = p.G;
+    unsigned char* tile = p.wrc + (e >> 5) * (size_t)wrc_tile_bytes(p.R);
+    const int j = (int)(e & 31);
+    for (int i = lane; i < ntr; i += 32) {                // padded type rows x+1 .. x+ntr; grid row = padded row - TP
+        const int pr = x + 1 + i, g = pr - p.TP;
+        const uint64_t row = ((unsigned)g < (unsigned)G) ? plane[g] : kObstAll;
+        reinterpret_cast<uint64_t*>(tile)[(pr % ntr) * 32 + j] = row;
+        if (s_ring) asm volatile("st.shared.u64 [%0], %1;" :: "r"(s_ring + 256 * (pr % ntr) + 8 * j), "l"(row) : "memory");
+    }
+    if (lane < 28) {                                      // padded nibble rows x .. x+6; grid row = padded row - 3
+        const int pn = x + (lane >> 2), w = lane & 3, vx = pn - kVisRowPad, c0 = w * 8 - 2;
+        uint32_t word = 0;
+        if (keep_visits) word = p.vis4[e * p.VE + pn * 4 + w];
+        else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int vy = c0 + k;
+                uint32_t v = 15u;
+                if ((unsigned)vx < (unsigned)G && (unsigned)vy < (unsigned)G) v = (vx == x && vy == y) ? 1u : 0u;
+                word |= v << (4 * k);
+            }
+        }
+        const int pl = (pn % 7) * 4 + w;
+        reinterpret_cast<uint32_t*>(tile + ntr * 256)[pl * 32 + j] = word;
+        if (s_ring) asm volatile("st.shared.u32 [%0], %1;" :: "r"(s_ring + ntr * 256 + 128 * pl + 4 * j), "r"(word) : "memory");
     }
 }
 

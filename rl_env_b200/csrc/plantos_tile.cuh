@@ -594,45 +594,46 @@ k_tile(const Params p, const RollIO io) {
             }
 #endif
 
-        // ---- auto-reset of finished envs (rare; warp-cooperative generic code in the same buffer)
+        // ---- auto-reset of finished envs (SB3 semantics; rare).  The observation just expanded IS the
+        // terminal observation: it is expanded once more, straight out of the code image, into
+        // terminal_obs (all finished envs first: the resets below reuse the image as their scratch).
         unsigned dmask = dmask0;
+        if (io.terminal_obs) {
+            while (dmask) {
+                const int j = __ffs(dmask) - 1;
+                dmask &= dmask - 1;
+                float* const trow = io.terminal_obs + ((size_t)e0 + j) * D;
+                for (int idx = lane; idx < D; idx += 32) {
+                    const uint32_t a = s_code + D * j + idx;
+                    const uint32_t byte = (lds_u32_v(a & ~3u) >> (8 * (a & 3u))) & 0xffu;
+                    trow[idx] = lds_f32(s_lut + byte);
+                }
+            }
+            __syncwarp();
+            dmask = dmask0;
+        }
         while (dmask) {
             const int j = __ffs(dmask) - 1;
             dmask &= dmask - 1;
             const size_t ej = (size_t)e0 + j;
             const int ep = __shfl_sync(FULL, episode, j);
-            const int px = __shfl_sync(FULL, x1, j), py = __shfl_sync(FULL, y1, j);
-            const uint64_t* types_e = p.types + ej * TS + TP;
-            const uint32_t* vis_e = p.vis4 + ej * VE;
-            if (io.terminal_obs) {
-                for (int idx = lane; idx < G; idx += 32) plane[idx] = types_e[idx];
-                __syncwarp();
-                build_obs_warp(p, tabs(), plane, vis_e, px, py, row_s, lane);
-                store_obs_row(row_s, io.terminal_obs + ej * D, D, lane);
-                __syncwarp();
-            }
             int keep = 0;
             if (p.cur_mode) {                                // CurriculumWrapper.reset
                 if (lane == 0) keep = curriculum_on_reset(p, (int)ej) ? 1 : 0;
                 keep = __shfl_sync(FULL, keep, 0);
             }
             const EnvRec nr = reset_env_warp(p, (int)ej, ep, plane, lane, keep != 0);
-            build_obs_warp(p, tabs(), plane, vis_e, nr.x, nr.y, row_s, lane, keep != 0);
+            // (fresh visit window: what the planes hold after a plain reset, and what the wrapper's reset
+            // observation shows when the counts are kept)
+            build_obs_warp(p, tabs(), plane, p.vis4 + ej * VE, nr.x, nr.y, row_s, lane, true);
             store_obs_row(row_s, io.obs + (size_t)k * io.obs_stride + ej * D, D, lane);
-            wrc_build_env_warp(p, ej, nr.x, lane);           // the new episode's rings
-            if (MULTI) {                                     // ... and into the resident copy; the lane's record restarts
-                __syncwarp();
-                const uint32_t* gsrc = reinterpret_cast<const uint32_t*>(g_tile);
-                for (int q = lane; q < 2 * NTR; q += 32)     // type planes: two words per slot and env
-                    sts_u32_v(s_win + 256 * (q >> 1) + 8 * j + 4 * (q & 1), __ldcg(gsrc + 64 * (q >> 1) + 2 * j + (q & 1)));
-                if (lane < 28) sts_u32_v(s_win + NTR * 256 + 128 * lane + 4 * j, __ldcg(gsrc + NTR * 64 + 32 * lane + j));
-                if (lane == j) r = nr;
-            }
-            if (!MULTI && lane == 0) {
+            // the new episode's rings: into the cache and, for the resident copy of the multi-step kernel, into shared memory
+            wrc_build_env_fresh_warp(p, ej, nr.x, nr.y, plane, keep != 0, lane, MULTI ? s_win : 0u);
+            if (MULTI) { if (lane == j) r = nr; }
+            else if (lane == 0) {
                 uint4 qa, qb;
                 pack_rec(nr, qa, qb);
-                p.rec[2 * ej] = qa;
-                p.rec[2 * ej + 1] = qb;
+                st_rec256(p.rec + 2 * ej, qa, qb);
             }
             __syncwarp();
         }
