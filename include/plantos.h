@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PLANTOS_ABI_VERSION 1
+#define PLANTOS_ABI_VERSION 2
 
 enum {
     PLANTOS_OK = 0,
@@ -185,6 +185,16 @@ int plantos_set_curriculum(plantos_t* h, int mode, double initial_threshold, dou
                            double threshold_increment, int max_episodes_per_maze);
 /* Current exploration thresholds, f64 [N] device pointer. */
 int plantos_get_curriculum_thresholds(plantos_t* h, double* out_dev, void* stream);
+/* "Same maze" as the reference's wrapper MEANS it (A2C_training.py:75-86 `reset(seed=self.current_maze_seed)`
+ * -- which in the reference never reaches the map generator, so it draws a new map every time): with
+ * enable != 0 every reset that keeps the current maze regenerates exactly the map (obstacles, plants,
+ * thirsty flags, rover start) of the episode the maze started in.  Default 0 = the reference's actual
+ * behaviour.  Needs an active curriculum. */
+int plantos_set_curriculum_reuse_map(plantos_t* h, int enable);
+
+/* PlantOSEnv.max_steps is a plain attribute callers may change between steps (plantos_env.py:120);
+ * takes effect for every step enqueued afterwards. */
+int plantos_set_max_steps(plantos_t* h, int max_steps);
 
 /* Rollout policy of the reference's MCTS planner (mcts_custom_trainer.py:168-216): with probability
  * 0.7 move to the least visited valid neighbour (first minimum in N, E, S, W order), otherwise -- and
@@ -205,8 +215,12 @@ typedef struct plantos_episode {
     uint32_t step_seq;     /* number of the plantos_step call (0-based) that finished the episode */
     uint32_t flags;        /* bit 0 terminated, bit 1 truncated */
     double episode_return; /* Monitor's r: rewards summed in step order, in double */
-    uint32_t collisions;
-    uint32_t watered;
+    uint16_t collisions;     /* info["total_collisions"] at the end of the episode */
+    uint16_t watered;        /* plants hydrated during the episode */
+    uint16_t explored_cells; /* info["explored_cells"] and ... */
+    uint16_t total_cells;    /* ... info["total_cells"]: exploration_percentage = explored / total * 100, the
+                                value the reference's EvaluationCallback tries to log per episode
+                                (A2C_training.py:161-179; SB3 Monitor's info_keywords) */
 } plantos_episode_t;
 /* capacity > 0 enables (or resizes and clears) the log, capacity == 0 disables it. */
 int plantos_episode_log_enable(plantos_t* h, int capacity);

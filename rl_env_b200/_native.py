@@ -8,7 +8,7 @@ from typing import Optional
 
 from . import build as _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK, EINVAL, ECUDA, ENOMAPS, ESTATE = 0, -1, -2, -3, -4
 MAPS_PHILOX, MAPS_INJECTED = 0, 1
@@ -73,6 +73,8 @@ SIGNATURES = {
     "plantos_kernel_name": (C.c_char_p, [_vp]),
     "plantos_last_step_kernel": (C.c_char_p, [_vp]),
     "plantos_set_pipelining": (C.c_int, [_vp, C.c_int]),
+    "plantos_set_curriculum_reuse_map": (C.c_int, [_vp, C.c_int]),
+    "plantos_set_max_steps": (C.c_int, [_vp, C.c_int]),
     "plantos_state_bytes_per_env": (C.c_int64, [_vp]),
     "plantos_last_error": (C.c_char_p, []),
     "plantos_abi_version": (C.c_int, []),

@@ -719,9 +719,24 @@ extern "C" int plantos_set_curriculum(plantos_t* h, int mode, double initial_thr
     k_fill_f64<<<256, 256>>>(p.cur_thr, initial_threshold, p.N);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());
-    p.cur_mode = mode; p.cur_max_eps = max_episodes_per_maze;
+    p.cur_mode = mode; p.cur_max_eps = max_episodes_per_maze; p.cur_reuse_map = 0;
     p.cur_max_thr = max_threshold; p.cur_inc = threshold_increment;
     h->did_reset = false;
+    return PLANTOS_OK;
+}
+
+extern "C" int plantos_set_curriculum_reuse_map(plantos_t* h, int enable) {
+    if (!h) return fail(PLANTOS_EINVAL, "handle is NULL");
+    if (!h->p.cur_mode) return fail(PLANTOS_ESTATE, "no curriculum is active (plantos_set_curriculum)");
+    h->p.cur_reuse_map = enable ? 1 : 0;
+    return PLANTOS_OK;
+}
+
+extern "C" int plantos_set_max_steps(plantos_t* h, int max_steps) {
+    if (!h) return fail(PLANTOS_EINVAL, "handle is NULL");
+    if (max_steps < 1 || max_steps > 65535) return fail(PLANTOS_EINVAL, "max_steps must be in [1, 65535]");
+    h->cfg.max_steps = max_steps;
+    h->p.max_steps = max_steps;          // read by the next enqueued step (kernel parameter)
     return PLANTOS_OK;
 }
 

@@ -84,9 +84,10 @@ struct Params {
     // optional CurriculumWrapper state (plantos_set_curriculum; generic kernel only)
     int cur_mode;               // 0 off, 1 reaching the threshold terminates (A2C_training.py), 2 marks only (trainingCode.py)
     int cur_max_eps;            // max_episodes_per_maze
+    int cur_reuse_map;          // 1: a kept maze is regenerated identically (plantos_set_curriculum_reuse_map)
     double cur_max_thr, cur_inc;
     double* cur_thr;            // [N] exploration_threshold
-    int2* cur_cnt;              // [N] {episodes_on_current_maze, bit0 maze_completed | bit1 persistent_visit_counts is not None}
+    int2* cur_cnt;              // [N] {episodes_on_current_maze, bit0 maze_completed | bit1 persistent_visit_counts is not None | bits 8.. the episode the maze started in}
     uint32_t* expl;             // [N][G][W] explored_map > 0, one bit per cell (restarts every episode)
     // window ring cache of k_step_tile (see wrc_* below); nullptr when the shape has no tile kernel
     unsigned char* wrc;

@@ -475,12 +475,14 @@ k_step_fast(const Params p, const StepIO io) {
                 store_obs_row(tile, io.terminal_obs + ej * D, D, lane);
                 __syncwarp();
             }
-            int keep = 0;
-            if (p.cur_mode) {                                  // CurriculumWrapper.reset
-                if (lane == 0) keep = curriculum_on_reset(p, (int)ej) ? 1 : 0;
-                keep = __shfl_sync(FULL, keep, 0);
+            int keep = 0, map_ep = -1;
+            if (p.cur_mode) {                                // CurriculumWrapper.reset
+                int cr = 0;
+                if (lane == 0) cr = curriculum_on_reset(p, (int)ej, episode);
+                cr = __shfl_sync(FULL, cr, 0);
+                keep = cr & 1; map_ep = cr >> 1;
             }
-            const EnvRec nr = reset_env_warp(p, (int)ej, episode, plane, lane, keep != 0);
+            const EnvRec nr = reset_env_warp(p, (int)ej, episode, plane, lane, keep != 0, map_ep);
             build_obs_warp(p, t, plane, vis_e, nr.x, nr.y, tile, lane, keep != 0);
             store_obs_row(tile, io.obs + ej * D, D, lane);
             if (lane == 0) {

@@ -70,14 +70,16 @@ __device__ __forceinline__ void store_obs_row(const float* obs_s, float* dst, in
 // 15) to global memory and returns the fresh record in all lanes.  `episode` selects the
 // injected map / Philox counter and is stored incremented.
 // `keep_visits` (curriculum): leave the visit planes as they are (persistent_visit_counts).
+// `map_episode` >= 0 (curriculum with reuse_map): the map is the one of that earlier episode again.
 __device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int episode, uint64_t* plane, int lane,
-                                                 bool keep_visits = false) {
+                                                 bool keep_visits = false, int map_episode = -1) {
     const int G = p.G, W = p.W;
     const int nwords = G * W;
     int rx = 0, ry = 0;
+    const int mep = map_episode >= 0 ? map_episode : episode;
     if (p.map_source == 1) {
         // recorded map (replaces plantos_env.py:338-372 for equivalence runs)
-        int k = episode;
+        int k = mep;
         if (k >= p.map_episodes) {
             if (lane == 0) atomicExch(p.err, -3);  // PLANTOS_ENOMAPS
             k = k % p.map_episodes;
@@ -107,7 +109,7 @@ __device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int epi
         const long long genv = p.env_base + e;
         for (int k = lane; k < p.nclusters; k += 32) {   // :343-354, one cluster per lane
             uint32_t d[4];
-            map_draw(p, genv, episode, 0, (uint32_t)k, d);
+            map_draw(p, genv, mep, 0, (uint32_t)k, d);
             const int cx = 2 + (int)bounded(d[0], (uint32_t)(G - 4));   // randint(2, G-3)
             const int cy = 2 + (int)bounded(d[1], (uint32_t)(G - 4));
             const int size = 2 + (int)(d[2] >> 31);                     // choice([2, 3])
@@ -130,7 +132,7 @@ __device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int epi
             int placed = 0;
             for (uint32_t j0 = 0; placed < p.P && j0 < (1u << 20); j0 += 32) {
                 uint32_t d[4];
-                map_draw(p, genv, episode, 1, j0 + (uint32_t)lane, d);
+                map_draw(p, genv, mep, 1, j0 + (uint32_t)lane, d);
                 const int cell = (int)bounded(d[0], ncell);
                 const int cx = cell / G, cy = cell - cx * G;
                 const bool empty = cell_of(plane[cx * W + (cy >> 5)], cy & 31) == kEmpty;
@@ -147,7 +149,7 @@ __device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int epi
             // rover: uniform over free cells that hold no plant (:372): the first candidate of stream 2 on an empty cell
             for (uint32_t j0 = 0; j0 < (1u << 20); j0 += 32) {
                 uint32_t d[4];
-                map_draw(p, genv, episode, 2, j0 + (uint32_t)lane, d);
+                map_draw(p, genv, mep, 2, j0 + (uint32_t)lane, d);
                 const int cell = (int)bounded(d[0], ncell);
                 const int cx = cell / G, cy = cell - cx * G;
                 const unsigned emask = __ballot_sync(0xffffffffu, cell_of(plane[cx * W + (cy >> 5)], cy & 31) == kEmpty);
@@ -271,8 +273,9 @@ __device__ __forceinline__ void accumulate_stats(const Params& p, bool done, con
             const unsigned long long rb = (unsigned long long)__double_as_longlong(r.ret);
             p.ep_log[2 * (size_t)slot] = make_uint4((unsigned)env, (unsigned)r.step, p.step_seq + seq_add,
                                                      (unsigned)(terminated | (truncated << 1)));
-            p.ep_log[2 * (size_t)slot + 1] = make_uint4((unsigned)rb, (unsigned)(rb >> 32), (unsigned)r.collisions,
-                                                         (unsigned)r.watered);
+            p.ep_log[2 * (size_t)slot + 1] = make_uint4((unsigned)rb, (unsigned)(rb >> 32),
+                                                         (unsigned)r.collisions | ((unsigned)r.watered << 16),
+                                                         (unsigned)r.explored | ((unsigned)r.total_free << 16));
         }
     }
     long long v[kStatCount];
@@ -291,11 +294,15 @@ __device__ __forceinline__ void accumulate_stats(const Params& p, bool done, con
     }
 }
 
-// CurriculumWrapper.reset (A2C_training.py:57-90): called by lane 0 before env e is reset; returns
-// whether the visit counts persist into the new episode.
-__device__ __forceinline__ bool curriculum_on_reset(const Params& p, int e) {
+// CurriculumWrapper.reset (A2C_training.py:57-90): called by lane 0 before env e is reset for its episode
+// number `episode`; returns bit 0 = the visit counts persist into the new episode, bits 1.. = the episode
+// whose map the reset draws.  The reference always draws a new map (its `reset(seed=current_maze_seed)`
+// never reaches the map generator); with plantos_set_curriculum_reuse_map the maze the wrapper means to keep
+// really is kept: the map of the episode in which the current maze started (cur_cnt.y bits 8..).
+__device__ __forceinline__ int curriculum_on_reset(const Params& p, int e, int episode) {
     int2 c = p.cur_cnt[e];
     double thr = p.cur_thr[e];
+    int maze_ep = (int)((unsigned)c.y >> 8);
     c.x += 1;                                                  // episodes_on_current_maze += 1
     const bool timeout = c.x >= p.cur_max_eps;
     bool keep;
@@ -303,13 +310,17 @@ __device__ __forceinline__ bool curriculum_on_reset(const Params& p, int e) {
         if (c.y & 1) thr = fmin(thr + p.cur_inc, p.cur_max_thr);   // :68-72
         c.x = 0; c.y = 0;                                      // maze_completed = False; persistent = None
         keep = false;
+        maze_ep = episode;                                     // a new maze starts with this episode
     } else {
         keep = (c.y & 2) != 0;                                 // :84-87
-        c.y |= 2;
+        c.y = (c.y & 0xff) | 2;
+        if (episode == 0) maze_ep = 0;
     }
+    c.y = (c.y & 0xff) | (int)(((unsigned)maze_ep & 0xffffffu) << 8);
     p.cur_cnt[e] = c;
     p.cur_thr[e] = thr;
-    return keep;
+    const int map_ep = p.cur_reuse_map ? maze_ep : episode;
+    return (keep ? 1 : 0) | (map_ep << 1);
 }
 
 // -------------------------------------------------- one env, one warp (any config)
@@ -390,12 +401,14 @@ __device__ __forceinline__ void step_env_warp(const Params& p, const Tables& t, 
         accumulate_stats(p, lane == 0, r, (flagw >> 17) & 1, (flagw >> 18) & 1, lane, e);
         episode = __shfl_sync(0xffffffffu, episode, 0);
         __syncwarp();
-        int keep = 0;
+        int keep = 0, map_ep = -1;
         if (p.cur_mode) {
-            if (lane == 0) keep = curriculum_on_reset(p, e) ? 1 : 0;
-            keep = __shfl_sync(0xffffffffu, keep, 0);
+            int cr = 0;
+            if (lane == 0) cr = curriculum_on_reset(p, e, episode);
+            cr = __shfl_sync(0xffffffffu, cr, 0);
+            keep = cr & 1; map_ep = cr >> 1;
         }
-        const EnvRec nr = reset_env_warp(p, e, episode, plane, lane, keep != 0);
+        const EnvRec nr = reset_env_warp(p, e, episode, plane, lane, keep != 0, map_ep);
         build_obs_warp(p, t, plane, vis_e, nr.x, nr.y, obs_s, lane, keep != 0);
         store_obs_row(obs_s, obs_row, p.D, lane);
         if (lane == 0) pack_rec(nr, ra, rb);
@@ -432,12 +445,14 @@ k_reset_all(const Params p, float* obs) {
         int episode = 0;
         if (lane == 0) episode = (int)p.rec[2 * (size_t)e].w;
         episode = __shfl_sync(0xffffffffu, episode, 0);
-        int keep = 0;
+        int keep = 0, map_ep = -1;
         if (p.cur_mode) {
-            if (lane == 0) keep = curriculum_on_reset(p, e) ? 1 : 0;
-            keep = __shfl_sync(0xffffffffu, keep, 0);
+            int cr = 0;
+            if (lane == 0) cr = curriculum_on_reset(p, e, episode);
+            cr = __shfl_sync(0xffffffffu, cr, 0);
+            keep = cr & 1; map_ep = cr >> 1;
         }
-        const EnvRec nr = reset_env_warp(p, e, episode, plane, lane, keep != 0);
+        const EnvRec nr = reset_env_warp(p, e, episode, plane, lane, keep != 0, map_ep);
         build_obs_warp(p, t, plane, p.vis4 + (size_t)e * p.VE, nr.x, nr.y, obs_s, lane, keep != 0);
         store_obs_row(obs_s, obs + (size_t)e * p.D, p.D, lane);
         if (lane == 0) {

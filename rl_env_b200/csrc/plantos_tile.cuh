@@ -617,12 +617,14 @@ k_tile(const Params p, const RollIO io) {
             dmask &= dmask - 1;
             const size_t ej = (size_t)e0 + j;
             const int ep = __shfl_sync(FULL, episode, j);
-            int keep = 0;
+            int keep = 0, map_ep = -1;
             if (p.cur_mode) {                                // CurriculumWrapper.reset
-                if (lane == 0) keep = curriculum_on_reset(p, (int)ej) ? 1 : 0;
-                keep = __shfl_sync(FULL, keep, 0);
+                int cr = 0;
+                if (lane == 0) cr = curriculum_on_reset(p, (int)ej, ep);
+                cr = __shfl_sync(FULL, cr, 0);
+                keep = cr & 1; map_ep = cr >> 1;
             }
-            const EnvRec nr = reset_env_warp(p, (int)ej, ep, plane, lane, keep != 0);
+            const EnvRec nr = reset_env_warp(p, (int)ej, ep, plane, lane, keep != 0, map_ep);
             // (fresh visit window: what the planes hold after a plain reset, and what the wrapper's reset
             // observation shows when the counts are kept)
             build_obs_warp(p, tabs(), plane, p.vis4 + ej * VE, nr.x, nr.y, row_s, lane, true);

@@ -119,10 +119,14 @@ class LazyInfos(Sequence):
             "total_collisions": int(src["total_collisions"][i]),
             "TimeLimit.truncated": bool(s["truncated"][i]) and not bool(s["terminated"][i]),
         }
+        if s.get("actions") is not None:                   # the Gradio fork's flag (gradio-app/plantos_env_new.py:184)
+            info["is_watering"] = bool(s["actions"][i] >= 4)
         if done:
             info["episode"] = {"r": round(float(s["term_return"][i]), 6),
                                "l": int(src["step_count"][i]),
                                "t": round(time.time() - env._t_start, 6)}
+            for key in env.info_keywords:                  # SB3 Monitor: ep_info[key] = info[key]
+                info["episode"][key] = info[key]
             if env._terminal_obs is not None:
                 info["terminal_observation"] = env._terminal_obs[i]
         return info
@@ -138,7 +142,7 @@ class PlantOSVecEnv:
                  env_id_base: int = 0, kernel: str = "auto",
                  rewards: Optional[Dict[str, float]] = None,
                  track_terminal_obs: bool = True, full_infos: Optional[bool] = None,
-                 obs_ring: int = 1, curriculum: Any = None):
+                 obs_ring: int = 1, curriculum: Any = None, info_keywords: Sequence[str] = ()):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("PlantOSVecEnv runs on a CUDA device only (no CPU path)")
@@ -192,6 +196,11 @@ class PlantOSVecEnv:
             nat.check(self._lib.plantos_set_curriculum(
                 self._h, mode, float(base["initial_threshold"]), float(base["max_threshold"]),
                 float(base["threshold_increment"]), int(base["max_episodes_per_maze"])))
+            # reuse_map=True: a kept maze really is regenerated identically, as the wrapper's
+            # `reset(seed=self.current_maze_seed)` means it to be (A2C_training.py:75-86); the
+            # reference itself draws a new map every time (default)
+            if base.get("reuse_map"):
+                nat.check(self._lib.plantos_set_curriculum_reuse_map(self._h, 1))
             self.curriculum = base
 
         # tables evaluated by the Python interpreter, exactly as the reference evaluates them
@@ -219,6 +228,10 @@ class PlantOSVecEnv:
         self._scalars = torch.empty((nat.SC_COUNT, n), dtype=torch.int32, device=dev)
         self._stats = torch.zeros(len(nat.STAT_NAMES), dtype=torch.float64, device=dev)
         self._host: Optional[Dict[str, torch.Tensor]] = None
+        # SB3 Monitor's info_keywords (A2C_training.py:124 passes none, so its EvaluationCallback :161-179
+        # never sees 'exploration_percentage'): info keys copied into info["episode"] of finished envs
+        self.info_keywords = tuple(info_keywords)
+        self._last_actions_host: Optional[np.ndarray] = None
         self._t_start = time.time()
         self._waiting = False
 
@@ -391,10 +404,32 @@ class PlantOSVecEnv:
         return [getattr(self, attr_name)] * len(self._indices(indices))
 
     def set_attr(self, attr_name: str, value: Any, indices=None) -> None:
-        raise NotImplementedError("env attributes are fixed at construction (they are baked into the device config)")
+        """The attributes a caller of the reference may change after construction: `max_steps`
+        (plantos_env.py:120) and the reward constants `R_*` (:65-93, also by their config names
+        `r_*`).  They apply to ALL envs of the batch (`indices` must cover every env) and to every
+        step enqueued afterwards.  Everything else is baked into the device state."""
+        if indices is not None and sorted(self._indices(indices)) != list(range(self.num_envs)):
+            raise ValueError("the batched simulator sets attributes for all envs at once (indices=None)")
+        name = attr_name.lower()
+        if name == "max_steps":
+            nat.check(self._lib.plantos_set_max_steps(self._h, int(value)))
+            self.max_steps = int(value)
+        elif name in self.rewards:
+            self.rewards[name] = float(value)
+            rw = tables.reward_table(self.rewards)
+            nat.check(self._lib.plantos_upload_tables(self._h, None, None, None, None, rw.ctypes.data))
+        else:
+            raise AttributeError(f"{attr_name!r} cannot be changed after construction "
+                                 f"(settable: max_steps, {', '.join(k.upper() for k in self.rewards)})")
 
     def env_method(self, method_name: str, *args, indices=None, **kwargs) -> List[Any]:
-        raise NotImplementedError(f"env_method({method_name!r}) is not available on the batched simulator")
+        """Per-env method calls have no counterpart on the batch; the only methods the reference's
+        call sites use through a VecEnv are answered for all envs at once."""
+        if method_name in ("get_wrapper_attr", "get_attr"):
+            return self.get_attr(args[0], indices)
+        if method_name == "close":
+            return [None] * len(self._indices(indices))
+        raise AttributeError(f"env_method({method_name!r}): PlantOSEnv exposes no such method through the batched simulator")
 
     def env_is_wrapped(self, wrapper_class, indices=None) -> List[bool]:
         return [False] * len(self._indices(indices))
@@ -482,7 +517,8 @@ class PlantOSVecEnv:
         done = self._dones.cpu().numpy()
         snap: Dict[str, Any] = {"live": live, "done": done,
                                 "terminated": self._terminated.cpu().numpy(),
-                                "truncated": self._truncated.cpu().numpy()}
+                                "truncated": self._truncated.cpu().numpy(),
+                                "actions": self._actions.cpu().numpy() if self._actions is not None and self._actions.dim() == 1 else None}
         if done.any():
             snap["term"] = {k: v.cpu().numpy() for k, v in self.scalars(True).items()}
             snap["term_return"] = self.returns(True).cpu().numpy()
@@ -504,7 +540,8 @@ class PlantOSVecEnv:
 
     # --------------------------------------------------------------- per-episode log (SB3 Monitor)
     EPISODE_DTYPE = np.dtype([("env", "<u4"), ("l", "<u4"), ("step_seq", "<u4"), ("flags", "<u4"),
-                              ("r", "<f8"), ("collisions", "<u4"), ("watered", "<u4")])
+                              ("r", "<f8"), ("collisions", "<u2"), ("watered", "<u2"),
+                              ("explored_cells", "<u2"), ("total_cells", "<u2")])
 
     def enable_episode_log(self, capacity: Optional[int] = None) -> None:
         """Record (env, r, l, ...) of every finished episode on the device -- what SB3's Monitor
@@ -522,7 +559,8 @@ class PlantOSVecEnv:
 
     def drain_episode_log(self):
         """Finished episodes since the last drain as a structured array (fields env [global id], l,
-        step_seq, flags, r, collisions, watered) plus the number of entries lost to overflow."""
+        step_seq, flags, r, collisions, watered, explored_cells, total_cells) plus the number of
+        entries lost to overflow."""
         n, dropped = C.c_int(0), C.c_int64(0)
         nat.check(self._lib.plantos_episode_log_drain(
             self._h, self._ep_buf.ctypes.data_as(C.c_void_p), self._ep_cap, C.byref(n), C.byref(dropped),
@@ -597,12 +635,26 @@ class MonitorCSV:
     `t` is the wall-clock time of the `flush()` that collected the episode, relative to t_start:
     steps are enqueued asynchronously, so the host never sees the exact moment an episode ended."""
 
+    # what `info_keywords` may name: info keys of PlantOSEnv._get_info (plantos_env.py:323-336) that the
+    # device log carries for the final step of an episode
+    INFO_KEYWORDS = {
+        "exploration_percentage": lambda ep: (int(ep["explored_cells"]) / int(ep["total_cells"])) * 100,
+        "explored_cells": lambda ep: int(ep["explored_cells"]),
+        "total_cells": lambda ep: int(ep["total_cells"]),
+        "total_collisions": lambda ep: int(ep["collisions"]),
+        "plants_watered": lambda ep: int(ep["watered"]),
+    }
+
     def __init__(self, env: "PlantOSVecEnv", directory: str, per_env_files: bool = False,
-                 env_column: bool = False, capacity: Optional[int] = None):
+                 env_column: bool = False, capacity: Optional[int] = None, info_keywords: Sequence[str] = ()):
         import json
         import os
         self.env, self.dir = env, directory
         self.per_env, self.env_column = per_env_files, env_column
+        unknown = [k for k in info_keywords if k not in self.INFO_KEYWORDS]
+        if unknown:
+            raise ValueError(f"info_keywords {unknown} are not recorded per episode (available: {sorted(self.INFO_KEYWORDS)})")
+        self.info_keywords = tuple(info_keywords)          # extra columns, like SB3 Monitor(info_keywords=...)
         self.t_start = time.time()
         self.dropped = 0
         os.makedirs(directory, exist_ok=True)
@@ -616,7 +668,7 @@ class MonitorCSV:
             name = "monitor.csv" if key is None else f"env_{key}.monitor.csv"
             f = open(self._os.path.join(self.dir, name), "w")
             f.write("#%s\n" % self._json.dumps({"t_start": self.t_start, "env_id": "None" if key is None else str(key)}))
-            f.write(("env," if (key is None and self.env_column) else "") + "r,l,t\n")
+            f.write(("env," if (key is None and self.env_column) else "") + ",".join(("r", "l", "t") + self.info_keywords) + "\n")
             self._files[key] = f
         return f
 
@@ -628,7 +680,8 @@ class MonitorCSV:
         for ep in eps:
             f = self._file(int(ep["env"]) if self.per_env else None)
             lead = f"{int(ep['env'])}," if (not self.per_env and self.env_column) else ""
-            f.write(f"{lead}{round(float(ep['r']), 6)},{int(ep['l'])},{t}\n")
+            extra = "".join("," + str(self.INFO_KEYWORDS[k](ep)) for k in self.info_keywords)
+            f.write(f"{lead}{round(float(ep['r']), 6)},{int(ep['l'])},{t}{extra}\n")
         for f in self._files.values():
             f.flush()
         return len(eps)

@@ -208,6 +208,85 @@ def test_step_many_equals_single_steps(n, kernel, preset, cur):
     a.close(); b.close()
 
 
+def test_monitor_info_keywords_is_watering_and_set_attr(tmp_path):
+    """SB3 Monitor(info_keywords=...) columns from the device episode log (the reference's EvaluationCallback
+    wants exploration_percentage per episode, A2C_training.py:161-179), the Gradio fork's info['is_watering']
+    (gradio-app/plantos_env_new.py:184), and set_attr for the attributes the reference lets callers change
+    (max_steps, plantos_env.py:120; the reward constants, :76-83)."""
+    import torch
+    from rl_env_b200 import MonitorCSV, PlantOSVecEnv
+    fx = load_fixture("replay_tiny_4env")
+    ora = PyOracleBackend(fx).env
+    env = PlantOSVecEnv(4, map_source="injected", max_steps=int(fx["cfg_max_steps"]), **fixture_kwargs(fx))
+    env.push_maps(fx["maps_cells"], fx["maps_rover"])
+    mon = MonitorCSV(env, str(tmp_path), info_keywords=("exploration_percentage", "total_collisions"))
+    with pytest.raises(ValueError):
+        MonitorCSV(env, str(tmp_path / "x"), info_keywords=("rover_position",))
+    ora.reset(); env.reset()
+    want = []
+    for t in range(700):
+        _, _, o_done, o_infos = ora.step(fx["actions"][t])
+        _, _, _, g_infos = env.step(fx["actions"][t])
+        for i in range(4):
+            assert g_infos[i]["is_watering"] == bool(fx["actions"][t][i] >= 4)
+            if o_done[i]:
+                want.append((o_infos[i]["episode"]["l"], o_infos[i]["exploration_percentage"], o_infos[i]["total_collisions"]))
+    mon.close()
+    lines = (tmp_path / "monitor.csv").read_text().splitlines()
+    assert lines[1] == "r,l,t,exploration_percentage,total_collisions"
+    got = sorted((int(l), float(x), int(c)) for _, l, _, x, c in (ln.split(",") for ln in lines[2:]))
+    assert got == sorted((l, float(x), c) for l, x, c in want) and len(got) >= 2
+    # set_attr: a new reward constant and a new horizon apply to the following steps
+    env.set_attr("R_INVALID", -7.0)
+    env.set_attr("max_steps", 2)
+    assert env.get_attr("max_steps") == [2] * 4
+    _, rew, d1, _ = env.step(np.zeros(4, np.int64))
+    d1 = d1.clone()
+    _, rew, d2, _ = env.step(np.zeros(4, np.int64))
+    assert bool((d1 | d2).all())                           # every env hits the new horizon within two steps
+    with pytest.raises(AttributeError):
+        env.set_attr("grid_size", 30)
+    twin = PlantOSVecEnv(64, seed=1, rewards={"r_invalid": -7.0}, **fixture_kwargs(fx))
+    late = PlantOSVecEnv(64, seed=1, **fixture_kwargs(fx))
+    late.set_attr("R_INVALID", -7.0)
+    twin.reset(); late.reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    for _ in range(30):
+        a = torch.randint(0, 5, (64,), device="cuda", generator=g)
+        assert torch.equal(twin.step(a)[1], late.step(a)[1])
+    env.close(); twin.close(); late.close()
+
+
+def test_curriculum_reuse_map_keeps_the_maze():
+    """reuse_map=True: while the wrapper stays on a maze, every reset regenerates exactly that maze (what
+    A2C_training.py:75-86 `reset(seed=self.current_maze_seed)` means to do); the default draws a new map at
+    every reset, like the reference really does.  With 3 episodes per maze and a threshold no random walk
+    reaches in 12 steps, episodes 0-1 share a maze, 2-4 share the next, 5-7 the one after."""
+    import torch
+    from rl_env_b200 import PlantOSVecEnv, PRESETS
+    from rl_env_b200.vec_env import CURRICULA
+    n, horizon = 96, 12
+    for reuse in (True, False):
+        env = PlantOSVecEnv(n, seed=9, max_steps=horizon, kernel="fast", full_infos=False,
+                            curriculum=dict(CURRICULA["a2c"], initial_threshold=99.0, reuse_map=reuse), **PRESETS["training"])
+        env.reset()
+        maps = []
+        g = torch.Generator(device="cuda"); g.manual_seed(1)
+        for ep in range(8):
+            st = env.get_state()
+            maps.append((st["cells"].clone(), st["x"].clone(), st["y"].clone()))
+            for _ in range(horizon):
+                _, _, done, _ = env.step(torch.randint(0, 4, (n,), device="cuda", generator=g))   # moves only: plants stay as generated
+            assert bool(done.all())
+        same = lambda a, b: all(torch.equal(u, v) for u, v in zip(maps[a], maps[b]))
+        if reuse:
+            assert same(0, 1) and same(2, 3) and same(2, 4) and same(5, 6) and same(5, 7)
+            assert not same(0, 2) and not same(2, 5)
+        else:
+            assert not any(same(a, a + 1) for a in range(7))
+        env.check(); env.close()
+
+
 def test_pipelined_eager_steps_equal_plain_steps():
     """plantos_set_pipelining on eager launches: back-to-back step_async calls into an observation ring
     overlap on the device (per-tile counters order them) and give exactly the plain results; every
