@@ -38,7 +38,11 @@ enum {
     PLANTOS_ESTATE = -4    /* call not valid in the handle's current state */
 };
 
-enum { PLANTOS_MAPS_PHILOX = 0, PLANTOS_MAPS_INJECTED = 1 };
+/* map_source: PHILOX = the reference's cluster generator (plantos_env.py:338-372) with Philox draws;
+ * INJECTED = recorded maps (plantos_push_maps); MAZE = the Gradio fork's 'maze' generator
+ * (gradio-app/plantos_env_new.py:408-604: randomised DFS over a (G-1)/6 meta grid, 5x5 rooms, 5-wide
+ * corridors, random extensions / corner cuts / bulges) with Philox draws, on the device. */
+enum { PLANTOS_MAPS_PHILOX = 0, PLANTOS_MAPS_INJECTED = 1, PLANTOS_MAPS_MAZE = 2 };
 
 /* kernel selection (plantos_config_t.kernel) */
 enum {

@@ -1,8 +1,9 @@
-"""Host-side map generators for map injection (`PlantOSVecEnv.push_maps`).
+"""TEST INFRASTRUCTURE ONLY -- restatement of the reference's two map generators for map injection
+(`PlantOSVecEnv.push_maps`) and as the yardstick of the device generators' statistics.
 
-The simulator's own resets draw maps on the device with Philox (csrc/plantos_generic.cuh); this module
-is for callers that want maps produced exactly the way the reference produces them -- with Python's
-global `random` module -- and pushes them as recorded maps.  Two generators:
+The simulator's own resets draw maps on the device with Philox (csrc/plantos_generic.cuh: clusters and,
+with map_source="maze", the fork's maze algorithm); this module produces maps exactly the way the
+reference produces them -- with Python's global `random` module.  Two generators:
 
   * `original_map`: the cluster generator of plantos_env.py:338-372 (also `_generate_map_original` of
     the Gradio fork, gradio-app/plantos_env_new.py:360-406);

@@ -11,7 +11,7 @@ from . import build as _build
 ABI_VERSION = 2
 
 OK, EINVAL, ECUDA, ENOMAPS, ESTATE = 0, -1, -2, -3, -4
-MAPS_PHILOX, MAPS_INJECTED = 0, 1
+MAPS_PHILOX, MAPS_INJECTED, MAPS_MAZE = 0, 1, 2
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST = 0, 1, 2
 RW_COUNT = 6
 SC_NAMES = ("x", "y", "step_count", "explored_cells", "total_cells", "thirsty_plants",

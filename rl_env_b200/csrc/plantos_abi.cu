@@ -10,7 +10,9 @@
 
 #include "../../include/plantos.h"
 #include "plantos_fast.cuh"
+#ifdef PLANTOS_WITH_LANE_KERNEL      // round 1's experimental lane-per-env kernel: a recorded experiment, not built by default
 #include "plantos_lane.cuh"
+#endif
 #include "plantos_tile.cuh"
 
 using namespace plantos_dev;
@@ -44,8 +46,10 @@ const FastVariant kFastVariants[] = {
     FAST_ROW(4, 8),
 };
 
+#ifdef PLANTOS_WITH_LANE_KERNEL
 #define LANE_ROW(R_, C_) {R_, C_, 0, k_step_lane<R_, C_, false>}, {R_, C_, 1, k_step_lane<R_, C_, true>}
 const FastVariant kLaneVariants[] = { LANE_ROW(6, 16), LANE_ROW(2, 10), LANE_ROW(4, 16), LANE_ROW(4, 8) };
+#endif
 
 // k_step_tile (plantos_tile.cuh): lane-per-env simulation + byte-coded observation output
 struct TileVariant { int R, C; tile_kernel_t step, rollout; };
@@ -152,8 +156,8 @@ static int validate(const plantos_config_t* c) {
         return fail(PLANTOS_EINVAL, "Not enough guaranteed-free positions (4G-4) to place num_plants plants and 1 rover");
     if (!(c->thirsty_plant_prob >= 0.0f && c->thirsty_plant_prob <= 1.0f))
         return fail(PLANTOS_EINVAL, "thirsty_plant_prob must be in [0, 1]");
-    if (c->map_source != PLANTOS_MAPS_PHILOX && c->map_source != PLANTOS_MAPS_INJECTED)
-        return fail(PLANTOS_EINVAL, "map_source must be PLANTOS_MAPS_PHILOX or PLANTOS_MAPS_INJECTED");
+    if (c->map_source != PLANTOS_MAPS_PHILOX && c->map_source != PLANTOS_MAPS_INJECTED && c->map_source != PLANTOS_MAPS_MAZE)
+        return fail(PLANTOS_EINVAL, "map_source must be PLANTOS_MAPS_PHILOX, PLANTOS_MAPS_INJECTED or PLANTOS_MAPS_MAZE");
     if (c->kernel < PLANTOS_KERNEL_AUTO || c->kernel > PLANTOS_KERNEL_FAST)
         return fail(PLANTOS_EINVAL, "kernel must be one of PLANTOS_KERNEL_*");
     return PLANTOS_OK;
@@ -348,8 +352,10 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
         }
         for (const FastVariant& v : kFastVariants)
             if (v.R == p.R && v.C == p.C && v.keep == keep) { h->use_fast = true; h->trip.fn = v.fn; }
+#ifdef PLANTOS_WITH_LANE_KERNEL
         for (const FastVariant& v : kLaneVariants)
             if (v.R == p.R && v.C == p.C && v.keep == keep) h->lane.fn = v.fn;
+#endif
         for (const TileVariant& v : kTileVariants)
             if (v.R == p.R && v.C == p.C && h->use_fast) {
                 h->tile.fn = h->trip.fn;                    // (non-null marks the tile path as available)
@@ -377,8 +383,10 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
         };
         shape(h->trip, kFastWarps, PLANTOS_FAST_MINBLOCKS,
               tables_bytes(p.G, p.R, p.C) + kFastWarps * fast_warp_scratch_bytes(p.R, p.G, p.D));
+#ifdef PLANTOS_WITH_LANE_KERNEL
         shape(h->lane, kLaneWarps, 1, tables_bytes(p.G, p.R, p.C) + kLaneWarps * lane_warp_scratch_bytes(p.R, p.D));
         if ((tables_bytes(p.G, p.R, p.C) >> 4) > kLaneWarps * 32) h->lane.fn = nullptr;
+#endif
         {
             // k_step_tile: one block of kTileWarps warps per SM, every warp walks 32-env tiles
             FastLaunch& L = h->tile;
@@ -413,6 +421,7 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     }
     cudaError_t e1 = cudaFuncSetAttribute(k_step_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);
     cudaError_t e2 = cudaFuncSetAttribute(k_reset_all, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_reset_done, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
         free_all(h);
         return fail(PLANTOS_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
@@ -508,7 +517,7 @@ static int launch_steps(plantos_t* h, int K, const int64_t* actions, float* obs,
     const size_t N = (size_t)h->p.N;
     const bool aligned = (((uintptr_t)obs) & 15u) == 0 && (K == 1 || (obs_stride & 3u) == 0);
     const bool use_tile = h->use_fast && aligned && h->impl == 0 && h->tile.fn && h->lane_offsets_ok;
-    if (!use_tile && K > 1) {                               // no multi-step kernel for this configuration
+    if ((!use_tile || h->p.map_source == PLANTOS_MAPS_MAZE) && K > 1) {   // no multi-step kernel for this configuration
         for (int k = 0; k < K; ++k) {
             int rc = launch_steps(h, 1, actions + k * N, obs + k * obs_stride, 0, reward + k * N, done + k * N,
                                   terminated ? terminated + k * N : nullptr, truncated ? truncated + k * N : nullptr,
@@ -568,6 +577,17 @@ static int launch_steps(plantos_t* h, int K, const int64_t* actions, float* obs,
             io.terminated = terminated; io.truncated = truncated; io.terminal_obs = terminal_obs;
             CUDA_TRY(cudaLaunchKernelEx(&lc, L.fn, h->p, io));
             h->wrc_valid = false;
+        }
+        if (h->p.map_source == PLANTOS_MAPS_MAZE) {
+            // maze handles: the specialised kernels leave the maze generator out; the envs they finished get
+            // their new episodes from this follow-up launch (scans the done flags)
+            CUDA_TRY(cudaGetLastError());
+            StepIO io;
+            io.actions = (const long long*)actions; io.obs = obs; io.reward = reward; io.done = done;
+            io.terminated = terminated; io.truncated = truncated; io.terminal_obs = terminal_obs;
+            k_reset_done<<<h->generic_grid, kGenericWarps * 32, h->generic_smem, (cudaStream_t)stream>>>(h->p, io);
+            h->launches += 1;
+            h->prev_tile_step = false;
         }
     } else {
         if (h->cfg.kernel == PLANTOS_KERNEL_FAST)

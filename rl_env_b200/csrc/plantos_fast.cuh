@@ -460,6 +460,7 @@ k_step_fast(const Params p, const StepIO io) {
         // buffer 0 is free now and serves as the type-plane scratch)
         unsigned dmask = __ballot_sync(FULL, act && done);
         uint64_t* plane = reinterpret_cast<uint64_t*>(win_buf(0));
+        const bool deferred = p.map_source == 2;             // maze handles: k_reset_done starts the new episodes after this launch
         while (dmask) {
             const int j = __ffs(dmask) - 1;
             dmask &= dmask - 1;
@@ -475,6 +476,7 @@ k_step_fast(const Params p, const StepIO io) {
                 store_obs_row(tile, io.terminal_obs + ej * D, D, lane);
                 __syncwarp();
             }
+            if (deferred) continue;
             int keep = 0, map_ep = -1;
             if (p.cur_mode) {                                // CurriculumWrapper.reset
                 int cr = 0;
@@ -482,7 +484,7 @@ k_step_fast(const Params p, const StepIO io) {
                 cr = __shfl_sync(FULL, cr, 0);
                 keep = cr & 1; map_ep = cr >> 1;
             }
-            const EnvRec nr = reset_env_warp(p, (int)ej, episode, plane, lane, keep != 0, map_ep);
+            const EnvRec nr = reset_env_warp<false>(p, (int)ej, episode, plane, lane, keep != 0, map_ep);
             build_obs_warp(p, t, plane, vis_e, nr.x, nr.y, tile, lane, keep != 0);
             store_obs_row(tile, io.obs + ej * D, D, lane);
             if (lane == 0) {
@@ -497,7 +499,7 @@ k_step_fast(const Params p, const StepIO io) {
 
     // ragged tail: envs beyond the last 4-env group, one at a time (no copies are in flight here)
     if (gwarp == nwarps - 1)
-        for (int e = nfull; e < p.N; ++e) step_env_warp(p, t, io, e, reinterpret_cast<uint64_t*>(win_buf(0)), tile, lane);
+        for (int e = nfull; e < p.N; ++e) step_env_warp<false>(p, t, io, e, reinterpret_cast<uint64_t*>(win_buf(0)), tile, lane);
 }
 
 }  // namespace plantos_dev

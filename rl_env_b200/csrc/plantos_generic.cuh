@@ -13,9 +13,17 @@ namespace plantos_dev {
 
 constexpr int kGenericWarps = 8;  // warps (= envs in flight) per block
 
+// scratch of the maze generator (map_source = maze): the DFS stack (one u16 per meta cell) and the visited bits
+// of the (G-1)/6 x (G-1)/6 meta grid.  It lives right behind the type plane of a reset's scratch (where the
+// observation row sits, which is not in use while a map is generated); every kernel leaves that much room.
+__host__ __device__ inline int maze_scratch_bytes(int G) {
+    const int m = (G - 1) / 6;
+    return align_up(m * m * 2, 4) + ((m * m + 31) / 32) * 4;
+}
 // per-warp scratch: the env's (unpadded) type plane, G*W u64, followed by one observation row
 __host__ __device__ inline int generic_warp_scratch_bytes(int G, int W, int D) {
-    return align_up(G * W * 8, 16) + align_up(D * 4, 16);
+    const int row = align_up(D * 4, 16), maze = align_up(maze_scratch_bytes(G), 16);
+    return align_up(G * W * 8, 16) + (row > maze ? row : maze);
 }
 
 // ----------------------------------------------------------------- observation
@@ -64,6 +72,87 @@ __device__ __forceinline__ void store_obs_row(const float* obs_s, float* dst, in
     for (int i = lane; i < D; i += 32) dst[i] = obs_s[i];
 }
 
+// ---------------------------------------------------------------- maze generator
+// The Gradio fork's 'maze' maps (gradio-app/plantos_env_new.py:408-604) with Philox draws: start from a
+// grid full of obstacles, run a randomised depth-first search over the (G-1)/6 x (G-1)/6 meta grid, carve a
+// 5x5 room per meta cell (with probability 0.3 each a 2x2 extension to the right / downwards, with 0.4 one
+// corner cut) and a 5-wide corridor between consecutive rooms (with 0.2 a 2x2 bulge to one side).  Word j of
+// Philox stream 3 is the j-th random decision, taken in the fork's order.  Executed by lane 0 (a serial
+// algorithm on at most 21 x 21 meta cells); `scratch` = maze_scratch_bytes(G) bytes of shared memory.
+struct MazeRng {
+    const Params& p; long long genv; int ep; uint32_t j; uint32_t buf[4];
+    __device__ __forceinline__ uint32_t next() {
+        if ((j & 3u) == 0u) map_draw(p, genv, ep, 3, j >> 2, buf);
+        return buf[j++ & 3u];
+    }
+    __device__ __forceinline__ bool chance(uint32_t thresh) { return next() < thresh; }   // random.random() < prob
+};
+
+__device__ __forceinline__ void maze_rect(uint64_t* plane, int G, int W, int x0, int x1, int y0, int y1, bool obstacle) {
+    // cells [x0, x1) x [y0, y1) clipped to the grid become empty (or obstacle)
+    x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, G); y1 = min(y1, G);
+    for (int x = x0; x < x1; ++x)
+        for (int y = y0; y < y1; ++y) {
+            uint64_t& w = plane[x * W + (y >> 5)];
+            const uint64_t m = 3ull << (2 * (y & 31));
+            w = obstacle ? ((w & ~m) | (1ull << (2 * (y & 31)))) : (w & ~m);
+        }
+}
+
+__device__ __forceinline__ void maze_room(MazeRng& rng, uint64_t* plane, int G, int W, int mx, int my) {   // :479-517
+    const int bx = mx * 6 + 1, by = my * 6 + 1;
+    maze_rect(plane, G, W, bx, bx + 5, by, by + 5, false);
+    if (rng.chance(1288490188u)) maze_rect(plane, G, W, bx + 5, bx + 7, by + 2, by + 4, false);   // 0.3: extend right
+    if (rng.chance(1288490188u)) maze_rect(plane, G, W, bx + 2, bx + 4, by + 5, by + 7, false);   // 0.3: extend down
+    if (rng.chance(1717986918u)) {                                                                 // 0.4: cut one corner
+        const int c = (int)bounded(rng.next(), 4u);                  // [(0,0), (4,0), (0,4), (4,4)]
+        const int px = bx + ((c & 1) ? 4 : 0), py = by + ((c & 2) ? 4 : 0);
+        maze_rect(plane, G, W, px, px + 1, py, py + 1, true);
+    }
+}
+
+__device__ inline void maze_generate(const Params& p, long long genv, int ep, uint64_t* plane, unsigned char* scratch) {
+    const int G = p.G, W = p.W, m = (G - 1) / 6;
+    for (int idx = 0; idx < G * W; ++idx) plane[idx] = kObstAll;       // (columns >= G are obstacles in any case)
+    if (m < 1) return;
+    uint16_t* stack = reinterpret_cast<uint16_t*>(scratch);
+    uint32_t* visited = reinterpret_cast<uint32_t*>(scratch + align_up(m * m * 2, 4));
+    for (int i = 0; i < (m * m + 31) / 32; ++i) visited[i] = 0u;
+    MazeRng rng{p, genv, ep, 0u, {0u, 0u, 0u, 0u}};
+    int cx = (int)bounded(rng.next(), (uint32_t)m), cy = (int)bounded(rng.next(), (uint32_t)m);   // randint(0, meta - 1) twice
+    int sp = 0;
+    stack[sp++] = (uint16_t)(cx * m + cy);
+    visited[(cx * m + cy) >> 5] |= 1u << ((cx * m + cy) & 31);
+    maze_room(rng, plane, G, W, cx, cy);
+    while (sp > 0) {                                                   // :434-457
+        const int cur = stack[sp - 1];
+        cx = cur / m; cy = cur - cx * m;
+        int cand[4], nc = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                                  // [(0,1), (0,-1), (1,0), (-1,0)]
+            const int nx = cx + (k == 2) - (k == 3), ny = cy + (k == 0) - (k == 1);
+            if ((unsigned)nx < (unsigned)m && (unsigned)ny < (unsigned)m && !((visited[(nx * m + ny) >> 5] >> ((nx * m + ny) & 31)) & 1u))
+                cand[nc++] = k;
+        }
+        if (nc == 0) { --sp; continue; }
+        const int k = cand[bounded(rng.next(), (uint32_t)nc)];
+        const int dx = (k == 2) - (k == 3), dy = (k == 0) - (k == 1);
+        const int nx = cx + dx, ny = cy + dy;
+        // corridor (:540-560): 5 wide, over both meta cells
+        if (dx == 0) maze_rect(plane, G, W, cx * 6 + 1, cx * 6 + 6, min(cy, ny) * 6 + 1, max(cy, ny) * 6 + 7, false);
+        else maze_rect(plane, G, W, min(cx, nx) * 6 + 1, max(cx, nx) * 6 + 7, cy * 6 + 1, cy * 6 + 6, false);
+        if (rng.chance(858993459u)) {                                  // 0.2: bulge (:562-580)
+            const int mx = (cx + nx) / 2, my = (cy + ny) / 2;
+            const int dir = bounded(rng.next(), 2u) ? 1 : -1;          // choice([-1, 1])
+            if (dx == 0) maze_rect(plane, G, W, mx * 6 + 2 + dir * 2, mx * 6 + 4 + dir * 2, my * 6 + 2, my * 6 + 4, false);
+            else maze_rect(plane, G, W, mx * 6 + 2, mx * 6 + 4, my * 6 + 2 + dir * 2, my * 6 + 4 + dir * 2, false);
+        }
+        maze_room(rng, plane, G, W, nx, ny);
+        visited[(nx * m + ny) >> 5] |= 1u << ((nx * m + ny) & 31);
+        stack[sp++] = (uint16_t)(nx * m + ny);
+    }
+}
+
 // ----------------------------------------------------------------------- reset
 // New episode for env e (local index): builds the map in `plane` (shared), writes the type
 // rows and a fresh visit-nibble plane (zeros, rover cell = 1, plantos_env.py:146-147; border
@@ -71,6 +160,9 @@ __device__ __forceinline__ void store_obs_row(const float* obs_s, float* dst, in
 // injected map / Philox counter and is stored incremented.
 // `keep_visits` (curriculum): leave the visit planes as they are (persistent_visit_counts).
 // `map_episode` >= 0 (curriculum with reuse_map): the map is the one of that earlier episode again.
+// MAZE = false leaves the maze generator out: the specialised step kernels instantiate it that way (its serial
+// DFS would sit in their register allocation) and hand the resets of maze handles to k_reset_done.
+template <bool MAZE = true>
 __device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int episode, uint64_t* plane, int lane,
                                                  bool keep_visits = false, int map_episode = -1) {
     const int G = p.G, W = p.W;
@@ -100,14 +192,28 @@ __device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int epi
         ry = p.map_rover[mi * 2 + 1];
         __syncwarp();
     } else {
+        const long long genv = p.env_base + e;
+        bool clusters = true;
+        if (MAZE && p.map_source == 2) {
+            // the fork's maze generator; like the fork (:463-467) it falls back to the cluster generator
+            // when the maze leaves fewer than P + 1 free cells
+            if (lane == 0) maze_generate(p, genv, mep, plane, reinterpret_cast<unsigned char*>(plane) + align_up(nwords * 8, 16));
+            __syncwarp();
+            int nfree = 0;
+            for (int idx = lane; idx < nwords; idx += 32) {
+                const uint64_t word = plane[idx];
+                nfree += __popcll(~(word | (word >> 1)) & col_mask(G, idx % W));
+            }
+            clusters = warp_sum_i(nfree) < p.P + 1;
+            __syncwarp();
+        }
         // procedural map, same construction as plantos_env.py:338-372 with Philox draws
-        for (int idx = lane; idx < nwords; idx += 32) {
+        for (int idx = lane; idx < (clusters ? nwords : 0); idx += 32) {
             const int w = idx % W;
             plane[idx] = kObstAll & ~col_mask(G, w);     // only the beyond-grid padding
         }
         __syncwarp();
-        const long long genv = p.env_base + e;
-        for (int k = lane; k < p.nclusters; k += 32) {   // :343-354, one cluster per lane
+        for (int k = lane; k < (clusters ? p.nclusters : 0); k += 32) {   // :343-354, one cluster per lane
             uint32_t d[4];
             map_draw(p, genv, mep, 0, (uint32_t)k, d);
             const int cx = 2 + (int)bounded(d[0], (uint32_t)(G - 4));   // randint(2, G-3)
@@ -324,6 +430,9 @@ __device__ __forceinline__ int curriculum_on_reset(const Params& p, int e, int e
 }
 
 // -------------------------------------------------- one env, one warp (any config)
+// MAZE = false (tails of the specialised kernels): no maze generator in the instantiation; a finished env of a
+// maze handle keeps its terminal record and k_reset_done starts its new episode.
+template <bool MAZE = true>
 __device__ __forceinline__ void step_env_warp(const Params& p, const Tables& t, const StepIO& io, int e,
                                               uint64_t* plane, float* obs_s, int lane) {
     uint4 ra = make_uint4(0, 0, 0, 0), rb = ra;
@@ -401,17 +510,19 @@ __device__ __forceinline__ void step_env_warp(const Params& p, const Tables& t, 
         accumulate_stats(p, lane == 0, r, (flagw >> 17) & 1, (flagw >> 18) & 1, lane, e);
         episode = __shfl_sync(0xffffffffu, episode, 0);
         __syncwarp();
-        int keep = 0, map_ep = -1;
-        if (p.cur_mode) {
-            int cr = 0;
-            if (lane == 0) cr = curriculum_on_reset(p, e, episode);
-            cr = __shfl_sync(0xffffffffu, cr, 0);
-            keep = cr & 1; map_ep = cr >> 1;
-        }
-        const EnvRec nr = reset_env_warp(p, e, episode, plane, lane, keep != 0, map_ep);
-        build_obs_warp(p, t, plane, vis_e, nr.x, nr.y, obs_s, lane, keep != 0);
-        store_obs_row(obs_s, obs_row, p.D, lane);
-        if (lane == 0) pack_rec(nr, ra, rb);
+        if (MAZE || p.map_source != 2) {
+            int keep = 0, map_ep = -1;
+            if (p.cur_mode) {
+                int cr = 0;
+                if (lane == 0) cr = curriculum_on_reset(p, e, episode);
+                cr = __shfl_sync(0xffffffffu, cr, 0);
+                keep = cr & 1; map_ep = cr >> 1;
+            }
+            const EnvRec nr = reset_env_warp<MAZE>(p, e, episode, plane, lane, keep != 0, map_ep);
+            build_obs_warp(p, t, plane, vis_e, nr.x, nr.y, obs_s, lane, keep != 0);
+            store_obs_row(obs_s, obs_row, p.D, lane);
+            if (lane == 0) pack_rec(nr, ra, rb);
+        }                                                 // (else: the terminal record stays; k_reset_done takes over)
     }
     if (lane == 0) {
         p.rec[2 * (size_t)e] = ra;
@@ -462,6 +573,48 @@ k_reset_all(const Params p, float* obs) {
             p.rec[2 * (size_t)e + 1] = rb;
         }
         __syncwarp();
+    }
+}
+
+// Deferred auto-reset (maze handles on the specialised kernels): the step kernel has written the terminal
+// record, flags and terminal observation of every finished env but left its episode running; this kernel
+// starts the new episodes (map, fresh observation into io.obs, record, window ring cache).  One warp per 32
+// envs scans their done flags.
+__global__ void __launch_bounds__(kGenericWarps * 32)
+k_reset_done(const Params p, const StepIO io) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Tables t = load_tables(p, smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* scratch = smem + tables_bytes(p.G, p.R, p.C) + warp * generic_warp_scratch_bytes(p.G, p.W, p.D);
+    uint64_t* plane = reinterpret_cast<uint64_t*>(scratch);
+    float* obs_s = reinterpret_cast<float*>(scratch + align_up(p.G * p.W * 8, 16));
+    for (int e0 = (blockIdx.x * kGenericWarps + warp) * 32; e0 < p.N; e0 += gridDim.x * kGenericWarps * 32) {
+        unsigned dmask = __ballot_sync(0xffffffffu, e0 + lane < p.N && io.done[e0 + lane] != 0);
+        while (dmask) {
+            const int e = e0 + __ffs(dmask) - 1;
+            dmask &= dmask - 1;
+            int episode = 0;
+            if (lane == 0) episode = (int)p.rec[2 * (size_t)e].w;
+            episode = __shfl_sync(0xffffffffu, episode, 0);
+            int keep = 0, map_ep = -1;
+            if (p.cur_mode) {
+                int cr = 0;
+                if (lane == 0) cr = curriculum_on_reset(p, e, episode);
+                cr = __shfl_sync(0xffffffffu, cr, 0);
+                keep = cr & 1; map_ep = cr >> 1;
+            }
+            const EnvRec nr = reset_env_warp<true>(p, e, episode, plane, lane, keep != 0, map_ep);
+            build_obs_warp(p, t, plane, p.vis4 + (size_t)e * p.VE, nr.x, nr.y, obs_s, lane, true);
+            store_obs_row(obs_s, io.obs + (size_t)e * p.D, p.D, lane);
+            wrc_build_env_fresh_warp(p, (size_t)e, nr.x, nr.y, plane, keep != 0, lane, 0u);
+            if (lane == 0) {
+                uint4 ra, rb;
+                pack_rec(nr, ra, rb);
+                p.rec[2 * (size_t)e] = ra;
+                p.rec[2 * (size_t)e + 1] = rb;
+            }
+            __syncwarp();
+        }
     }
 }
 

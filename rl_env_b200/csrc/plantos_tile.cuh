@@ -612,6 +612,7 @@ k_tile(const Params p, const RollIO io) {
             __syncwarp();
             dmask = dmask0;
         }
+        if (p.map_source == 2) dmask = 0u;                   // maze handles: k_reset_done starts the new episodes after this launch
         while (dmask) {
             const int j = __ffs(dmask) - 1;
             dmask &= dmask - 1;
@@ -624,7 +625,7 @@ k_tile(const Params p, const RollIO io) {
                 cr = __shfl_sync(FULL, cr, 0);
                 keep = cr & 1; map_ep = cr >> 1;
             }
-            const EnvRec nr = reset_env_warp(p, (int)ej, ep, plane, lane, keep != 0, map_ep);
+            const EnvRec nr = reset_env_warp<false>(p, (int)ej, ep, plane, lane, keep != 0, map_ep);
             // (fresh visit window: what the planes hold after a plain reset, and what the wrapper's reset
             // observation shows when the counts are kept)
             build_obs_warp(p, tabs(), plane, p.vis4 + ej * VE, nr.x, nr.y, row_s, lane, true);
@@ -672,7 +673,7 @@ k_tile(const Params p, const RollIO io) {
             sio.actions = io.actions + ko; sio.obs = io.obs + (size_t)k * io.obs_stride; sio.reward = io.reward + ko;
             sio.done = io.done + ko; sio.terminated = io.terminated ? io.terminated + ko : nullptr;
             sio.truncated = io.truncated ? io.truncated + ko : nullptr; sio.terminal_obs = io.terminal_obs;
-            for (int e = nfull; e < p.N; ++e) step_env_warp(p, tabs(), sio, e, plane, row_s, lane);
+            for (int e = nfull; e < p.N; ++e) step_env_warp<false>(p, tabs(), sio, e, plane, row_s, lane);
         }
 }
 

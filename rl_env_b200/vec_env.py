@@ -148,8 +148,8 @@ class PlantOSVecEnv:
             raise ValueError("PlantOSVecEnv runs on a CUDA device only (no CPU path)")
         if not torch.cuda.is_available():
             raise RuntimeError("PlantOSVecEnv needs a CUDA device; torch.cuda.is_available() is False")
-        if map_source not in ("philox", "injected"):
-            raise ValueError("map_source must be 'philox' or 'injected'")
+        if map_source not in ("philox", "injected", "maze"):
+            raise ValueError("map_source must be 'philox', 'injected' or 'maze'")
         self._lib = nat.load()
         self.num_envs = int(num_envs)
         self.grid_size, self.num_plants, self.num_obstacles = int(grid_size), int(num_plants), int(num_obstacles)
@@ -172,7 +172,8 @@ class PlantOSVecEnv:
         cfg.lidar_range, cfg.lidar_channels = self.lidar_range, self.lidar_channels
         cfg.max_steps = self.max_steps
         cfg.thirsty_plant_prob = self.thirsty_plant_prob
-        cfg.map_source = nat.MAPS_INJECTED if map_source == "injected" else nat.MAPS_PHILOX
+        # "maze": the Gradio fork's maze generator (gradio-app/plantos_env_new.py:408-604) on the device
+        cfg.map_source = {"philox": nat.MAPS_PHILOX, "injected": nat.MAPS_INJECTED, "maze": nat.MAPS_MAZE}[map_source]
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         for key, val in self.rewards.items():
             setattr(cfg, key, float(val))

@@ -72,17 +72,6 @@ def test_device_curriculum_replays_reference_wrapper(name, kernel, replicas):
         be.env.set_state(cells=torch.zeros(1))                 # refused while a curriculum is active
 
 
-@pytest.mark.parametrize("name,replicas", [("replay_T_8env", 13), ("replay_DFLT_1env", 70), ("replay_odd_4env", 40)])
-def test_lane_kernel_replays_reference(name, replicas, monkeypatch):
-    """The experimental lane-per-env kernel (PLANTOS_FAST_IMPL=lane, compile-time LIDAR offsets)
-    replays the reference trajectories bit-exactly too."""
-    monkeypatch.setenv("PLANTOS_FAST_IMPL", "lane")
-    if name not in FAST_FIXTURES:
-        pytest.skip("shape has no fast instantiation")
-    res = _run(name, "fast", replicas=replicas)
-    assert res["bitexact_obs"] == 1 and res["bitexact_reward"] == 1
-
-
 @pytest.mark.parametrize("impl", ["tile", "trip"])
 @pytest.mark.parametrize("grid,replicas", [(1, 60), (2, 60), (1, 24), (5, 100), (1, 200), (2, 131)])
 def test_fast_kernel_buffer_reuse(grid, replicas, impl, monkeypatch):

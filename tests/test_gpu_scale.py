@@ -141,6 +141,57 @@ def test_philox_maps_match_host_mirror_and_sharding():
     a.close(); b.close()
 
 
+def test_device_maze_maps_match_host_mirror_and_lockstep():
+    """map_source="maze": the Gradio fork's maze generator (gradio-app/plantos_env_new.py:408-604) on the device.
+    (1) The maps are bit-identical to the host mirror (oracle.philox_mapgen.generate_maze_map), episode after
+    episode, on the fast and the generic kernel, for the training preset and for a 64x64 grid (10x10 meta grid).
+    (2) Lock-step against the C oracle on those maps (read back after every reset) -- long corridors and rooms
+    are a different LIDAR workload than the cluster maps."""
+    from oracle.c_oracle import COracle
+    from oracle.philox_mapgen import generate_maze_map
+    from rl_env_b200 import PlantOSVecEnv
+    for kw, kernel, n in ((T_KW, "fast", 8), (T_KW, "generic", 8), (XL_KW, "generic", 4)):
+        env = PlantOSVecEnv(n, seed=77, env_id_base=3, max_steps=4, map_source="maze", kernel=kernel, **kw)
+        env.reset()
+        for episode in range(3):
+            st = env.get_state()
+            cells, xs, ys = st["cells"].cpu().numpy(), st["x"].cpu().numpy(), st["y"].cpu().numpy()
+            for i in range(n):
+                want_cells, want_rover = generate_maze_map(77, 3 + i, episode, kw["grid_size"], kw["num_plants"], kw["num_obstacles"])
+                assert np.array_equal(cells[i], want_cells), (kernel, i, episode)
+                assert (xs[i], ys[i]) == want_rover
+            for _ in range(4):
+                env.step(np.full(n, 4, np.int64))
+        env.check(); env.close()
+    n, steps, max_steps = 2048, 90, 30
+    kw = T_KW
+    env = PlantOSVecEnv(n, seed=5, max_steps=max_steps, map_source="maze", kernel="fast", **kw)
+    ora = COracle(n, kw["grid_size"], kw["num_plants"], kw["num_obstacles"], kw["lidar_range"], kw["lidar_channels"], max_steps)
+    obs = env.reset().cpu().numpy()
+    st = env.get_state()
+    cells, xs, ys = st["cells"].cpu().numpy(), st["x"].cpu().numpy(), st["y"].cpu().numpy()
+    for i in range(n):
+        ora.reset_one(i, cells[i], (xs[i], ys[i]))
+    assert np.array_equal(obs.view(np.uint32), ora.obs.view(np.uint32))
+    free = (cells != 1).reshape(n, -1).sum(1)
+    assert 400 < free.mean() < 600                         # 16 rooms + corridors on 625 cells: ~16 % walls in long straight runs
+    rng = np.random.default_rng(2)
+    for t in range(steps):
+        a = rng.integers(0, 5, size=n).astype(np.int64)
+        g_obs, g_rew, g_done, _ = env.step(a)
+        o_obs, o_rew, o_term, o_trunc = ora.step(a)
+        done = o_term | o_trunc
+        assert np.array_equal(g_done.cpu().numpy(), done), t
+        assert np.array_equal(g_rew.cpu().numpy(), o_rew.astype(np.float32)), t
+        if done.any():
+            st = env.get_state()
+            cells, xs, ys = st["cells"].cpu().numpy(), st["x"].cpu().numpy(), st["y"].cpu().numpy()
+            for i in np.nonzero(done)[0]:
+                ora.reset_one(int(i), cells[i], (xs[i], ys[i]))
+        assert np.array_equal(g_obs.cpu().numpy().view(np.uint32), ora.obs.view(np.uint32)), t
+    env.check(); env.close()
+
+
 def test_philox_maps_distribution_matches_reference_generator():
     """Same construction => same distribution: compare the device's maps with maps drawn by the
     Python port of the reference generator (global `random`, plantos_env.py:338-372)."""
@@ -237,14 +288,14 @@ def test_full_size_properties_and_kernel_agreement():
 
 @pytest.mark.parametrize("kernel", ["fast", "generic"])
 def test_maze_maps_injected_lockstep(kernel):
-    """Maps from the host-side maze generator (rl_env_b200.maps, the Gradio fork's 'maze' algorithm:
+    """Maps from the host-side maze generator (oracle.ref_maps, the Gradio fork's 'maze' algorithm:
     corridors and rooms, a much denser LIDAR workload than the cluster maps) pushed as recorded maps:
     the device and the restated reference env agree step by step, auto-resets included."""
     import random
     import torch
     from oracle.plantos_oracle import OracleVecEnv
     from rl_env_b200 import PlantOSVecEnv
-    from rl_env_b200.maps import make_maps
+    from oracle.ref_maps import make_maps
     n, episodes, steps = 36, 6, 260
     random.seed(12)
     cells, rover = make_maps("maze", n, episodes, T_KW["grid_size"], T_KW["num_plants"], T_KW["num_obstacles"])

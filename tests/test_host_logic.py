@@ -58,12 +58,12 @@ def test_philox_mirror_builds_valid_maps_like_the_reference_generator():
 
 
 def test_maze_maps_are_connected_and_well_formed():
-    """Host-side maze generator (rl_env_b200.maps, the Gradio fork's 'maze' algorithm): every free cell
+    """Host-side maze generator (oracle.ref_maps, the Gradio fork's 'maze' algorithm): every free cell
     is reachable from the rover (the DFS carves one connected system of rooms), plant count and codes
     are right, the rover stands on an empty cell."""
     import random
     from collections import deque
-    from rl_env_b200.maps import make_maps
+    from oracle.ref_maps import make_maps
     random.seed(4)
     cells, rover = make_maps("maze", 3, 4, grid_size=25, num_plants=10, num_obstacles=12)
     assert cells.shape == (3, 4, 25, 25) and rover.shape == (3, 4, 2)
@@ -82,3 +82,40 @@ def test_maze_maps_are_connected_and_well_formed():
                     if 0 <= nx < 25 and 0 <= ny < 25 and free[nx, ny] and not seen[nx, ny]:
                         seen[nx, ny] = True; queue.append((nx, ny))
             assert seen.sum() == free.sum()
+
+
+def test_philox_maze_mirror_matches_the_forks_generator_in_distribution():
+    """oracle.philox_mapgen.generate_maze_map (the host mirror of the device's map_source="maze" reset) against
+    the restated generator of the Gradio fork (oracle.ref_maps.maze_map == gradio-app/plantos_env_new.py:408-604,
+    pinned to the fork in test_oracle_vs_reference.py): same construction, different random stream -> same
+    statistics.  Free-cell count (mean and spread), per-cell free marginal, solid outer ring, 100 % connectivity,
+    plant count and thirsty fraction."""
+    import random
+    from collections import deque
+    from oracle.philox_mapgen import generate_maze_map
+    from oracle.ref_maps import maze_map
+    g, n = 25, 300
+    random.seed(11)
+    ref = [maze_map(g, 10, 12)[0] for _ in range(n)]
+    got = [generate_maze_map(1234, 7 + i, i % 5, g, 10, 12) for i in range(n)]
+    ref_free = np.array([(c != 1).sum() for c in ref]); got_free = np.array([(c != 1).sum() for c, _ in got])
+    assert abs(ref_free.mean() - got_free.mean()) < 4.0 and abs(ref_free.std() - got_free.std()) < 3.0
+    marg_ref = np.mean([(c != 1) for c in ref], axis=0); marg_got = np.mean([(c != 1) for c, _ in got], axis=0)
+    assert np.abs(marg_ref - marg_got).max() < 0.15
+    thirsty = np.mean([(c == 3).sum() for c, _ in got]) / 10
+    assert abs(thirsty - 0.7) < 0.05
+    for c, (rx, ry) in got:
+        assert c[rx, ry] == 0 and int(((c == 2) | (c == 3)).sum()) == 10
+        free = c != 1
+        seen = np.zeros_like(free); seen[rx, ry] = True
+        queue = deque([(rx, ry)])
+        while queue:
+            x, y = queue.popleft()
+            for dx, dy in ((-1, 0), (0, 1), (1, 0), (0, -1)):
+                nx, ny = x + dx, y + dy
+                if 0 <= nx < g and 0 <= ny < g and free[nx, ny] and not seen[nx, ny]:
+                    seen[nx, ny] = True; queue.append((nx, ny))
+        assert seen.sum() == free.sum()                                    # one connected system of rooms
+    # a grid too small for a single room falls back to the cluster generator, like the fork (:463-467)
+    small, _ = generate_maze_map(5, 0, 0, 6, 2, 3)
+    assert (small != 1).sum() > 20

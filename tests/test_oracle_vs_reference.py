@@ -135,12 +135,12 @@ def test_curriculum_port_matches_the_reference_wrapper_class(variant, init, max_
 
 @pytest.mark.parametrize("algo", ["maze", "original"])
 def test_host_map_generators_equal_the_gradio_fork(algo):
-    """rl_env_b200.maps (host-side generators for map injection) against `_generate_map` of the Gradio
+    """oracle.ref_maps (host-side generators for map injection) against `_generate_map` of the Gradio
     fork's env class (gradio-app/plantos_env_new.py:353-604) with the same `random.seed`: same obstacle /
     plant / rover cells and the same number of RNG draws."""
     import importlib, os, sys, types
     from oracle import ref_shim
-    from rl_env_b200.maps import maze_map, original_map
+    from oracle.ref_maps import maze_map, original_map
     fork_dir = os.path.join(ref_shim.REFERENCE_DIR, "gradio-app")
     if not os.path.isfile(os.path.join(fork_dir, "plantos_env_new.py")):
         pytest.skip("fork not in the checkout")

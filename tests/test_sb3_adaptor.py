@@ -136,7 +136,9 @@ def test_adaptor_matches_dummyvecenv_monitor_on_the_device():
     assert ndone >= 2
     # max_steps is a plain attribute of the reference env (plantos_env.py:120): changing it takes effect
     venv.set_attr("max_steps", 3)
+    seen = np.zeros(4, bool)
     for t in range(600, 612):
         _, _, done, _ = venv.step(fx["actions"][t])
-    assert done.any()
+        seen |= done
+    assert seen.all()                                          # every env truncates within the new 3-step horizon
     venv.close()
