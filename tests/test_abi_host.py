@@ -97,7 +97,7 @@ def test_validation_and_loud_failure_without_gpu():
     lib, cfg = _cfg(21, 8, 50, 2, 10)
     h = C.c_void_p()
     bad = [("grid_size", 4), ("grid_size", 129), ("lidar_range", 0), ("lidar_channels", 65), ("max_steps", 70000),
-           ("num_envs", 0), ("num_plants", 100), ("map_source", 2), ("kernel", 9), ("struct_size", 8)]
+           ("num_envs", 0), ("num_plants", 100), ("map_source", 3), ("kernel", 9), ("struct_size", 8)]
     for field, val in bad:
         _, c2 = _cfg(21, 8, 50, 2, 10)
         setattr(c2, field, val)
