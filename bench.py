@@ -262,6 +262,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # the rank's thread and its pinned host buffers go to the NUMA node of its GPU (matters for the
+    # host-buffer e2e path when several ranks copy 57 MB per step at the same time)
+    from rl_env_b200.affinity import bind_to_gpu
+    placement = bind_to_gpu(local_rank) if not args.no_numa_bind else {"numa_node": None, "cpus": None, "mempolicy": False}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = args.envs_per_gpu
@@ -442,7 +446,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * (4 * OBS_DIM + 4 + 1),
                     "steps": e2e_steps, "api": "plantos_step_host (pinned host buffers), one call per step and GPU; bytes are per GPU, "
                                                "value is the aggregate over all GPUs (max over ranks of the wall time)",
-                    "ms_per_step_by_rank": [round(m / e2e_steps, 4) for m in per_rank_e2e]},
+                    "ms_per_step_by_rank": [round(m / e2e_steps, 4) for m in per_rank_e2e],
+                    "host_placement_rank0": placement},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
@@ -489,6 +494,7 @@ def main():
     ap.add_argument("--no-pipeline", action="store_true", help="full grid-wide dependency between consecutive step launches (graph / eager loops)")
     ap.add_argument("--no-stagger", action="store_true", help="all envs start at step 0 (no auto-reset before step 1000)")
     ap.add_argument("--no-step-launch", action="store_true", help="skip the single-launch-per-step side measurements")
+    ap.add_argument("--no-numa-bind", action="store_true", help="leave CPU affinity and memory policy as inherited")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.no_graph:

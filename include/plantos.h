@@ -82,7 +82,14 @@ typedef struct plantos_config {
     double  r_goal, r_mistake, r_invalid, r_water_empty, r_step,
             r_exploration, r_revisit, r_complete_exploration;
     int32_t kernel;             /* PLANTOS_KERNEL_* */
-    int32_t reserved[7];
+    /* Tuning / test knobs, all 0 by default (they never change results): */
+    int32_t tune_fast_grid;     /* > 0: number of thread blocks of the specialised kernels' persistent grid */
+    int32_t tune_fast_impl;     /* 0: k_step_tile (lane-per-env tiles); 1: k_step_fast (round 1's table-driven kernel, also
+                                   the fallback for caller-supplied LIDAR offsets); 2: k_step_lane when the library was
+                                   built with it */
+    int32_t tune_no_pdl;        /* != 0: plain launches instead of programmatic dependent launches */
+    int32_t tune_l2_keep_mb;    /* > 0: k_step_fast tags state accesses L2::evict_last inside a persisting set-aside of that size */
+    int32_t reserved[3];
 } plantos_config_t;
 
 typedef struct plantos plantos_t;

@@ -34,7 +34,8 @@ class Config(C.Structure):
         ("r_goal", C.c_double), ("r_mistake", C.c_double), ("r_invalid", C.c_double),
         ("r_water_empty", C.c_double), ("r_step", C.c_double), ("r_exploration", C.c_double),
         ("r_revisit", C.c_double), ("r_complete_exploration", C.c_double),
-        ("kernel", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("kernel", C.c_int32), ("tune_fast_grid", C.c_int32), ("tune_fast_impl", C.c_int32),
+        ("tune_no_pdl", C.c_int32), ("tune_l2_keep_mb", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 

@@ -160,6 +160,8 @@ static int validate(const plantos_config_t* c) {
         return fail(PLANTOS_EINVAL, "map_source must be PLANTOS_MAPS_PHILOX, PLANTOS_MAPS_INJECTED or PLANTOS_MAPS_MAZE");
     if (c->kernel < PLANTOS_KERNEL_AUTO || c->kernel > PLANTOS_KERNEL_FAST)
         return fail(PLANTOS_EINVAL, "kernel must be one of PLANTOS_KERNEL_*");
+    if (c->tune_fast_grid < 0 || c->tune_fast_impl < 0 || c->tune_fast_impl > 2 || c->tune_l2_keep_mb < 0)
+        return fail(PLANTOS_EINVAL, "tune_* fields out of range");
     return PLANTOS_OK;
 }
 
@@ -338,8 +340,7 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
         // set-aside.  Off by default: with the compact state layout the plain LRU already keeps
         // the state resident (steady-state DRAM reads ~16 MB per 131 072-env step), and the
         // set-aside measured neutral to slightly negative (profiles/r1_summary.md).
-        int keep = 0;
-        if (const char* s = std::getenv("PLANTOS_L2_KEEP")) keep = std::atoi(s) ? 1 : 0;
+        int keep = cfg->tune_l2_keep_mb > 0 ? 1 : 0;
         p.l2_keep = keep;
         if (keep) {
             // evict_last lines only persist inside the persisting-L2 set-aside, which is 0 by
@@ -347,7 +348,7 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
             // slightly, 64 MB and more slows the step down by 40 %, so stay at 56 MB.
             size_t want = (size_t)56 << 20;
             if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
-            if (const char* s = std::getenv("PLANTOS_L2_PERSIST_MB")) want = (size_t)std::atoi(s) << 20;
+            want = (size_t)cfg->tune_l2_keep_mb << 20;
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
         }
         for (const FastVariant& v : kFastVariants)
@@ -373,7 +374,7 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
         // experimental lane-per-env kernel (k_step_lane) instead of k_step_fast.
         auto shape = [&](FastLaunch& L, int warps, int blocks_per_sm, int smem) {
             long long blocks = (long long)h->num_sms * blocks_per_sm;
-            if (const char* s = std::getenv("PLANTOS_FAST_GRID")) { const int v = std::atoi(s); if (v > 0) blocks = v; }
+            if (cfg->tune_fast_grid > 0) blocks = cfg->tune_fast_grid;
             const long long need = ((long long)p.N / 8 + warps - 1) / warps;
             if (blocks > need) blocks = need;
             L.grid = (int)(blocks < 1 ? 1 : blocks);
@@ -393,7 +394,7 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
             const long long ntiles = (((long long)p.N & ~3LL) + 31) / 32;
             long long blocks = (ntiles + kTileWarps - 1) / kTileWarps;
             if (blocks > (long long)h->num_sms * PLANTOS_TILE_MINBLOCKS) blocks = (long long)h->num_sms * PLANTOS_TILE_MINBLOCKS;
-            if (const char* s = std::getenv("PLANTOS_FAST_GRID")) { const int v = std::atoi(s); if (v > 0 && v < blocks) blocks = v; }
+            if (cfg->tune_fast_grid > 0 && cfg->tune_fast_grid < blocks) blocks = cfg->tune_fast_grid;
             L.grid = (int)(blocks < 1 ? 1 : blocks);
             L.threads = kTileWarps * 32; L.smem = tile_block_smem_bytes(p.R, p.G, p.C); L.q = 32;
             h->rollout_smem = tile_block_smem_bytes_multi(p.R, p.G, p.C);
@@ -412,12 +413,9 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
         }
         h->prefer_lane = false;
         h->impl = 0;
-        if (const char* s = std::getenv("PLANTOS_FAST_IMPL")) {
-            h->prefer_lane = std::strcmp(s, "lane") == 0;
-            h->impl = std::strcmp(s, "trip") == 0 ? 1 : (h->prefer_lane ? 2 : 0);
-        }
-        h->use_pdl = true;
-        if (const char* s = std::getenv("PLANTOS_PDL")) h->use_pdl = std::atoi(s) != 0;
+        h->impl = cfg->tune_fast_impl;                       // 0 k_step_tile, 1 k_step_fast, 2 k_step_lane (if built)
+        h->prefer_lane = h->impl == 2;
+        h->use_pdl = cfg->tune_no_pdl == 0;
     }
     cudaError_t e1 = cudaFuncSetAttribute(k_step_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);
     cudaError_t e2 = cudaFuncSetAttribute(k_reset_all, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);

@@ -13,6 +13,7 @@ Everything is computed by libplantos_b200.so (include/plantos.h) -- there is no 
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 from typing import Any, Dict, List, Optional, Sequence
 
@@ -142,7 +143,8 @@ class PlantOSVecEnv:
                  env_id_base: int = 0, kernel: str = "auto",
                  rewards: Optional[Dict[str, float]] = None,
                  track_terminal_obs: bool = True, full_infos: Optional[bool] = None,
-                 obs_ring: int = 1, curriculum: Any = None, info_keywords: Sequence[str] = ()):
+                 obs_ring: int = 1, curriculum: Any = None, info_keywords: Sequence[str] = (),
+                 tuning: Optional[Dict[str, int]] = None):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("PlantOSVecEnv runs on a CUDA device only (no CPU path)")
@@ -178,6 +180,18 @@ class PlantOSVecEnv:
         for key, val in self.rewards.items():
             setattr(cfg, key, float(val))
         cfg.kernel = _KERNELS[kernel]
+        # tuning / test knobs of plantos_config_t (never change results): fast_grid, fast_impl ("tile" | "trip" |
+        # "lane"), no_pdl, l2_keep_mb.  The PLANTOS_FAST_GRID / PLANTOS_FAST_IMPL / PLANTOS_PDL / PLANTOS_L2_PERSIST_MB
+        # environment variables of round 1's experiments are honoured HERE (the C library reads no environment).
+        tune = {"fast_grid": int(os.environ.get("PLANTOS_FAST_GRID", "0") or 0),
+                "fast_impl": os.environ.get("PLANTOS_FAST_IMPL", "tile") or "tile",
+                "no_pdl": 1 if os.environ.get("PLANTOS_PDL", "1") == "0" else 0,
+                "l2_keep_mb": int(os.environ.get("PLANTOS_L2_PERSIST_MB", "0") or 0) if os.environ.get("PLANTOS_L2_KEEP", "0") == "1" else 0}
+        tune.update(tuning or {})
+        cfg.tune_fast_grid = int(tune["fast_grid"])
+        cfg.tune_fast_impl = {"tile": 0, "trip": 1, "lane": 2}.get(tune["fast_impl"], tune["fast_impl"]) if isinstance(tune["fast_impl"], str) else int(tune["fast_impl"])
+        cfg.tune_no_pdl = int(tune["no_pdl"])
+        cfg.tune_l2_keep_mb = int(tune["l2_keep_mb"])
         self._cfg = cfg
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.device = torch.device("cuda", dev_index)
@@ -335,7 +349,7 @@ class PlantOSVecEnv:
     def step_many(self, actions, with_flags: bool = False):
         """K open-loop steps in ONE call (plantos_rollout): `actions` int64 [K, N] -> obs [K, N, D],
         rewards [K, N], dones [K, N] (+ terminated, truncated [K, N] with `with_flags`); the tensors
-        are reused by the next call with the same K.  Bit-identical to K `step` calls, auto-resets
+        are reused by the next call with the same K (one buffer set per K is kept).  Bit-identical to K `step` calls, auto-resets
         included.  On the fast presets the K steps are one launch of the state-resident kernel (the
         envs' window rings and records never leave the SM between steps) -- the GPU form of the
         reference's MCTS rollout loop (mcts_custom_trainer.py:139-166)."""
@@ -345,8 +359,10 @@ class PlantOSVecEnv:
         if actions.dim() != 2 or actions.shape[1] != self.num_envs:
             raise ValueError(f"expected actions of shape [K, {self.num_envs}], got {tuple(actions.shape)}")
         k, n, d, dev = int(actions.shape[0]), self.num_envs, self.obs_dim, self.device
-        buf = getattr(self, "_many", None)
-        if buf is None or buf["k"] != k:
+        if not hasattr(self, "_many"):
+            self._many = {}                                # one buffer set per rollout length
+        buf = self._many.get(k)
+        if buf is None:
             stride = (n * d + 3) // 4 * 4                  # per-step stride padded to 16 bytes
             buf = {"k": k, "stride": stride,
                    "obs": torch.empty(k * stride, dtype=torch.float32, device=dev),
@@ -354,7 +370,7 @@ class PlantOSVecEnv:
                    "done": torch.zeros((k, n), dtype=torch.bool, device=dev),
                    "term": torch.zeros((k, n), dtype=torch.bool, device=dev),
                    "trunc": torch.zeros((k, n), dtype=torch.bool, device=dev)}
-            self._many = buf
+            self._many[k] = buf
         tobs = self._terminal_obs.data_ptr() if self._terminal_obs is not None else None
         nat.check(self._lib.plantos_rollout(
             self._h, k, actions.data_ptr(), buf["obs"].data_ptr(), buf["stride"], buf["rew"].data_ptr(),
