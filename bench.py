@@ -40,9 +40,28 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ENVS_PER_GPU = 131072
-PRESET = dict(grid_size=25, num_plants=10, num_obstacles=12, lidar_range=6, lidar_channels=16)
+# --preset: "training" is the headline workload (BASELINE.json configs[3]); "default" = the reference ctor's
+# defaults (configs[0]'s env at batch size); "xl" = configs[4], the 64x64 / range-32 stress map with a 100-step
+# horizon (reset-heavy), 32 768 envs per GPU
+PRESETS = {
+    "training": (dict(grid_size=25, num_plants=10, num_obstacles=12, lidar_range=6, lidar_channels=16), 131072, 1000,
+                 "PlantOS training preset G25/P10/O12/R6/C16"),
+    "default": (dict(grid_size=21, num_plants=8, num_obstacles=50, lidar_range=2, lidar_channels=10), 131072, 1000,
+                "PlantOS ctor-default preset G21/P8/O50/R2/C10"),
+    "xl": (dict(grid_size=64, num_plants=64, num_obstacles=600, lidar_range=32, lidar_channels=16), 32768, 100,
+           "PlantOS XL stress preset G64/P64/O600/R32/C16, max_steps 100"),
+}
+PRESET, _, MAX_STEPS, PRESET_LABEL = PRESETS["training"]
 OBS_DIM = 5 * PRESET["lidar_channels"] + 27
 B_ALG = 4 * OBS_DIM + 4 + 1 + 8          # obs f32[D] + reward f32 + done u8 + action i64
+
+
+def select_preset(name: str, envs_per_gpu):
+    global PRESET, ENVS_PER_GPU, MAX_STEPS, PRESET_LABEL, OBS_DIM, B_ALG
+    PRESET, default_envs, MAX_STEPS, PRESET_LABEL = PRESETS[name]
+    ENVS_PER_GPU = int(envs_per_gpu) if envs_per_gpu else default_envs
+    OBS_DIM = 5 * PRESET["lidar_channels"] + 27
+    B_ALG = 4 * OBS_DIM + 4 + 1 + 8
 ACTION_RING = 16                          # steps per rollout call / per replayed graph
 ACTION_POOL = 4                           # distinct [16, N] action blocks the timed loop cycles through (64 i.i.d. vectors)
 OBS_RING = 5                              # rollout-buffer depth (A2C n_steps=5, A2C_training.py:229-247)
@@ -51,7 +70,7 @@ UNIT = "env-steps/s"
 
 
 def workload_name(n_gpus: int) -> str:
-    return (f"PlantOS training preset G25/P10/O12/R6/C16 (D=107), {ENVS_PER_GPU} envs/GPU x {n_gpus} GPU "
+    return (f"{PRESET_LABEL} (D={OBS_DIM}), {ENVS_PER_GPU} envs/GPU x {n_gpus} GPU "
             f"= {ENVS_PER_GPU * n_gpus} envs, fused step+LIDAR obs+auto-reset, random actions, staggered episode phases")
 
 
@@ -84,7 +103,7 @@ def _cpu_worker(conn, n_envs, seed, literal_trig):
     from oracle.plantos_oracle import OracleVecEnv
     random.seed(seed)
     rng = np.random.default_rng(seed)
-    env = OracleVecEnv(n_envs, literal_trig=literal_trig, **PRESET)
+    env = OracleVecEnv(n_envs, literal_trig=literal_trig, max_steps=MAX_STEPS, **PRESET)
     env.reset()
     conn.send("ready")
     while True:
@@ -270,7 +289,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.init_process_group("nccl", device_id=dev)
     n = args.envs_per_gpu
     env = make_sharded(n * world, rank, world, local_device=local_rank, seed=0, kernel=args.kernel,
-                       obs_ring=OBS_RING, track_terminal_obs=not args.no_terminal_obs, full_infos=False, **PRESET)
+                       obs_ring=OBS_RING, track_terminal_obs=not args.no_terminal_obs, full_infos=False,
+                       max_steps=MAX_STEPS, **PRESET)
     assert env.num_envs == n and env.obs_dim == OBS_DIM
     gen = torch.Generator(device=dev).manual_seed(rank)
     # ACTION_POOL blocks of ACTION_RING i.i.d. action vectors (the timed loop cycles through the blocks)
@@ -305,32 +325,41 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         stats_every = max(ACTION_RING, min(args.stats_every, max(1, args.steps // 2)) // ACTION_RING * ACTION_RING)
     counters = {"stats": 0, "launches": 0}
 
+    # chunks: ACTION_RING steps per rollout call / graph replay; a remainder shorter than ACTION_RING rides on
+    # the last chunk (rollout loop: one call of up to 2 * ACTION_RING - 1 steps), so that a short timed region
+    # (--steps 20) is ONE call, not a 16-step call plus a 4-step call with a host round trip in between
+    pool2 = [torch.cat([pool[b], pool[(b + 1) % ACTION_POOL]]) for b in range(ACTION_POOL)]   # [2 * ACTION_RING, n] each
+
     def run_steps(k, start):
-        """k consecutive steps, numbered from `start` (the block of actions follows the step number)."""
-        i, end = start, start + k
-        while i < end:
-            blk, off = pool[(i // ACTION_RING) % ACTION_POOL], i % ACTION_RING
-            m = min(ACTION_RING - off, end - i)
+        """k consecutive steps; `start` only selects which pre-generated action blocks are used."""
+        i = 0
+        while i < k:
+            m = k - i if k - i < 2 * ACTION_RING else ACTION_RING
+            b = ((start + i) // ACTION_RING) % ACTION_POOL
             if loop == "rollout":
-                env.step_many(blk[off:off + m], with_flags=True)   # ONE plantos_rollout call: m steps
+                env.step_many(pool2[b][:m], with_flags=True)        # ONE plantos_rollout call: m steps
                 counters["launches"] += 1
-            elif loop == "graph" and m == ACTION_RING:
-                roll.actions.copy_(blk, non_blocking=True)           # (1 MB device copy per 16 steps, inside the timed region)
+            elif loop == "graph" and m >= ACTION_RING:
+                roll.actions.copy_(pool[b], non_blocking=True)       # (1 MB device copy per 16 steps, inside the timed region)
                 roll.graph.replay()
                 counters["launches"] += ACTION_RING
+                m = ACTION_RING
             else:
-                for t in range(off, off + m):
-                    env.step_async(blk[t])
+                for t in range(m):
+                    env.step_async(pool2[b][t])
                     env.step_wait()
                 counters["launches"] += m
             i += m
-            if stats_every and i % stats_every < m and i >= stats_every:
+            done_steps = counters["steps"] = counters.get("steps", 0) + m
+            if stats_every and done_steps % stats_every < m and done_steps >= stats_every:
                 env.episode_stats_tensor(all_reduce=True)   # NCCL all-reduce of 8 doubles, no host sync
                 counters["stats"] += 1
 
     # untimed extra steps before the W warm-up steps: first launches, graph instantiation and the
     # first NCCL collective on every rank (a cold rank once made a whole 4-GPU run 30 % slower)
     run_steps(2 * ACTION_RING, 0)
+    if args.steps % ACTION_RING:                          # (the odd-sized last chunk of the timed region: its buffers exist now)
+        run_steps(args.steps % ACTION_RING + (ACTION_RING if args.steps > ACTION_RING else 0), 0)
     if world > 1:
         env.episode_stats_tensor(all_reduce=True)
     barrier()
@@ -339,7 +368,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     sampler = ClockSampler(local_rank)
     sampler.sample()
     sampler.start()
-    counters["stats"] = counters["launches"] = 0
+    counters["stats"] = counters["launches"] = counters["steps"] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     run_steps(args.steps, 2 * ACTION_RING + args.warmup)
@@ -437,7 +466,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "config": {"workload": workload_name(world), "envs_per_gpu": n, "obs_dim": OBS_DIM,
                        "kernel": kernel_name, "loop_kernel": kernel_of_loop, "maps": "philox seed 0", "state_bytes_per_env": state_bytes,
                        "actions": f"{ACTION_POOL * ACTION_RING} pre-generated i.i.d. uniform vectors, cycled",
-                       "episode_phases": "all envs start at step 0" if args.no_stagger else "staggered: step_count = hash(env id) mod 1000 (about N/1000 auto-resets in every step)",
+                       "episode_phases": "all envs start at step 0" if args.no_stagger else f"staggered: step_count = hash(env id) mod {MAX_STEPS} (about N/{MAX_STEPS} auto-resets in every step)",
                        "l2": f"outputs larger than L2: {ACTION_RING if loop != 'eager' else OBS_RING} observation buffers x {n * OBS_DIM * 4 / 1e6:.0f} MB "
                              f"written round-robin vs 126 MB L2 (per-GPU state {n * state_bytes / 1e6:.0f} MB); no explicit flush",
                        "launch": launch_desc,
@@ -481,7 +510,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3000)
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--preset", default="training", choices=sorted(PRESETS),
+                    help="training (headline, configs[3]) | default (ctor defaults) | xl (configs[4]: 64x64, range 32, 32768 envs/GPU)")
+    ap.add_argument("--envs-per-gpu", type=int, default=0, help="default: 131072 (32768 for --preset xl); 4096 = configs[2]")
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fast"])
     ap.add_argument("--stats-every", type=int, default=100)
     ap.add_argument("--e2e-steps", type=int, default=100)
@@ -497,6 +528,8 @@ def main():
     ap.add_argument("--no-numa-bind", action="store_true", help="leave CPU affinity and memory policy as inherited")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
+    select_preset(args.preset, args.envs_per_gpu)
+    args.envs_per_gpu = ENVS_PER_GPU
     if args.no_graph:
         args.loop = "eager"
     rank = int(os.environ.get("RANK", "0"))

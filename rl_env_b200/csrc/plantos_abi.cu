@@ -53,7 +53,7 @@ const FastVariant kLaneVariants[] = { LANE_ROW(6, 16), LANE_ROW(2, 10), LANE_ROW
 
 // k_step_tile (plantos_tile.cuh): lane-per-env simulation + byte-coded observation output
 struct TileVariant { int R, C; tile_kernel_t step, rollout; };
-#define TILE_ROW(R_, C_) {R_, C_, k_tile<R_, C_, false>, k_tile<R_, C_, true>}
+#define TILE_ROW(R_, C_) {R_, C_, k_tile<R_, C_, false>, k_tile_rollout<R_, C_>}
 const TileVariant kTileVariants[] = { TILE_ROW(6, 16), TILE_ROW(2, 10), TILE_ROW(4, 16), TILE_ROW(4, 8) };
 
 // Does a LIDAR offset table equal the compile-time one the lane kernel was built with?
@@ -102,6 +102,7 @@ struct plantos {
     const char* last_kernel;     // name of the kernel the latest plantos_step launched
     bool wrc_valid;              // the window ring cache mirrors the planes (k_step_tile keeps it so)
     void* d_sync;                // tickets (8 B) + per-tile step flags of k_step_tile
+    Params* d_params;            // Params::self: the global-memory copy of p (see sync_params)
     bool pipelining;             // plantos_set_pipelining
     bool prev_tile_step;         // the handle's latest enqueued operation was a k_step_tile launch ...
     const float* prev_obs;       // ... that wrote this observation buffer on this stream
@@ -116,6 +117,10 @@ struct plantos {
     int64_t launches;
     int64_t steps;               // plantos_step calls so far (episode log's step_seq)
 };
+
+// Params::self mirrors h->p in global memory for the tile kernels' reset path.  Called (after the device is idle)
+// by everything that changes a field that path reads: create, push_maps, set_curriculum(+reuse_map), upload_tables.
+static int sync_params(plantos_t* h);
 
 // every enqueued kernel other than a step launch ends a pipelined sequence of steps
 static void note_launch(plantos_t* h) { h->launches += 1; h->prev_tile_step = false; }
@@ -232,7 +237,7 @@ static void free_all(plantos_t* h) {
     cudaFree(h->d_tables); cudaFree(h->d_table_blob); cudaFree(h->d_lane_tab); cudaFree(h->p.stats); cudaFree(h->p.err);
     cudaFree(h->d_map_cells); cudaFree(h->d_map_rover);
     cudaFree(h->p.ep_log); cudaFree(h->p.ep_log_count);
-    cudaFree(h->p.cur_thr); cudaFree(h->p.cur_cnt); cudaFree(h->p.expl); cudaFree(h->p.wrc); cudaFree(h->d_sync);
+    cudaFree(h->p.cur_thr); cudaFree(h->p.cur_cnt); cudaFree(h->p.expl); cudaFree(h->p.wrc); cudaFree(h->d_sync); cudaFree(h->d_params);
     cudaFree(h->s_actions); cudaFree(h->s_obs); cudaFree(h->s_reward); cudaFree(h->s_done);
     delete h;
 }
@@ -445,7 +450,18 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     }
     cudaError_t es = cudaDeviceSynchronize();
     if (es != cudaSuccess) { free_all(h); return fail(PLANTOS_ECUDA, std::string("create: ") + cudaGetErrorString(es)); }
+    if (cudaMalloc((void**)&h->d_params, sizeof(Params)) != cudaSuccess || sync_params(h) != PLANTOS_OK) {
+        free_all(h);
+        return fail(PLANTOS_ECUDA, "create: parameter mirror");
+    }
     *out = h;
+    return PLANTOS_OK;
+}
+
+static int sync_params(plantos_t* h) {
+    if (!h->d_params) return PLANTOS_OK;
+    h->p.self = h->d_params;
+    CUDA_TRY(cudaMemcpy(h->d_params, &h->p, sizeof(Params), cudaMemcpyHostToDevice));
     return PLANTOS_OK;
 }
 
@@ -487,6 +503,7 @@ extern "C" int plantos_push_maps(plantos_t* h, const uint8_t* cells, const int16
     CUDA_TRY(cudaMemcpy(h->d_map_cells, cells, n * gg, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(h->d_map_rover, rover, n * 2 * sizeof(int16_t), cudaMemcpyHostToDevice));
     p.map_cells = h->d_map_cells; p.map_rover = h->d_map_rover; p.map_episodes = episodes;
+    { int rc = sync_params(h); if (rc) return rc; }
     // restart every env's map cursor (episode index lives in rec.w of the first uint4)
     CUDA_TRY(cudaMemset(p.rec, 0, (size_t)p.N * 32));
     h->did_reset = false;
@@ -727,7 +744,7 @@ extern "C" int plantos_set_curriculum(plantos_t* h, int mode, double initial_thr
     Params& p = h->p;
     cudaFree(p.cur_thr); cudaFree(p.cur_cnt); cudaFree(p.expl);
     p.cur_thr = nullptr; p.cur_cnt = nullptr; p.expl = nullptr; p.cur_mode = PLANTOS_CURRICULUM_OFF;
-    if (mode == PLANTOS_CURRICULUM_OFF) return PLANTOS_OK;
+    if (mode == PLANTOS_CURRICULUM_OFF) return sync_params(h);
     const size_t N = (size_t)p.N;
     CUDA_TRY(cudaMalloc((void**)&p.cur_thr, N * 8));
     CUDA_TRY(cudaMalloc((void**)&p.cur_cnt, N * 8));
@@ -740,14 +757,16 @@ extern "C" int plantos_set_curriculum(plantos_t* h, int mode, double initial_thr
     p.cur_mode = mode; p.cur_max_eps = max_episodes_per_maze; p.cur_reuse_map = 0;
     p.cur_max_thr = max_threshold; p.cur_inc = threshold_increment;
     h->did_reset = false;
-    return PLANTOS_OK;
+    return sync_params(h);
 }
 
 extern "C" int plantos_set_curriculum_reuse_map(plantos_t* h, int enable) {
     if (!h) return fail(PLANTOS_EINVAL, "handle is NULL");
     if (!h->p.cur_mode) return fail(PLANTOS_ESTATE, "no curriculum is active (plantos_set_curriculum)");
     h->p.cur_reuse_map = enable ? 1 : 0;
-    return PLANTOS_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return sync_params(h);
 }
 
 extern "C" int plantos_set_max_steps(plantos_t* h, int max_steps) {

@@ -97,6 +97,10 @@ struct Params {
     // starts tile t when tile_flags[t] == ordinal.
     unsigned int* tickets;
     unsigned int* tile_flags;
+    // a copy of this struct in global memory (kept in sync by the host): the rarely taken reset path of the tile
+    // kernels is a real function call that reads its parameters through this pointer, so that its register needs
+    // stay out of the hot loop's allocation
+    const struct Params* self;
     int pipelined;
     int release;                // the handle may overlap launches (plantos_set_pipelining): publish tile flags with release semantics
 };

@@ -89,14 +89,17 @@ struct MazeRng {
 };
 
 __device__ __forceinline__ void maze_rect(uint64_t* plane, int G, int W, int x0, int x1, int y0, int y1, bool obstacle) {
-    // cells [x0, x1) x [y0, y1) clipped to the grid become empty (or obstacle)
+    // cells [x0, x1) x [y0, y1) clipped to the grid become empty (or obstacle): one masked update per row word
     x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, G); y1 = min(y1, G);
-    for (int x = x0; x < x1; ++x)
-        for (int y = y0; y < y1; ++y) {
-            uint64_t& w = plane[x * W + (y >> 5)];
-            const uint64_t m = 3ull << (2 * (y & 31));
-            w = obstacle ? ((w & ~m) | (1ull << (2 * (y & 31)))) : (w & ~m);
+    if (x0 >= x1 || y0 >= y1) return;
+    for (int wd = y0 >> 5; wd <= (y1 - 1) >> 5; ++wd) {
+        const int lo = max(y0, 32 * wd) - 32 * wd, n = min(y1, 32 * wd + 32) - 32 * wd - lo;     // n cells from cell lo of this word
+        const uint64_t m = (n >= 32 ? ~0ull : ((1ull << (2 * n)) - 1ull)) << (2 * lo);
+        for (int x = x0; x < x1; ++x) {
+            uint64_t& w = plane[x * W + wd];
+            w = obstacle ? ((w & ~m) | (kObstAll & m)) : (w & ~m);
         }
+    }
 }
 
 __device__ __forceinline__ void maze_room(MazeRng& rng, uint64_t* plane, int G, int W, int mx, int my) {   // :479-517

@@ -182,9 +182,37 @@ struct RollIO {
 //                fetched once, patched in place for K steps (visit-count patches also go to the plane, the
 //                source of the rows that enter a window), and written back once; the code image has its own
 //                buffer; half as many warps per SM, each walking its tiles one after the other.
+// New episode for env ej (SB3 auto-reset, after the terminal observation has been written): map, fresh
+// observation into `obs_row`, fresh rings into the cache (and into the resident copy at shared address s_ring if
+// that is non-zero); returns the packed fresh record.  Deliberately NOT inlined and fed from the global-memory
+// copy of the parameters: inlined, its register needs made ptxas spill loop invariants of the hot loop (23 % of
+// the rollout kernel's stall samples were reloads from local memory).
+struct PackedRec { uint4 a, b; };
+__device__ __noinline__ PackedRec tile_reset_env(const Params* gp, size_t ej, int ep, uint64_t* plane, float* row_s,
+                                                  float* obs_row, uint32_t s_ring, int lane) {
+    const Params& p = *gp;
+    int keep = 0, map_ep = -1;
+    if (p.cur_mode) {                                        // CurriculumWrapper.reset
+        int cr = 0;
+        if (lane == 0) cr = curriculum_on_reset(p, (int)ej, ep);
+        cr = __shfl_sync(0xffffffffu, cr, 0);
+        keep = cr & 1; map_ep = cr >> 1;
+    }
+    const EnvRec nr = reset_env_warp<false>(p, (int)ej, ep, plane, lane, keep != 0, map_ep);
+    // (fresh visit window: what the planes hold after a plain reset, and what the wrapper's reset observation
+    // shows when the counts are kept)
+    const Tables tb = tables_at(const_cast<unsigned char*>(reinterpret_cast<const unsigned char*>(p.table_blob)), p.G, p.R);
+    build_obs_warp(p, tb, plane, p.vis4 + ej * p.VE, nr.x, nr.y, row_s, lane, true);
+    store_obs_row(row_s, obs_row, p.D, lane);
+    wrc_build_env_fresh_warp(p, ej, nr.x, nr.y, plane, keep != 0, lane, s_ring);
+    PackedRec out;
+    pack_rec(nr, out.a, out.b);
+    __syncwarp();
+    return out;
+}
+
 template <int R, int C, bool MULTI>
-__global__ void __launch_bounds__(kTileWarps * 32, MULTI ? PLANTOS_TILE_MINBLOCKS / 2 : PLANTOS_TILE_MINBLOCKS)
-k_tile(const Params p, const RollIO io) {
+__device__ __forceinline__ void tile_body(const Params& p, const RollIO& io) {
     using Gen = LidarGen<R, C>;
     static_assert(Gen::ok, "no generated LIDAR offsets for this (R, C)");
     constexpr int D = 5 * C + 27;
@@ -341,8 +369,9 @@ k_tile(const Params p, const RollIO io) {
         const size_t ko = (size_t)k * (size_t)p.N;           // offset of step k in the [K, N] outputs
         long long action_next = 0;
         if (MULTI) {
-            if (act && k + 1 < K) action_next = __ldcg(io.actions + ko + p.N + e);   // in flight during this step
             cp_async_wait_all();                             // the rows the previous step pulled into this lane's rings
+            if (act && k + 1 < K) action_next = __ldcg(io.actions + ko + p.N + e);   // in flight during this step (issued
+                                                             // AFTER the wait: both would sit on the same scoreboard)
         }
         const int x0 = r.x;
         // ---- transition (plantos_env.py:160-222), one lane per env, out of the rings
@@ -613,31 +642,18 @@ k_tile(const Params p, const RollIO io) {
             dmask = dmask0;
         }
         if (p.map_source == 2) dmask = 0u;                   // maze handles: k_reset_done starts the new episodes after this launch
+#ifdef PROBE_NO_PHASEC
+        dmask = 0u;
+#endif
         while (dmask) {
             const int j = __ffs(dmask) - 1;
             dmask &= dmask - 1;
             const size_t ej = (size_t)e0 + j;
             const int ep = __shfl_sync(FULL, episode, j);
-            int keep = 0, map_ep = -1;
-            if (p.cur_mode) {                                // CurriculumWrapper.reset
-                int cr = 0;
-                if (lane == 0) cr = curriculum_on_reset(p, (int)ej, ep);
-                cr = __shfl_sync(FULL, cr, 0);
-                keep = cr & 1; map_ep = cr >> 1;
-            }
-            const EnvRec nr = reset_env_warp<false>(p, (int)ej, ep, plane, lane, keep != 0, map_ep);
-            // (fresh visit window: what the planes hold after a plain reset, and what the wrapper's reset
-            // observation shows when the counts are kept)
-            build_obs_warp(p, tabs(), plane, p.vis4 + ej * VE, nr.x, nr.y, row_s, lane, true);
-            store_obs_row(row_s, io.obs + (size_t)k * io.obs_stride + ej * D, D, lane);
-            // the new episode's rings: into the cache and, for the resident copy of the multi-step kernel, into shared memory
-            wrc_build_env_fresh_warp(p, ej, nr.x, nr.y, plane, keep != 0, lane, MULTI ? s_win : 0u);
-            if (MULTI) { if (lane == j) r = nr; }
-            else if (lane == 0) {
-                uint4 qa, qb;
-                pack_rec(nr, qa, qb);
-                st_rec256(p.rec + 2 * ej, qa, qb);
-            }
+            const PackedRec fresh = tile_reset_env(p.self, ej, ep, plane, row_s, io.obs + (size_t)k * io.obs_stride + ej * D,
+                                                   MULTI ? s_win : 0u, lane);
+            if (MULTI) { if (lane == j) r = unpack_rec(fresh.a, fresh.b); }   // the lane's record restarts
+            else if (lane == 0) st_rec256(p.rec + 2 * ej, fresh.a, fresh.b);
             __syncwarp();
         }
         if (!MULTI && dmask0 != 0u && lane == 0) {           // tiles with resets complete here
@@ -676,5 +692,17 @@ k_tile(const Params p, const RollIO io) {
             for (int e = nfull; e < p.N; ++e) step_env_warp<false>(p, tabs(), sio, e, plane, row_s, lane);
         }
 }
+
+// The two kernels: 28 warps per SM at 72 registers for the single step; for the state-resident rollout 14 warps
+// per SM (the code image needs its own buffer behind the rings) with 128 registers (8 blocks per SM), so that the
+// record it carries through the K steps does not push loop invariants out to local memory (a reload from there
+// stalled a warp like a global load: 23 % of the rollout kernel's stall samples before).
+template <int R, int C, bool MULTI>
+__global__ void __launch_bounds__(kTileWarps * 32, PLANTOS_TILE_MINBLOCKS)
+k_tile(const Params p, const RollIO io) { tile_body<R, C, false>(p, io); }
+
+template <int R, int C>
+__global__ void __maxnreg__(128)
+k_tile_rollout(const Params p, const RollIO io) { tile_body<R, C, true>(p, io); }
 
 }  // namespace plantos_dev

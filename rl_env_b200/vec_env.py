@@ -353,9 +353,11 @@ class PlantOSVecEnv:
         included.  On the fast presets the K steps are one launch of the state-resident kernel (the
         envs' window rings and records never leave the SM between steps) -- the GPU form of the
         reference's MCTS rollout loop (mcts_custom_trainer.py:139-166)."""
-        if not isinstance(actions, torch.Tensor):
-            actions = torch.as_tensor(np.asarray(actions), dtype=torch.int64)
-        actions = actions.to(device=self.device, dtype=torch.int64, non_blocking=True).contiguous()
+        if not (isinstance(actions, torch.Tensor) and actions.dtype == torch.int64 and actions.device == self.device
+                and actions.is_contiguous()):              # (the fast path costs no torch calls at all)
+            if not isinstance(actions, torch.Tensor):
+                actions = torch.as_tensor(np.asarray(actions), dtype=torch.int64)
+            actions = actions.to(device=self.device, dtype=torch.int64, non_blocking=True).contiguous()
         if actions.dim() != 2 or actions.shape[1] != self.num_envs:
             raise ValueError(f"expected actions of shape [K, {self.num_envs}], got {tuple(actions.shape)}")
         k, n, d, dev = int(actions.shape[0]), self.num_envs, self.obs_dim, self.device
@@ -370,17 +372,20 @@ class PlantOSVecEnv:
                    "done": torch.zeros((k, n), dtype=torch.bool, device=dev),
                    "term": torch.zeros((k, n), dtype=torch.bool, device=dev),
                    "trunc": torch.zeros((k, n), dtype=torch.bool, device=dev)}
+            buf["obs_view"] = buf["obs"].as_strided((k, n, d), (stride, d, 1))
+            buf["ptrs"] = (buf["obs"].data_ptr(), buf["rew"].data_ptr(), buf["done"].data_ptr(),
+                           buf["term"].data_ptr(), buf["trunc"].data_ptr(),
+                           self._terminal_obs.data_ptr() if self._terminal_obs is not None else None)
             self._many[k] = buf
-        tobs = self._terminal_obs.data_ptr() if self._terminal_obs is not None else None
-        nat.check(self._lib.plantos_rollout(
-            self._h, k, actions.data_ptr(), buf["obs"].data_ptr(), buf["stride"], buf["rew"].data_ptr(),
-            buf["done"].data_ptr(), buf["term"].data_ptr() if with_flags else None,
-            buf["trunc"].data_ptr() if with_flags else None, tobs, self._stream()))
+        po, pr, pd, pt, pu, ptobs = buf["ptrs"]
+        rc = self._lib.plantos_rollout(self._h, k, actions.data_ptr(), po, buf["stride"], pr, pd,
+                                       pt if with_flags else None, pu if with_flags else None, ptobs, self._stream())
+        if rc:
+            nat.check(rc)
         self._actions = actions                            # keep alive until the launch has consumed it
-        obs = buf["obs"].as_strided((k, n, d), (buf["stride"], d, 1))
         if with_flags:
-            return obs, buf["rew"], buf["done"], buf["term"], buf["trunc"]
-        return obs, buf["rew"], buf["done"]
+            return buf["obs_view"], buf["rew"], buf["done"], buf["term"], buf["trunc"]
+        return buf["obs_view"], buf["rew"], buf["done"]
 
     def set_pipelining(self, enable: bool) -> None:
         """Let back-to-back `step_async` calls overlap on the device (open-loop stepping only: the

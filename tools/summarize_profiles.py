@@ -1,79 +1,101 @@
 #!/usr/bin/env python3
-"""Turn the raw evidence a GPU run left in gpurun_out/ev/ into the committed summaries under profiles/.
-usage: tools/summarize_profiles.py <round-tag, e.g. r1> [ev-dir]
-Inputs (see profiles/<tag>_summary.md for the commands that produce them):
-  launches.csv        ncu --metrics gpu__time_duration.sum --clock-control none (launch list)
-  prof_fast_*.ncu-rep ncu --set full of one k_step_fast launch
-  steady_dram.csv     ncu --replay-mode application --cache-control none, dram bytes of 4 launches
-  bench_*.json, pytest_gpu.log"""
+"""Turn the raw evidence of tools/gpu_evidence.sh (gpurun_out/ev2/) into the committed summaries under profiles/.
+usage: tools/summarize_profiles.py <round-tag, e.g. r2> [ev-dir]"""
 import collections, csv, glob, io, json, os, shutil, subprocess, sys
 tag = sys.argv[1]
-ev = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/ev"
+ev = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/ev2"
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = os.path.join(root, "profiles")
+
 
 def csv_rows(path):
     lines = [l for l in open(path) if l.startswith('"')]
     return list(csv.DictReader(io.StringIO("".join(lines))))
 
-# launch list
+
+def last_json(path):
+    try:
+        return json.loads(open(path).read().strip().splitlines()[-1])
+    except Exception:
+        return None
+
+
+# ---- bench lines and logs
+for name in ("bench_1gpu", "bench_1gpu_20steps", "bench_reference_cpu", "bench_nostagger"):
+    d = last_json(os.path.join(ev, name + ".json"))
+    if d is not None:
+        json.dump(d, open(os.path.join(out, f"{tag}_{name}.json"), "w"))
+loops = {}
+for name in ("bench_loop_graph", "bench_loop_graph_plain", "bench_loop_eager", "bench_loop_eager_plain"):
+    d = last_json(os.path.join(ev, name + ".json"))
+    if d is not None:
+        loops[name] = {"us_per_step": round(d["ms_per_step"] * 1e3, 2), "frac": round(d["roofline"]["frac"], 3),
+                       "launch": d["config"]["launch"], "episodes": d["episode_stats"]["episodes"]}
+json.dump(loops, open(os.path.join(out, f"{tag}_bench_loops.json"), "w"), indent=1)
+for name in ("presets.log", "pytest_gpu.log", "gpu.txt"):
+    if os.path.exists(os.path.join(ev, name)):
+        text = open(os.path.join(ev, name)).read()
+        if name == "pytest_gpu.log":
+            text = "\n".join(text.strip().splitlines()[-3:]) + "\n"
+        open(os.path.join(out, f"{tag}_{name}"), "w").write(text)
+
+# ---- launch list (no cache flush between launches)
 rows = csv_rows(os.path.join(ev, "launches.csv"))
 shutil.copy(os.path.join(ev, "launches.csv"), os.path.join(out, f"{tag}_launches.csv"))
 agg = collections.OrderedDict()
 for r in rows:
-    if r["Metric Name"] != "gpu__time_duration.sum": continue
+    if r["Metric Name"] != "gpu__time_duration.sum":
+        continue
     ns = float(r["Metric Value"]) * {"ns": 1, "us": 1e3, "ms": 1e6}.get(r["Metric Unit"], 1)
-    a = agg.setdefault(r["Kernel Name"][:72], [0, 0.0]); a[0] += 1; a[1] += ns
+    a = agg.setdefault(r["Kernel Name"][:80], [0, 0.0]); a[0] += 1; a[1] += ns
 tot = sum(a[1] for a in agg.values())
 summ = [{"kernel": k, "launches": a[0], "mean_us": round(a[1] / a[0] / 1e3, 2), "total_us": round(a[1] / 1e3, 1),
          "share": round(a[1] / tot, 4)} for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])]
 json.dump(summ, open(os.path.join(out, f"{tag}_launches_summary.json"), "w"), indent=1)
 
-# full-set metrics of the hot kernel
-rep = sorted(glob.glob(os.path.join(ev, "prof_fast_*.ncu-rep")))[-1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(io.StringIO(raw)))
-names, units, vals = rr[0], rr[1], rr[2]
+# ---- full-set metrics of the two hot kernels
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
         "smsp__issue_active.avg.per_cycle_active", "smsp__warps_active.avg.per_cycle_active",
         "smsp__warps_eligible.avg.per_cycle_active", "launch__registers_per_thread", "launch__grid_size",
-        "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
-        "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.sum",
-        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct",
-        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
-sel = {}
-with open(os.path.join(out, f"{tag}_fast_kernel_metrics.csv"), "w") as f:
-    f.write("metric,unit,value\n")
-    for i, n in enumerate(names):
-        if n in want or (n.startswith("smsp__average_warps_issue_stalled") and n.endswith("per_issue_active.ratio")):
-            f.write(f"{n},{units[i]},{vals[i]}\n"); sel[n] = (units[i], float(vals[i].replace(",", "")))
-def to_bytes(n):
-    u, v = sel[n]; return int(v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u])
+        "launch__block_size", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem",
+        "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum",
+        "lts__t_sector_hit_rate.pct", "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum"]
+for which in ("rollout", "step"):
+    rep = os.path.join(ev, f"prof_{which}.ncu-rep")
+    if not os.path.exists(rep):
+        continue
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(io.StringIO(raw)))
+    names, units, vals = rr[0], rr[1], rr[2]
+    with open(os.path.join(out, f"{tag}_{which}_kernel_metrics.csv"), "w") as f:
+        w = csv.writer(f)
+        w.writerow(["metric", "unit", "value"])
+        w.writerow(["kernel", "", vals[names.index("Kernel Name")] if "Kernel Name" in names else ""])
+        for i, n in enumerate(names):
+            if n in want or n.startswith("smsp__average_warps_issue_stalled") and n.endswith("per_issue_active.ratio"):
+                w.writerow([n, units[i], vals[i]])
 
-# steady-state DRAM
-st = csv_rows(os.path.join(ev, "steady_dram.csv"))
-shutil.copy(os.path.join(ev, "steady_dram.csv"), os.path.join(out, f"{tag}_steady_state_dram.csv"))
-rd = [float(r["Metric Value"]) for r in st if r["Metric Name"] == "dram__bytes_read.sum"]
-wr = [float(r["Metric Value"]) for r in st if r["Metric Name"] == "dram__bytes_write.sum"]
-cold_r, cold_w = to_bytes("dram__bytes_read.sum"), to_bytes("dram__bytes_write.sum")
-traffic = {
-    "kernel": rows and [r["Kernel Name"] for r in rows if "k_step_fast" in r["Kernel Name"]][0][:60],
-    "workload": "131072 envs, training preset (D=107)",
-    "source": f"ncu --set full --clock-control none, {os.path.basename(rep)} (caches flushed between replay passes)",
-    "dram_bytes_read": cold_r, "dram_bytes_write": cold_w, "dram_bytes_per_launch": cold_r + cold_w,
-    "note": "cold-cache per-launch figure: ncu flushes L2 before each pass, so state reads come from DRAM while most of "
-            "the bytes written are still dirty in L2 when the kernel ends. steady_state_* = mean of 4 consecutive launches "
-            "inside the bench loop (ncu --replay-mode application --cache-control none, profiles/%s_steady_state_dram.csv)." % tag,
-    "steady_state_dram_bytes_read": int(sum(rd) / len(rd)), "steady_state_dram_bytes_write": int(sum(wr) / len(wr)),
-    "steady_state_dram_bytes_per_launch": int(sum(rd) / len(rd) + sum(wr) / len(wr)),
-    "algorithmic_bytes_per_launch": 131072 * 441,
-}
+# ---- steady-state DRAM traffic
+traffic = {"envs": 131072, "how": "ncu --replay-mode application --cache-control none (no cache flush), bench.py timed loop", "kernels": {}}
+for which, kname, steps in (("rollout", "k_rollout_tile", 16), ("step", "k_step_tile", 1)):
+    path = os.path.join(ev, f"steady_dram_{which}.csv")
+    if not os.path.exists(path):
+        continue
+    rows = csv_rows(path)
+    shutil.copy(path, os.path.join(out, f"{tag}_steady_dram_{which}.csv"))
+    rd = [float(r["Metric Value"]) for r in rows if r["Metric Name"] == "dram__bytes_read.sum"]
+    wr = [float(r["Metric Value"]) for r in rows if r["Metric Name"] == "dram__bytes_write.sum"]
+    if rd and wr:
+        traffic["kernels"][kname] = {"dram_bytes_per_step": int((sum(rd) / len(rd) + sum(wr) / len(wr)) / steps),
+                                     "read_per_step": int(sum(rd) / len(rd) / steps), "write_per_step": int(sum(wr) / len(wr) / steps),
+                                     "launches_sampled": len(rd), "steps_per_launch": steps,
+                                     "source": f"profiles/{tag}_steady_dram_{which}.csv"}
 json.dump(traffic, open(os.path.join(out, f"{tag}_traffic.json"), "w"), indent=1)
-for src, dst in [("bench_1gpu.json", f"{tag}_bench_1gpu.json"), ("bench_2gpu.json", f"{tag}_bench_2gpu.json"),
-                 ("bench_8gpu.json", f"{tag}_bench_8gpu.json"), ("pytest_gpu.log", f"{tag}_pytest_gpu.log"),
-                 ("sizes.log", f"{tag}_sizes.log")]:
-    if os.path.exists(os.path.join(ev, src)): shutil.copy(os.path.join(ev, src), os.path.join(out, dst))
-print(json.dumps(summ[:4], indent=1)); print(json.dumps(traffic, indent=1))
+print(json.dumps(traffic["kernels"], indent=1))
+print(json.dumps(loops, indent=1))
+print(json.dumps(summ[:6], indent=1))
