@@ -32,7 +32,6 @@ import json
 import multiprocessing as mp
 import os
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -62,6 +61,8 @@ def select_preset(name: str, envs_per_gpu):
     ENVS_PER_GPU = int(envs_per_gpu) if envs_per_gpu else default_envs
     OBS_DIM = 5 * PRESET["lidar_channels"] + 27
     B_ALG = 4 * OBS_DIM + 4 + 1 + 8
+PREWARM_CHUNKS = 40                       # untimed steps (x ACTION_RING) before the W warm-up steps: the GPU has idled for seconds
+                                          # while the process started, and 200 ms of idle already cost a 20-step region 40 %
 ACTION_RING = 16                          # steps per rollout call / per replayed graph
 ACTION_POOL = 4                           # distinct [16, N] action blocks the timed loop cycles through (64 i.i.d. vectors)
 OBS_RING = 5                              # rollout-buffer depth (A2C n_steps=5, A2C_training.py:229-247)
@@ -215,13 +216,18 @@ def run_reference(args, rank: int):
 
 
 # ------------------------------------------------------------------ clocks
-class ClockSampler(threading.Thread):
+class ClockSampler:
+    """SM clock and throttle reasons read through NVML while the timed steps execute.
+
+    The timed region is enqueued first (kernel launches are asynchronous), then the calling thread polls NVML
+    until the closing event has completed: every sample is taken while the GPU is running timed steps, and no
+    NVML call competes with the launches for the driver (a sampler thread that started polling next to the
+    first launch cost 50-70 us of a 300 us region)."""
+
     def __init__(self, index: int):
-        super().__init__(daemon=True)
         self.index = index
         self.samples, self.reasons = [], set()
         self.max_mhz = None
-        self._stop_evt = threading.Event()
         self._h = None
         try:
             import pynvml
@@ -250,14 +256,13 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
-    def run(self):
-        while not self._stop_evt.is_set():
+    def sample_until(self, event, max_samples: int = 4000):
+        """Poll until `event` (recorded after the last timed step) has completed; at least one sample."""
+        self.sample()
+        while not event.query() and len(self.samples) < max_samples:
             self.sample()
-            time.sleep(0.002)
-
-    def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=2)
+            time.sleep(0.0005)
+        self.in_flight = len(self.samples)
         self.sample()
 
     def summary(self):
@@ -265,7 +270,7 @@ class ClockSampler(threading.Thread):
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"], "samples": 0}
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "samples_while_timed_steps_ran": getattr(self, "in_flight", 0)}
 
 
 # ------------------------------------------------------------------ ours
@@ -330,11 +335,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # (--steps 20) is ONE call, not a 16-step call plus a 4-step call with a host round trip in between
     pool2 = [torch.cat([pool[b], pool[(b + 1) % ACTION_POOL]]) for b in range(ACTION_POOL)]   # [2 * ACTION_RING, n] each
 
+    chunk = min(max(args.chunk, 1), ACTION_RING) if loop == "rollout" else ACTION_RING
+
     def run_steps(k, start):
         """k consecutive steps; `start` only selects which pre-generated action blocks are used."""
         i = 0
         while i < k:
-            m = k - i if k - i < 2 * ACTION_RING else ACTION_RING
+            m = k - i if k - i < 2 * chunk else chunk
             b = ((start + i) // ACTION_RING) % ACTION_POOL
             if loop == "rollout":
                 env.step_many(pool2[b][:m], with_flags=True)        # ONE plantos_rollout call: m steps
@@ -357,24 +364,24 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     # untimed extra steps before the W warm-up steps: first launches, graph instantiation and the
     # first NCCL collective on every rank (a cold rank once made a whole 4-GPU run 30 % slower)
-    run_steps(2 * ACTION_RING, 0)
-    if args.steps % ACTION_RING:                          # (the odd-sized last chunk of the timed region: its buffers exist now)
-        run_steps(args.steps % ACTION_RING + (ACTION_RING if args.steps > ACTION_RING else 0), 0)
+    sampler = ClockSampler(local_rank)      # (NVML initialised here: tens of ms of idle GPU right before the timed
+    sampler.sample()                        #  region drop its clocks -- a 300 us region then runs 40 % slower)
+    sampler.samples.clear()
+    run_steps(PREWARM_CHUNKS * ACTION_RING, 0)
+    if args.steps % chunk:                                # (the odd-sized last chunk of the timed region: its buffers exist now)
+        run_steps(args.steps % chunk + (chunk if args.steps > chunk else 0), 0)
     if world > 1:
         env.episode_stats_tensor(all_reduce=True)
     barrier()
     run_steps(args.warmup, 2 * ACTION_RING)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.sample()
-    sampler.start()
     counters["stats"] = counters["launches"] = counters["steps"] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     run_steps(args.steps, 2 * ACTION_RING + args.warmup)
     e1.record()
+    sampler.sample_until(e1)
     barrier()
-    sampler.stop()
     ms = e0.elapsed_time(e1)
     launches, stats_in_window = counters["launches"], counters["stats"]
     kernel_of_loop = env.last_step_kernel
@@ -470,6 +477,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        "l2": f"outputs larger than L2: {ACTION_RING if loop != 'eager' else OBS_RING} observation buffers x {n * OBS_DIM * 4 / 1e6:.0f} MB "
                              f"written round-robin vs 126 MB L2 (per-GPU state {n * state_bytes / 1e6:.0f} MB); no explicit flush",
                        "launch": launch_desc,
+                       "untimed_steps_before_warmup": PREWARM_CHUNKS * ACTION_RING,
                        "stats_allreduce_every": stats_every, "stats_allreduces_in_timed_window": stats_in_window},
             "e2e": {"value": total_envs * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * (4 * OBS_DIM + 4 + 1),
@@ -521,6 +529,7 @@ def main():
     ap.add_argument("--no-terminal-obs", action="store_true")
     ap.add_argument("--loop", default="rollout", choices=["rollout", "graph", "eager"],
                     help="timed loop: step_many (16 steps per rollout launch), replayed graph of 16 step launches, or eager steps")
+    ap.add_argument("--chunk", type=int, default=ACTION_RING, help="rollout loop: steps per plantos_rollout call (<= %d)" % ACTION_RING)
     ap.add_argument("--no-graph", action="store_true", help="same as --loop eager")
     ap.add_argument("--no-pipeline", action="store_true", help="full grid-wide dependency between consecutive step launches (graph / eager loops)")
     ap.add_argument("--no-stagger", action="store_true", help="all envs start at step 0 (no auto-reset before step 1000)")

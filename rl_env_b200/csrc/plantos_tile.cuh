@@ -701,8 +701,11 @@ template <int R, int C, bool MULTI>
 __global__ void __launch_bounds__(kTileWarps * 32, PLANTOS_TILE_MINBLOCKS)
 k_tile(const Params p, const RollIO io) { tile_body<R, C, false>(p, io); }
 
+#ifndef PLANTOS_ROLLOUT_REGS
+#define PLANTOS_ROLLOUT_REGS 112
+#endif
 template <int R, int C>
-__global__ void __maxnreg__(128)
+__global__ void __maxnreg__(PLANTOS_ROLLOUT_REGS)
 k_tile_rollout(const Params p, const RollIO io) { tile_body<R, C, true>(p, io); }
 
 }  // namespace plantos_dev
