@@ -337,12 +337,21 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     chunk = min(max(args.chunk, 1), ACTION_RING) if loop == "rollout" else ACTION_RING
 
+    pending_stats = []
+
     def run_steps(k, start):
         """k consecutive steps; `start` only selects which pre-generated action blocks are used."""
         i = 0
         while i < k:
             m = k - i if k - i < 2 * chunk else chunk
             b = ((start + i) // ACTION_RING) % ACTION_POOL
+            # episode statistics: whenever the steps about to be enqueued cross a multiple of `stats_every`, the
+            # counters as they stand are snapshotted and all-reduced (NCCL, 8 doubles) on the process group's stream,
+            # next to those steps; the timed region ends only after every such all-reduce has completed
+            done_steps = counters.get("steps", 0)
+            if stats_every and (done_steps + m) // stats_every > done_steps // stats_every:
+                pending_stats.append(env.episode_stats_tensor(all_reduce=True, async_op=True))
+                counters["stats"] += 1
             if loop == "rollout":
                 env.step_many(pool2[b][:m], with_flags=True)        # ONE plantos_rollout call: m steps
                 counters["launches"] += 1
@@ -357,10 +366,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     env.step_wait()
                 counters["launches"] += m
             i += m
-            done_steps = counters["steps"] = counters.get("steps", 0) + m
-            if stats_every and done_steps % stats_every < m and done_steps >= stats_every:
-                env.episode_stats_tensor(all_reduce=True)   # NCCL all-reduce of 8 doubles, no host sync
-                counters["stats"] += 1
+            counters["steps"] = done_steps + m
+        for ps in pending_stats:                                     # (a stream-level wait, no host sync)
+            ps.wait()
+        pending_stats.clear()
 
     # untimed extra steps before the W warm-up steps: first launches, graph instantiation and the
     # first NCCL collective on every rank (a cold rank once made a whole 4-GPU run 30 % slower)

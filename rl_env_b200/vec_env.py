@@ -554,10 +554,17 @@ class PlantOSVecEnv:
         vals = self.episode_stats_tensor(clear=clear, all_reduce=all_reduce).cpu().tolist()
         return dict(zip(nat.STAT_NAMES, vals))
 
-    def episode_stats_tensor(self, clear: bool = False, all_reduce: bool = True) -> torch.Tensor:
+    def episode_stats_tensor(self, clear: bool = False, all_reduce: bool = True, async_op: bool = False):
         """Same 8-vector as a float64 CUDA tensor, enqueued without a host sync (the kernel
-        and the collective are stream-ordered), for callers that poll it off the step path."""
+        and the collective are stream-ordered), for callers that poll it off the step path.
+
+        `async_op=True` returns a `PendingStats`: the snapshot is taken on the env's stream now, the
+        all-reduce runs on the process group's own stream NEXT TO the steps enqueued afterwards (it is
+        8 doubles: pure latency, which the following launches hide); `.wait()` makes the env's stream
+        wait for it and returns the tensor."""
         nat.check(self._lib.plantos_stats(self._h, self._stats.data_ptr(), int(clear), self._stream()))
+        if async_op:
+            return all_reduce_stats(self._stats, async_op=True) if all_reduce else PendingStats(self._stats, None)
         return all_reduce_stats(self._stats) if all_reduce else self._stats
 
     # --------------------------------------------------------------- per-episode log (SB3 Monitor)
@@ -715,14 +722,30 @@ class MonitorCSV:
         self._files.clear()
 
 
-def all_reduce_stats(vec: torch.Tensor) -> torch.Tensor:
+class PendingStats:
+    """A statistics vector whose all-reduce may still be in flight (`all_reduce_stats(async_op=True)`)."""
+
+    def __init__(self, tensor: torch.Tensor, work):
+        self.tensor, self._work = tensor, work
+
+    def wait(self) -> torch.Tensor:
+        """Order the current stream (NCCL) / the caller (gloo) after the collective; returns the summed vector."""
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        return self.tensor
+
+
+def all_reduce_stats(vec: torch.Tensor, async_op: bool = False):
     """Sum a rank-local statistics vector over the default process group (no-op if there is
-    none).  Works on NCCL (CUDA tensor) and gloo (CPU tensor) alike."""
+    none).  Works on NCCL (CUDA tensor) and gloo (CPU tensor) alike.  `async_op=True` returns a
+    `PendingStats` instead of the tensor."""
     import torch.distributed as dist
+    work = None
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         vec = vec.clone()
-        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
-    return vec
+        work = dist.all_reduce(vec, op=dist.ReduceOp.SUM, async_op=async_op)
+    return PendingStats(vec, work) if async_op else vec
 
 
 def shard_range(total_envs: int, rank: int, world_size: int):

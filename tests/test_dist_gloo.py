@@ -30,6 +30,8 @@ def _worker(rank, world, port, total_envs, q):
                          torch.tensor(0.0, dtype=torch.float64), torch.tensor(float(count), dtype=torch.float64)])
     out = all_reduce_stats(local)
     assert out is not local  # the rank-local vector is left untouched
+    pending = all_reduce_stats(local, async_op=True)      # the overlapped form bench.py uses: same sums after wait()
+    assert torch.equal(pending.wait(), out) and pending.wait() is pending.tensor
     q.put((rank, start, count, out.tolist()))
     dist.barrier()
     dist.destroy_process_group()
@@ -61,3 +63,4 @@ def test_all_reduce_is_identity_without_process_group():
     from rl_env_b200 import all_reduce_stats
     v = torch.arange(8, dtype=torch.float64)
     assert all_reduce_stats(v) is v
+    assert all_reduce_stats(v, async_op=True).wait() is v
