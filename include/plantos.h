@@ -126,7 +126,10 @@ int plantos_upload_tables(plantos_t* h, const int8_t* lidar_off, const float* di
 /* Injected-map mode: give every env a queue of `episodes` recorded maps, consumed one per
  * reset in order (replaces the procedural generator, plantos_env.py:338-372).  Host pointers:
  * cells u8 [num_envs][episodes][G*G], rover i16 [num_envs][episodes][2] (x,y).  Resets the
- * per-env map cursor to 0.  Synchronous. */
+ * per-env map cursor to 0.  Synchronous.  A map may hold at most 255 plant cells (the env record counts thirsty
+ * plants in 8 bits; EINVAL otherwise, and plantos_set_state flags the same through plantos_check); the info
+ * surface reports total_plants from the config's num_plants, as the reference does (plantos_env.py:317-336), so
+ * recorded maps are expected to hold exactly num_plants plants, which every reference map does. */
 int plantos_push_maps(plantos_t* h, const uint8_t* cells, const int16_t* rover, int episodes);
 
 /* VecEnv.reset(): start a new episode in every env (PlantOSEnv.reset, plantos_env.py:125-158)

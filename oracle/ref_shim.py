@@ -135,6 +135,10 @@ class ReferenceEnv:
         try:
             return env.step(action)
         except TypeError:
+            # only the documented failure is substituted: watering while standing on an already hydrated plant
+            # (plants[pos] is False there and the reference adds `None`); any other TypeError is a real error
+            if not (int(action) >= 4 and env.plants.get(env.rover_pos) is False):
+                raise
             # state at this point: step_count already += 1, nothing else changed
             self.mistake_steps += 1
             reward = env.R_STEP

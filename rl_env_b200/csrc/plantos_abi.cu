@@ -5,7 +5,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/plantos.h"
@@ -53,7 +56,7 @@ const FastVariant kLaneVariants[] = { LANE_ROW(6, 16), LANE_ROW(2, 10), LANE_ROW
 
 // k_step_tile (plantos_tile.cuh): lane-per-env simulation + byte-coded observation output
 struct TileVariant { int R, C; tile_kernel_t step, rollout; };
-#define TILE_ROW(R_, C_) {R_, C_, k_tile<R_, C_, false>, k_tile_rollout<R_, C_>}
+#define TILE_ROW(R_, C_) {R_, C_, k_step_tile<R_, C_>, k_rollout_tile<R_, C_>}
 const TileVariant kTileVariants[] = { TILE_ROW(6, 16), TILE_ROW(2, 10), TILE_ROW(4, 16), TILE_ROW(4, 8) };
 
 // Does a LIDAR offset table equal the compile-time one the lane kernel was built with?
@@ -95,8 +98,8 @@ struct plantos {
     bool use_fast;               // a specialised kernel exists for this shape
     FastLaunch trip;             // k_step_fast (fn == nullptr: none)
     FastLaunch lane;             // k_step_lane
-    FastLaunch tile;             // k_step_tile = k_tile<R, C, false> (fn unused: see tile_step)
-    tile_kernel_t tile_step, tile_rollout;   // k_tile<R, C, false / true>
+    FastLaunch tile;             // k_step_tile<R, C> (fn unused: see tile_step)
+    tile_kernel_t tile_step, tile_rollout;   // k_step_tile<R, C> / k_rollout_tile<R, C>
     int rollout_grid, rollout_smem;
     int impl;                    // 0: k_step_tile when possible, 1: k_step_fast, 2: k_step_lane (experiments)
     const char* last_kernel;     // name of the kernel the latest plantos_step launched
@@ -240,6 +243,19 @@ static void free_all(plantos_t* h) {
     cudaFree(h->p.cur_thr); cudaFree(h->p.cur_cnt); cudaFree(h->p.expl); cudaFree(h->p.wrc); cudaFree(h->d_sync); cudaFree(h->d_params);
     cudaFree(h->s_actions); cudaFree(h->s_obs); cudaFree(h->s_reward); cudaFree(h->s_done);
     delete h;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per function and process-wide: a later handle with a smaller
+// need must not lower what an earlier live handle relies on.  Only ever raise it (per device).
+static cudaError_t raise_dyn_smem(const void* fn, int device, int bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> cur;
+    std::lock_guard<std::mutex> lock(mu);
+    int& have = cur[{fn, device}];
+    if (bytes <= have) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
 }
 
 extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t** out) {
@@ -422,9 +438,9 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
         h->prefer_lane = h->impl == 2;
         h->use_pdl = cfg->tune_no_pdl == 0;
     }
-    cudaError_t e1 = cudaFuncSetAttribute(k_step_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);
-    cudaError_t e2 = cudaFuncSetAttribute(k_reset_all, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);
-    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_reset_done, cudaFuncAttributeMaxDynamicSharedMemorySize, h->generic_smem);
+    cudaError_t e1 = raise_dyn_smem((const void*)k_step_generic, h->device, h->generic_smem);
+    cudaError_t e2 = raise_dyn_smem((const void*)k_reset_all, h->device, h->generic_smem);
+    if (e2 == cudaSuccess) e2 = raise_dyn_smem((const void*)k_reset_done, h->device, h->generic_smem);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
         free_all(h);
         return fail(PLANTOS_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
@@ -437,12 +453,12 @@ extern "C" int plantos_create(const plantos_config_t* cfg, int device, plantos_t
     h->generic_grid = (int)(want < cap ? want : cap);
     for (FastLaunch* L : {&h->trip, &h->lane}) {
         if (!h->use_fast || !L->fn) continue;
-        cudaError_t e3 = cudaFuncSetAttribute(L->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, L->smem);
+        cudaError_t e3 = raise_dyn_smem((const void*)L->fn, h->device, L->smem);
         if (e3 != cudaSuccess) { free_all(h); return fail(PLANTOS_ECUDA, std::string("cudaFuncSetAttribute(fast): ") + cudaGetErrorString(e3)); }
     }
     if (h->use_fast && h->tile.fn) {
-        cudaError_t e3 = cudaFuncSetAttribute(h->tile_step, cudaFuncAttributeMaxDynamicSharedMemorySize, h->tile.smem);
-        cudaError_t e4 = cudaFuncSetAttribute(h->tile_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, h->rollout_smem);
+        cudaError_t e3 = raise_dyn_smem((const void*)h->tile_step, h->device, h->tile.smem);
+        cudaError_t e4 = raise_dyn_smem((const void*)h->tile_rollout, h->device, h->rollout_smem);
         if (e3 != cudaSuccess || e4 != cudaSuccess) {
             free_all(h);
             return fail(PLANTOS_ECUDA, std::string("cudaFuncSetAttribute(tile): ") + cudaGetErrorString(e3 != cudaSuccess ? e3 : e4));
@@ -492,8 +508,15 @@ extern "C" int plantos_push_maps(plantos_t* h, const uint8_t* cells, const int16
         if (x < 0 || x >= p.G || y < 0 || y >= p.G) return fail(PLANTOS_EINVAL, "rover start outside the grid");
         if (cells[i * gg + (size_t)x * p.G + y] == 1) return fail(PLANTOS_EINVAL, "rover start on an obstacle");
     }
-    for (size_t i = 0; i < n * gg; ++i)
-        if (cells[i] > 3) return fail(PLANTOS_EINVAL, "cell code > 3");
+    for (size_t i = 0; i < n; ++i) {
+        int plants = 0;
+        for (size_t c = 0; c < gg; ++c) {
+            const uint8_t v = cells[i * gg + c];
+            if (v > 3) return fail(PLANTOS_EINVAL, "cell code > 3");
+            plants += v >= 2;
+        }
+        if (plants > 255) return fail(PLANTOS_EINVAL, "more than 255 plant cells in one map (the env record counts thirsty plants in 8 bits)");
+    }
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaDeviceSynchronize());
     cudaFree(h->d_map_cells); cudaFree(h->d_map_rover);
@@ -525,7 +548,7 @@ extern "C" int plantos_reset(plantos_t* h, float* obs_dev, void* stream) {
 }
 
 // K consecutive steps (K = 1: plantos_step).  The tile kernels take them in one launch (K > 1: the
-// state-resident k_tile<R, C, true>); every other configuration steps K times.
+// state-resident k_rollout_tile<R, C>); every other configuration steps K times.
 static int launch_steps(plantos_t* h, int K, const int64_t* actions, float* obs, size_t obs_stride, float* reward,
                         uint8_t* done, uint8_t* terminated, uint8_t* truncated, float* terminal_obs, void* stream) {
     CUDA_TRY(cudaSetDevice(h->device));
@@ -722,6 +745,7 @@ extern "C" int plantos_check(plantos_t* h, void* stream) {
     CUDA_TRY(cudaMemcpyAsync(&err, h->p.err, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     if (err == PLANTOS_ENOMAPS) return fail(PLANTOS_ENOMAPS, "an env was reset more often than maps were pushed for it");
+    if (err == PLANTOS_EINVAL) return fail(err, "plantos_set_state: more than 255 thirsty plants in one env (8-bit counter)");
     if (err != 0) return fail(err, "device-side error flag set");
     return PLANTOS_OK;
 }

@@ -81,7 +81,7 @@ struct Params {
     unsigned int* ep_log_count; // entries appended since the last drain (may exceed ep_log_cap: dropped)
     int ep_log_cap;
     unsigned int step_seq;      // number of the step launch, set by the host
-    // optional CurriculumWrapper state (plantos_set_curriculum; generic kernel only)
+    // optional CurriculumWrapper state (plantos_set_curriculum; every step kernel implements it)
     int cur_mode;               // 0 off, 1 reaching the threshold terminates (A2C_training.py), 2 marks only (trainingCode.py)
     int cur_max_eps;            // max_episodes_per_maze
     int cur_reuse_map;          // 1: a kept maze is regenerated identically (plantos_set_curriculum_reuse_map)

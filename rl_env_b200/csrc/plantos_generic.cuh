@@ -671,6 +671,7 @@ __global__ void k_set_state(const Params p, const uint8_t* cells, const int32_t*
         }
         r.total_free = gg - warp_sum_i(n_obst);
         r.thirsty = warp_sum_i(n_thirsty);
+        if (r.thirsty > 255 && lane == 0) atomicExch(p.err, -1);   // PLANTOS_EINVAL: the record counts thirsty plants in 8 bits
     }
     if (visits) {
         uint32_t* vis_e = p.vis4 + (size_t)e * p.VE;

@@ -695,15 +695,15 @@ __device__ __forceinline__ void tile_body(const Params& p, const RollIO& io) {
 // per SM (the code image needs its own buffer behind the rings) with 128 registers (8 blocks per SM), so that the
 // record it carries through the K steps does not push loop invariants out to local memory (a reload from there
 // stalled a warp like a global load: 23 % of the rollout kernel's stall samples before).
-template <int R, int C, bool MULTI>
+template <int R, int C>
 __global__ void __launch_bounds__(kTileWarps * 32, PLANTOS_TILE_MINBLOCKS)
-k_tile(const Params p, const RollIO io) { tile_body<R, C, false>(p, io); }
+k_step_tile(const Params p, const RollIO io) { tile_body<R, C, false>(p, io); }
 
 #ifndef PLANTOS_ROLLOUT_REGS
 #define PLANTOS_ROLLOUT_REGS 112
 #endif
 template <int R, int C>
 __global__ void __maxnreg__(PLANTOS_ROLLOUT_REGS)
-k_tile_rollout(const Params p, const RollIO io) { tile_body<R, C, true>(p, io); }
+k_rollout_tile(const Params p, const RollIO io) { tile_body<R, C, true>(p, io); }
 
 }  // namespace plantos_dev

@@ -6,7 +6,7 @@
 #   bench     bench.py lines: default, the driver's --steps 20 --warmup 5, reference arm, graph / eager loops, no-stagger
 #   presets   tools/bench_presets.py (the other BASELINE.json configurations)
 #   launches  ncu launch list of the default bench loop (no cache flush between launches)
-#   rollout   ncu --set full of one k_tile_rollout launch        step     ncu --set full of one k_tile (single step) launch
+#   rollout   ncu --set full of one k_rollout_tile launch        step     ncu --set full of one k_step_tile launch
 #   others    ncu --set full of k_step_generic / k_reset_all / k_wrc_build / k_reset_done (one launch each)
 #   dram_rollout / dram_step   steady-state DRAM traffic (application replay, no cache flush)
 OUT=gpurun_out/ev2
@@ -40,12 +40,12 @@ launches)
 rollout)
   CMD="python bench.py --steps 48 --warmup 16 --no-cpu-baseline --e2e-steps 3 --no-step-launch"
   $CMD > $OUT/plain_full_rollout.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:k_tile_rollout -s 6 -c 1 -f -o $OUT/prof_rollout $CMD > $OUT/ncu_full_rollout.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:k_rollout_tile -s 6 -c 1 -f -o $OUT/prof_rollout $CMD > $OUT/ncu_full_rollout.log 2>&1
   tail -n 2 $OUT/ncu_full_rollout.log ;;
 step)
   CMD="python bench.py --loop eager --no-pipeline --steps 30 --warmup 5 --no-cpu-baseline --e2e-steps 3 --no-step-launch"
   $CMD > $OUT/plain_full_step.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:k_tile -s 700 -c 1 -f -o $OUT/prof_step $CMD > $OUT/ncu_full_step.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:k_step_tile -s 700 -c 1 -f -o $OUT/prof_step $CMD > $OUT/ncu_full_step.log 2>&1
   tail -n 2 $OUT/ncu_full_step.log ;;
 others)
   CMD="python tools/run_other_kernels.py"
@@ -55,12 +55,12 @@ others)
 dram_rollout)
   CMD="python bench.py --steps 96 --warmup 16 --no-cpu-baseline --e2e-steps 3 --no-step-launch"
   $CMD > $OUT/plain_dram_rollout.log 2>&1 &&
-  ncu --replay-mode application --cache-control none --clock-control none --metrics $M -k regex:k_tile_rollout -s 44 -c 3 --csv --log-file $OUT/steady_dram_rollout.csv $CMD > $OUT/ncu_dram_rollout.log 2>&1
+  ncu --replay-mode application --cache-control none --clock-control none --metrics $M -k regex:k_rollout_tile -s 44 -c 3 --csv --log-file $OUT/steady_dram_rollout.csv $CMD > $OUT/ncu_dram_rollout.log 2>&1
   tail -n 4 $OUT/steady_dram_rollout.csv | cut -c1-300 ;;
 dram_step)
   CMD="python bench.py --loop eager --no-pipeline --steps 60 --warmup 5 --no-cpu-baseline --e2e-steps 3 --no-step-launch"
   $CMD > $OUT/plain_dram_step.log 2>&1 &&
-  ncu --replay-mode application --cache-control none --clock-control none --metrics $M -k regex:k_tile -s 700 -c 4 --csv --log-file $OUT/steady_dram_step.csv $CMD > $OUT/ncu_dram_step.log 2>&1
+  ncu --replay-mode application --cache-control none --clock-control none --metrics $M -k regex:k_step_tile -s 700 -c 4 --csv --log-file $OUT/steady_dram_step.csv $CMD > $OUT/ncu_dram_step.log 2>&1
   tail -n 4 $OUT/steady_dram_step.csv | cut -c1-300 ;;
 *) echo "unknown stage $1"; exit 1 ;;
 esac

@@ -21,12 +21,39 @@ def last_json(path):
 
 
 # ---- bench lines and logs
-for name in ("bench_1gpu", "bench_1gpu_20steps", "bench_reference_cpu", "bench_nostagger"):
+def last_json(path):      # (multi-rank runs: other text may share the file)
+    try:
+        return json.loads([l for l in open(path).read().splitlines() if l.startswith("{")][-1])
+    except Exception:
+        return None
+
+
+for name in ("bench_1gpu", "bench_1gpu_20steps", "bench_reference_cpu", "bench_nostagger", "bench_preset_default", "bench_preset_xl",
+             "bench_4096", "bench_2gpu", "bench_4gpu", "bench_8gpu", "bench_2gpu_640steps", "bench_4gpu_640steps", "bench_8gpu_640steps"):
     d = last_json(os.path.join(ev, name + ".json"))
     if d is not None:
         json.dump(d, open(os.path.join(out, f"{tag}_{name}.json"), "w"))
+scale = {}
+for n in (1, 2, 4, 8):
+    for suffix, key in (("", "steps20"), ("_640steps", "steps640")):
+        d = last_json(os.path.join(ev, ("bench_1gpu_20steps" if suffix == "" else "bench_1gpu") + ".json")) if n == 1 else \
+            last_json(os.path.join(ev, f"bench_{n}gpu{suffix}.json"))
+        if d is not None:
+            scale.setdefault(str(n), {})[key if n > 1 or suffix == "" else "steps3000"] = {
+                "steps": d["steps"], "us_per_step": round(d["ms_per_step"] * 1e3, 2), "value": d["value"],
+                "frac": round(d["roofline"]["frac"], 3), "e2e": d["e2e"]["value"],
+                "e2e_ms_per_step_by_rank": d["e2e"].get("ms_per_step_by_rank"),
+                "stats_allreduces_in_timed_window": d["config"].get("stats_allreduces_in_timed_window")}
+json.dump(scale, open(os.path.join(out, f"{tag}_scaling.json"), "w"), indent=1)
+for n in (2, 4, 8):
+    if os.path.exists(os.path.join(ev, f"topo_{n}gpu.txt")):
+        shutil.copy(os.path.join(ev, f"topo_{n}gpu.txt"), os.path.join(out, f"{tag}_topo_{n}gpu.txt"))
+    err = os.path.join(ev, f"bench_{n}gpu.err")
+    if os.path.exists(err):     # the NCCL lines the driver's rank check looks for
+        keep = [l for l in open(err, errors="replace") if "NCCL INFO" in l and ("nranks" in l or "Init COMPLETE" in l or "NVLS" in l)]
+        open(os.path.join(out, f"{tag}_nccl_{n}gpu.log"), "w").write("".join(keep[:80]))
 loops = {}
-for name in ("bench_loop_graph", "bench_loop_graph_plain", "bench_loop_eager", "bench_loop_eager_plain"):
+for name in ("bench_loop_graph", "bench_loop_graph_plain", "bench_loop_eager", "bench_loop_eager_plain", "bench_loop_graph_nostagger"):
     d = last_json(os.path.join(ev, name + ".json"))
     if d is not None:
         loops[name] = {"us_per_step": round(d["ms_per_step"] * 1e3, 2), "frac": round(d["roofline"]["frac"], 3),
@@ -79,6 +106,26 @@ for which in ("rollout", "step"):
         for i, n in enumerate(names):
             if n in want or n.startswith("smsp__average_warps_issue_stalled") and n.endswith("per_issue_active.ratio"):
                 w.writerow([n, units[i], vals[i]])
+
+# ---- the kernels off the default loop (tools/run_other_kernels.py): one column of metrics per captured launch
+rep = os.path.join(ev, "prof_others.ncu-rep")
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(io.StringIO(raw)))
+    names, units = rr[0], rr[1]
+    seen, cols = set(), []
+    for vals in rr[2:]:
+        k = vals[names.index("Kernel Name")]
+        g = vals[names.index("launch__grid_size")] if "launch__grid_size" in names else ""
+        if (k, g) in seen:
+            continue
+        seen.add((k, g)); cols.append(vals)
+    with open(os.path.join(out, f"{tag}_other_kernels_metrics.csv"), "w") as f:
+        w = csv.writer(f)
+        w.writerow(["metric", "unit"] + [c[names.index("Kernel Name")][:60] for c in cols])
+        for i, n in enumerate(names):
+            if n in want or n.startswith("smsp__average_warps_issue_stalled") and n.endswith("per_issue_active.ratio"):
+                w.writerow([n, units[i]] + [c[i] for c in cols])
 
 # ---- steady-state DRAM traffic
 traffic = {"envs": 131072, "how": "ncu --replay-mode application --cache-control none (no cache flush), bench.py timed loop", "kernels": {}}
