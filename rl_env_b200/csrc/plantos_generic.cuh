@@ -77,8 +77,8 @@ __device__ __forceinline__ void store_obs_row(const float* obs_s, float* dst, in
 // grid full of obstacles, run a randomised depth-first search over the (G-1)/6 x (G-1)/6 meta grid, carve a
 // 5x5 room per meta cell (with probability 0.3 each a 2x2 extension to the right / downwards, with 0.4 one
 // corner cut) and a 5-wide corridor between consecutive rooms (with 0.2 a 2x2 bulge to one side).  Word j of
-// Philox stream 3 is the j-th random decision, taken in the fork's order.  Executed by lane 0 (a serial
-// algorithm on at most 21 x 21 meta cells); `scratch` = maze_scratch_bytes(G) bytes of shared memory.
+// Philox stream 3 is the j-th random decision, taken in the fork's order.  A serial algorithm on at most
+// 21 x 21 meta cells; `scratch` = maze_scratch_bytes(G) bytes of shared memory.
 struct MazeRng {
     const Params& p; long long genv; int ep; uint32_t j; uint32_t buf[4];
     __device__ __forceinline__ uint32_t next() {
@@ -88,46 +88,57 @@ struct MazeRng {
     __device__ __forceinline__ bool chance(uint32_t thresh) { return next() < thresh; }   // random.random() < prob
 };
 
-__device__ __forceinline__ void maze_rect(uint64_t* plane, int G, int W, int x0, int x1, int y0, int y1, bool obstacle) {
+// Executed by the whole warp with identical arguments: every lane owns the grid rows x with x % 32 == lane, so a
+// row word is only ever touched by one lane and the carving needs no synchronisation until the plane is read.
+__device__ __forceinline__ void maze_rect(uint64_t* plane, int G, int W, int x0, int x1, int y0, int y1, bool obstacle, int lane) {
     // cells [x0, x1) x [y0, y1) clipped to the grid become empty (or obstacle): one masked update per row word
     x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, G); y1 = min(y1, G);
     if (x0 >= x1 || y0 >= y1) return;
     for (int wd = y0 >> 5; wd <= (y1 - 1) >> 5; ++wd) {
         const int lo = max(y0, 32 * wd) - 32 * wd, n = min(y1, 32 * wd + 32) - 32 * wd - lo;     // n cells from cell lo of this word
         const uint64_t m = (n >= 32 ? ~0ull : ((1ull << (2 * n)) - 1ull)) << (2 * lo);
-        for (int x = x0; x < x1; ++x) {
+        for (int x = x0 + ((lane - x0) & 31); x < x1; x += 32) {
             uint64_t& w = plane[x * W + wd];
             w = obstacle ? ((w & ~m) | (kObstAll & m)) : (w & ~m);
         }
     }
 }
 
-__device__ __forceinline__ void maze_room(MazeRng& rng, uint64_t* plane, int G, int W, int mx, int my) {   // :479-517
+__device__ __forceinline__ void maze_room(MazeRng& rng, uint64_t* plane, int G, int W, int mx, int my, int lane) {   // :479-517
     const int bx = mx * 6 + 1, by = my * 6 + 1;
-    maze_rect(plane, G, W, bx, bx + 5, by, by + 5, false);
-    if (rng.chance(1288490188u)) maze_rect(plane, G, W, bx + 5, bx + 7, by + 2, by + 4, false);   // 0.3: extend right
-    if (rng.chance(1288490188u)) maze_rect(plane, G, W, bx + 2, bx + 4, by + 5, by + 7, false);   // 0.3: extend down
+    maze_rect(plane, G, W, bx, bx + 5, by, by + 5, false, lane);
+    if (rng.chance(1288490188u)) maze_rect(plane, G, W, bx + 5, bx + 7, by + 2, by + 4, false, lane);   // 0.3: extend right
+    if (rng.chance(1288490188u)) maze_rect(plane, G, W, bx + 2, bx + 4, by + 5, by + 7, false, lane);   // 0.3: extend down
     if (rng.chance(1717986918u)) {                                                                 // 0.4: cut one corner
         const int c = (int)bounded(rng.next(), 4u);                  // [(0,0), (4,0), (0,4), (4,4)]
         const int px = bx + ((c & 1) ? 4 : 0), py = by + ((c & 2) ? 4 : 0);
-        maze_rect(plane, G, W, px, px + 1, py, py + 1, true);
+        maze_rect(plane, G, W, px, px + 1, py, py + 1, true, lane);
     }
 }
 
-__device__ inline void maze_generate(const Params& p, long long genv, int ep, uint64_t* plane, unsigned char* scratch) {
+// All 32 lanes run the search with the same draws (the decisions are a serial chain; computing them 32 times costs
+// nothing extra) and each lane carves the rows it owns (maze_rect): a rectangle is one masked update instead of a
+// loop over its rows.  The stack and the visited bits have one writer (lane 0) and warp barriers around the reads.
+__device__ inline void maze_generate(const Params& p, long long genv, int ep, uint64_t* plane, unsigned char* scratch, int lane) {
     const int G = p.G, W = p.W, m = (G - 1) / 6;
-    for (int idx = 0; idx < G * W; ++idx) plane[idx] = kObstAll;       // (columns >= G are obstacles in any case)
+    for (int x = lane; x < G; x += 32)
+        for (int w = 0; w < W; ++w) plane[x * W + w] = kObstAll;       // (columns >= G are obstacles in any case)
     if (m < 1) return;
     uint16_t* stack = reinterpret_cast<uint16_t*>(scratch);
     uint32_t* visited = reinterpret_cast<uint32_t*>(scratch + align_up(m * m * 2, 4));
-    for (int i = 0; i < (m * m + 31) / 32; ++i) visited[i] = 0u;
+    if (lane == 0)
+        for (int i = 0; i < (m * m + 31) / 32; ++i) visited[i] = 0u;
     MazeRng rng{p, genv, ep, 0u, {0u, 0u, 0u, 0u}};
     int cx = (int)bounded(rng.next(), (uint32_t)m), cy = (int)bounded(rng.next(), (uint32_t)m);   // randint(0, meta - 1) twice
     int sp = 0;
-    stack[sp++] = (uint16_t)(cx * m + cy);
-    visited[(cx * m + cy) >> 5] |= 1u << ((cx * m + cy) & 31);
-    maze_room(rng, plane, G, W, cx, cy);
+    if (lane == 0) {                                                   // (one writer; every lane reads after the barrier)
+        stack[sp] = (uint16_t)(cx * m + cy);
+        visited[(cx * m + cy) >> 5] |= 1u << ((cx * m + cy) & 31);
+    }
+    ++sp;
+    maze_room(rng, plane, G, W, cx, cy, lane);
     while (sp > 0) {                                                   // :434-457
+        __syncwarp();
         const int cur = stack[sp - 1];
         cx = cur / m; cy = cur - cx * m;
         int cand[4], nc = 0;
@@ -142,17 +153,21 @@ __device__ inline void maze_generate(const Params& p, long long genv, int ep, ui
         const int dx = (k == 2) - (k == 3), dy = (k == 0) - (k == 1);
         const int nx = cx + dx, ny = cy + dy;
         // corridor (:540-560): 5 wide, over both meta cells
-        if (dx == 0) maze_rect(plane, G, W, cx * 6 + 1, cx * 6 + 6, min(cy, ny) * 6 + 1, max(cy, ny) * 6 + 7, false);
-        else maze_rect(plane, G, W, min(cx, nx) * 6 + 1, max(cx, nx) * 6 + 7, cy * 6 + 1, cy * 6 + 6, false);
+        if (dx == 0) maze_rect(plane, G, W, cx * 6 + 1, cx * 6 + 6, min(cy, ny) * 6 + 1, max(cy, ny) * 6 + 7, false, lane);
+        else maze_rect(plane, G, W, min(cx, nx) * 6 + 1, max(cx, nx) * 6 + 7, cy * 6 + 1, cy * 6 + 6, false, lane);
         if (rng.chance(858993459u)) {                                  // 0.2: bulge (:562-580)
             const int mx = (cx + nx) / 2, my = (cy + ny) / 2;
             const int dir = bounded(rng.next(), 2u) ? 1 : -1;          // choice([-1, 1])
-            if (dx == 0) maze_rect(plane, G, W, mx * 6 + 2 + dir * 2, mx * 6 + 4 + dir * 2, my * 6 + 2, my * 6 + 4, false);
-            else maze_rect(plane, G, W, mx * 6 + 2, mx * 6 + 4, my * 6 + 2 + dir * 2, my * 6 + 4 + dir * 2, false);
+            if (dx == 0) maze_rect(plane, G, W, mx * 6 + 2 + dir * 2, mx * 6 + 4 + dir * 2, my * 6 + 2, my * 6 + 4, false, lane);
+            else maze_rect(plane, G, W, mx * 6 + 2, mx * 6 + 4, my * 6 + 2 + dir * 2, my * 6 + 4 + dir * 2, false, lane);
         }
-        maze_room(rng, plane, G, W, nx, ny);
-        visited[(nx * m + ny) >> 5] |= 1u << ((nx * m + ny) & 31);
-        stack[sp++] = (uint16_t)(nx * m + ny);
+        maze_room(rng, plane, G, W, nx, ny, lane);
+        __syncwarp();                                                  // (every lane has read this round's stack top and visited bits)
+        if (lane == 0) {
+            visited[(nx * m + ny) >> 5] |= 1u << ((nx * m + ny) & 31);
+            stack[sp] = (uint16_t)(nx * m + ny);
+        }
+        ++sp;
     }
 }
 
@@ -200,7 +215,7 @@ __device__ __forceinline__ EnvRec reset_env_warp(const Params& p, int e, int epi
         if (MAZE && p.map_source == 2) {
             // the fork's maze generator; like the fork (:463-467) it falls back to the cluster generator
             // when the maze leaves fewer than P + 1 free cells
-            if (lane == 0) maze_generate(p, genv, mep, plane, reinterpret_cast<unsigned char*>(plane) + align_up(nwords * 8, 16));
+            maze_generate(p, genv, mep, plane, reinterpret_cast<unsigned char*>(plane) + align_up(nwords * 8, 16), lane);
             __syncwarp();
             int nfree = 0;
             for (int idx = lane; idx < nwords; idx += 32) {

@@ -362,3 +362,28 @@ def test_rollout_policy_matches_the_mcts_heuristic():
         u = torch.rand((n, 2), dtype=torch.float32, device="cuda", generator=g)
         uh = u.cpu().numpy()
         assert env.rollout_policy(u).cpu().tolist() == [rollout_policy(ora.envs[i], uh[i, 0], uh[i, 1]) for i in range(n)]
+
+
+def test_more_than_255_plants_are_rejected():
+    """The env record counts thirsty plants in 8 bits: recorded maps and injected state beyond that are refused
+    (plantos_push_maps: EINVAL; plantos_set_state: flagged on the device, raised by check())."""
+    import torch
+    from rl_env_b200 import PlantOSVecEnv
+    from rl_env_b200._native import PlantOSError
+    g = 21
+    env = PlantOSVecEnv(2, map_source="injected", grid_size=g, num_plants=8, num_obstacles=0, lidar_range=2, lidar_channels=10)
+    cells = np.zeros((2, 1, g, g), dtype=np.uint8)
+    cells[:, 0, 1:15, :] = 3                                   # 294 thirsty plants
+    rover = np.zeros((2, 1, 2), dtype=np.int16)
+    with pytest.raises(PlantOSError, match="255"):
+        env.push_maps(cells, rover)
+    cells[:, 0, 13:15, :] = 0                                  # 252: accepted
+    env.push_maps(cells, rover)
+    env.reset()
+    env.check()
+    too_many = torch.as_tensor(np.ascontiguousarray(cells[:, 0]), device=env.device).clone()
+    too_many[:, 13:16, :] = 3
+    env.set_state(cells=too_many)
+    with pytest.raises(PlantOSError, match="255"):
+        env.check()
+    env.close()

@@ -33,7 +33,7 @@ bench)
 presets)
   timeout 900 python tools/bench_presets.py 320 > $OUT/presets.log 2>&1; cat $OUT/presets.log ;;
 launches)
-  CMD="python bench.py --steps 64 --warmup 16 --no-cpu-baseline --e2e-steps 3"
+  CMD="python bench.py --steps 64 --warmup 16 --no-cpu-baseline --e2e-steps 3 --no-step-launch"
   $CMD > $OUT/plain_launches.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 400 --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_launches.log 2>&1
   tail -n 2 $OUT/ncu_launches.log ;;
