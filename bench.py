@@ -319,8 +319,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     pipelined = not args.no_pipeline
     loop = args.loop
     roll = None
-    if loop != "rollout":
-        env.set_pipelining(pipelined)      # eager steps too (the obs ring gives every step its own buffer)
+    env.set_pipelining(pipelined)          # every loop: eager steps (the obs ring gives every step its own buffer), graphs, rollout calls
     if loop == "graph":
         roll = env.make_rollout(ACTION_RING, with_flags=True, pipelined=pipelined)
 
@@ -471,7 +470,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         traffic, traffic_src = measured_traffic(n, kernel_of_loop)
         launch_desc = {
             "rollout": "env.step_many: %d steps per plantos_rollout call (one launch of the state-resident kernel %s per call; "
-                       "every step reads its own action vector and writes its own obs/reward/done buffers)" % (ACTION_RING, kernel_of_loop),
+                       "every step reads its own action vector and writes its own obs/reward/done buffers)" % (ACTION_RING, kernel_of_loop)
+                       + ("; consecutive launches pipelined on the device (plantos_set_pipelining)" if pipelined else ""),
             "graph": "CUDA graph of %d single-step plantos_step launches, replayed" % ACTION_RING
                      + ("; consecutive launches pipelined on the device (plantos_set_pipelining)" if pipelined else ""),
             "eager": "eager, one plantos_step launch per step" + ("; pipelined (plantos_set_pipelining)" if pipelined else ""),

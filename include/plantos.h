@@ -264,12 +264,14 @@ int plantos_rollout(plantos_t* h, int num_steps, const int64_t* actions_dev, flo
                     float* terminal_obs_dev, void* stream);
 
 /* Pipelined stepping for OPEN-LOOP sequences (rollouts with pre-generated actions, benchmarks): with
- * enable != 0 a plantos_step that directly follows another plantos_step of this handle on the same
- * stream, writing a DIFFERENT obs buffer, no longer waits for the previous launch as a whole; per-tile
- * counters on the device order the two steps env by env, so the next step's loads and simulation
- * overlap the previous step's observation stores.  Results are identical.  Contract: `actions` of such a
- * step must not be produced by work enqueued after the previous plantos_step (anything else enqueued
- * on the stream in between must not touch the step's inputs).  Default off; the reference has no
+ * enable != 0 a plantos_step / plantos_rollout that directly follows another one of this handle on the same
+ * stream no longer waits for the previous launch as a whole; per-tile counters on the device order the two
+ * launches env by env, so the next launch's loads and simulation overlap the previous launch's observation
+ * stores and the drain of its last wave.  A launch that follows a plantos_step must write a DIFFERENT obs
+ * range (a single step publishes an env before its observation is stored); after a plantos_rollout the same
+ * buffers may be written again.  Results are identical.  Contract: `actions` of such a launch must not be
+ * produced by work enqueued after the previous launch (anything else enqueued on the stream in between must
+ * not touch the launch's inputs or read buffers the next launch overwrites).  Default off; the reference has no
  * counterpart (its DummyVecEnv steps synchronously, A2C_training.py:218). */
 int plantos_set_pipelining(plantos_t* h, int enable);
 /* The kernel the latest plantos_step actually launched: "k_step_tile", "k_step_fast" (both are the

@@ -107,8 +107,10 @@ struct plantos {
     void* d_sync;                // tickets (8 B) + per-tile step flags of k_step_tile
     Params* d_params;            // Params::self: the global-memory copy of p (see sync_params)
     bool pipelining;             // plantos_set_pipelining
-    bool prev_tile_step;         // the handle's latest enqueued operation was a k_step_tile launch ...
-    const float* prev_obs;       // ... that wrote this observation buffer on this stream
+    bool prev_tile_step;         // the handle's latest enqueued operation was a k_step_tile / k_rollout_tile launch ...
+    bool prev_multi;             // ... of the multi-step kernel (publishes its tiles after its last store)
+    const float* prev_obs;       // ... that wrote this observation range on this stream
+    size_t prev_obs_bytes;
     void* prev_stream;
     bool lane_offsets_ok;        // the uploaded LIDAR offsets equal the lane kernel's compile-time table
     bool prefer_lane;
@@ -578,16 +580,17 @@ static int launch_steps(plantos_t* h, int K, const int64_t* actions, float* obs,
             h->launches += 1;
         }
         h->wrc_valid = use_tile;
-        // Pipelined launch (plantos_set_pipelining): allowed when the handle's previous operation was a
-        // k_step_tile launch on this stream into a DIFFERENT observation buffer (the expansion stores of
-        // consecutive steps are not ordered) and there is no ragged tail (its envs bypass the tile flags).
-        const size_t obs_bytes = N * h->p.D * sizeof(float);
+        // Pipelined launch (plantos_set_pipelining): allowed when the handle's previous operation was a tile-kernel
+        // launch on this stream and there is no ragged tail (its envs bypass the tile flags).  A single-step launch
+        // publishes a tile BEFORE its expansion stores, so whatever follows it must write a DIFFERENT observation
+        // range; a multi-step launch publishes a tile after its last store, so its successor may reuse the buffers.
+        const size_t obs_bytes = ((size_t)(K - 1) * obs_stride + N * h->p.D) * sizeof(float);
         const bool disjoint = h->prev_obs && ((const char*)obs + obs_bytes <= (const char*)h->prev_obs ||
-                                              (const char*)h->prev_obs + obs_bytes <= (const char*)obs);
-        h->p.pipelined = (use_tile && K == 1 && h->pipelining && h->use_pdl && h->prev_tile_step && disjoint &&
+                                              (const char*)h->prev_obs + h->prev_obs_bytes <= (const char*)obs);
+        h->p.pipelined = (use_tile && h->pipelining && h->use_pdl && h->prev_tile_step && (h->prev_multi || disjoint) &&
                           h->prev_stream == stream && (h->p.N & 3) == 0) ? 1 : 0;
         h->p.release = h->pipelining ? 1 : 0;
-        h->prev_tile_step = use_tile && K == 1; h->prev_obs = obs; h->prev_stream = stream;
+        h->prev_tile_step = use_tile; h->prev_multi = K > 1; h->prev_obs = obs; h->prev_obs_bytes = obs_bytes; h->prev_stream = stream;
         // (the experimental lane kernel has no curriculum path)
         const bool use_lane = h->prefer_lane && h->lane.fn && h->lane_offsets_ok && !h->p.cur_mode;
         const FastLaunch& L = use_tile ? h->tile : (use_lane ? h->lane : h->trip);

@@ -321,6 +321,51 @@ def test_pipelined_eager_steps_equal_plain_steps():
     a.close(); b.close()
 
 
+def test_pipelined_rollouts_equal_plain_steps():
+    """plantos_set_pipelining on step_many: consecutive multi-step launches (same output buffers, mixed with
+    single steps into an observation ring) overlap on the device through the per-tile counters and give exactly
+    what plain single steps give, auto-resets included."""
+    import torch
+    from rl_env_b200 import PlantOSVecEnv, PRESETS
+    n, ring = 16384, 4
+    kw = dict(PRESETS["training"], max_steps=23, seed=9, kernel="fast", full_infos=False)
+    a, b = PlantOSVecEnv(n, **kw), PlantOSVecEnv(n, obs_ring=ring, **kw)
+    b.set_pipelining(True)
+    assert torch.equal(a.reset(), b.reset())
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    plan = [5, 5, 1, 1, 7, 5, 1, 12, 12, 3]                 # K of every call (1 = step_async / step_wait)
+    acts = torch.randint(0, 5, (sum(plan), n), device="cuda", generator=g)
+    want = []
+    for t in range(acts.shape[0]):
+        obs, rew, done, _ = a.step(acts[t])
+        want.append((obs.clone(), rew.clone(), done.clone()))
+    t, checks = 0, []
+    for k in plan:                                          # everything enqueued back to back, no host sync
+        if k == 1:
+            b.step_async(acts[t])
+            obs, rew, done, _ = b.step_wait()
+            checks.append((t, obs, None, None, 0))
+        else:
+            obs, rew, done = b.step_many(acts[t:t + k])
+            # (the next call with the same K reuses these buffers: copy them out, stream-ordered)
+            checks.append((t, obs.clone(), rew.clone(), done.clone(), k))
+        t += k
+    torch.cuda.synchronize()
+    for t0, obs, rew, done, k in checks:
+        if k == 0:
+            assert torch.equal(obs, want[t0][0]), t0
+        else:
+            for j in range(k):
+                assert torch.equal(obs[j], want[t0 + j][0]), (t0, j)
+                assert torch.equal(rew[j], want[t0 + j][1]) and torch.equal(done[j], want[t0 + j][2]), (t0, j)
+    assert b.last_step_kernel == "k_rollout_tile"
+    sa, sb = a.get_state(), b.get_state()
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    assert a.episode_stats(all_reduce=False) == b.episode_stats(all_reduce=False)
+    a.check(); b.check()
+    a.close(); b.close()
+
+
 def test_rollout_policy_matches_the_mcts_heuristic():
     """plantos_rollout_policy against the restated MCTS rollout policy (mcts_custom_trainer.py:168-216)
     on the same states and the same injected uniforms, while both sides follow that policy for 300
