@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Step time of the other BASELINE.json configurations and presets (secondary numbers, not the bench.py line).
 For every configuration: (a) eager single-step launches (closed-loop style: full dependency between steps),
-(b) env.step_many with 16 steps per call (one launch of the state-resident kernel where it exists).
+(b) env.step_many with 16 steps per call (one launch of the state-resident kernel where it exists; consecutive
+launches pipelined on the device, plantos_set_pipelining).
 CUDA-event timing, staggered episode phases (hash(env id) mod max_steps) unless a curriculum is active.
 usage: tools/bench_presets.py [steps]"""
 import json
@@ -25,6 +26,7 @@ def run(label, n, steps, **kw):
     d = env.obs_dim
     out = {"config": label, "envs": n, "obs_dim": d}
     for mode in ("step", "step_many16"):
+        env.set_pipelining(mode == "step_many16")      # consecutive rollout launches overlap on the device; single steps: plain
         def once():
             if mode == "step":
                 for t in range(16):
