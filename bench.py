@@ -83,14 +83,20 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def measured_traffic(envs_per_gpu: int, kernel: str):
+def measured_traffic(envs_per_gpu: int, kernel: str, preset: str):
     """Steady-state DRAM bytes per STEP of the dominant kernel from the committed ncu capture
-    (profiles/r2_traffic.json: application replay, no cache flush); only valid for the workload and
-    kernel it was captured on, else null."""
+    (profiles/r2_traffic.json: application replay, no cache flush); only valid for the workload, the
+    kernel and the kernel SOURCES it was captured on (hash of the .cuh files), else null."""
     try:
+        import hashlib
         with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             t = json.load(f)
-        if envs_per_gpu == int(t.get("envs", 0)) and kernel in t.get("kernels", {}):
+        h = hashlib.sha256()
+        for name in ("plantos_tile.cuh", "plantos_common.cuh", "plantos_generic.cuh"):
+            with open(os.path.join(ROOT, "rl_env_b200", "csrc", name), "rb") as f:
+                h.update(f.read())
+        if (envs_per_gpu == int(t.get("envs", 0)) and preset == t.get("preset") and kernel in t.get("kernels", {})
+                and h.hexdigest()[:16] == t.get("kernel_source_sha")):
             return int(t["kernels"][kernel]["dram_bytes_per_step"]), t["kernels"][kernel].get("source", "")
     except Exception:
         pass
@@ -467,7 +473,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         peak, peak_src = measured_peak_gbs()
         step_s = ms * 1e-3 / args.steps
         achieved = n * B_ALG / step_s / 1e9
-        traffic, traffic_src = measured_traffic(n, kernel_of_loop)
+        traffic, traffic_src = measured_traffic(n, kernel_of_loop, args.preset)
         launch_desc = {
             "rollout": "env.step_many: %d steps per plantos_rollout call (one launch of the state-resident kernel %s per call; "
                        "every step reads its own action vector and writes its own obs/reward/done buffers)" % (ACTION_RING, kernel_of_loop)

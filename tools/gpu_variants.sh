@@ -1,4 +1,5 @@
 #!/bin/bash
+# usage: tools/gpu_variants.sh base <name>...: 640-step bench of build/libplantos_<name>.so variants (tools/build_variant.sh), one line each
 mkdir -p gpurun_out/r2
 for v in "$@"; do
   if [ "$v" = "base" ]; then unset PLANTOS_LIB; else export PLANTOS_LIB=build/libplantos_$v.so; fi

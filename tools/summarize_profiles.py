@@ -128,7 +128,13 @@ if os.path.exists(rep):
                 w.writerow([n, units[i]] + [c[i] for c in cols])
 
 # ---- steady-state DRAM traffic
-traffic = {"envs": 131072, "how": "ncu --replay-mode application --cache-control none (no cache flush), bench.py timed loop", "kernels": {}}
+import hashlib
+def kernel_source_sha():
+    h = hashlib.sha256()
+    for name in ("plantos_tile.cuh", "plantos_common.cuh", "plantos_generic.cuh"):
+        h.update(open(os.path.join(root, "rl_env_b200", "csrc", name), "rb").read())
+    return h.hexdigest()[:16]
+traffic = {"envs": 131072, "preset": "training", "kernel_source_sha": kernel_source_sha(), "how": "ncu --replay-mode application --cache-control none (no cache flush), bench.py timed loop", "kernels": {}}
 for which, kname, steps in (("rollout", "k_rollout_tile", 16), ("step", "k_step_tile", 1)):
     path = os.path.join(ev, f"steady_dram_{which}.csv")
     if not os.path.exists(path):
