@@ -28,6 +28,7 @@ HBM copy peak; `cpu_baseline` = the oracle port of the reference on this box's h
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import multiprocessing as mp
 import os
@@ -344,27 +345,39 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     pending_stats = []
 
-    def run_steps(k, start):
-        """k consecutive steps; `start` only selects which pre-generated action blocks are used."""
-        i = 0
+    def plan_steps(k, start):
+        """The calls of k consecutive steps as (m, action block) pairs; `start` only selects which pre-generated
+        action blocks are used.  Built before the clock starts: slicing tensors is not part of a step."""
+        plan, i = [], 0
         while i < k:
             m = k - i if k - i < 2 * chunk else chunk
+            if loop == "graph":
+                m = min(m, ACTION_RING) if m >= ACTION_RING else m
             b = ((start + i) // ACTION_RING) % ACTION_POOL
+            if loop == "rollout":
+                plan.append((m, pool2[b][:m]))
+            elif loop == "graph" and m >= ACTION_RING:
+                plan.append((ACTION_RING, pool[b]))
+            else:
+                plan.append((m, [pool2[b][t] for t in range(m)]))
+            i += plan[-1][0]
+        return plan
+
+    def run_steps(k, start, plan=None):
+        for m, acts in (plan if plan is not None else plan_steps(k, start)):
             done_steps = counters.get("steps", 0)
             if loop == "rollout":
-                env.step_many(pool2[b][:m], with_flags=True)        # ONE plantos_rollout call: m steps
+                env.step_many(acts, with_flags=True)                 # ONE plantos_rollout call: m steps
                 counters["launches"] += 1
-            elif loop == "graph" and m >= ACTION_RING:
-                roll.actions.copy_(pool[b], non_blocking=True)       # (1 MB device copy per 16 steps, inside the timed region)
+            elif loop == "graph" and m == ACTION_RING and not isinstance(acts, list):
+                roll.actions.copy_(acts, non_blocking=True)          # (1 MB device copy per 16 steps, inside the timed region)
                 roll.graph.replay()
                 counters["launches"] += ACTION_RING
-                m = ACTION_RING
             else:
-                for t in range(m):
-                    env.step_async(pool2[b][t])
+                for a in acts:
+                    env.step_async(a)
                     env.step_wait()
                 counters["launches"] += m
-            i += m
             counters["steps"] = done_steps + m
             # episode statistics: whenever the steps just enqueued crossed a multiple of `stats_every`, the counters
             # are snapshotted behind them and all-reduced (NCCL, 8 doubles) on the process group's stream, next to the
@@ -383,6 +396,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     sampler = ClockSampler(local_rank)      # (NVML initialised here: tens of ms of idle GPU right before the timed
     sampler.sample()                        #  region drop its clocks -- a 300 us region then runs 40 % slower)
     sampler.samples.clear()
+    # everything the host can do ahead of the clock happens BEFORE the untimed steps: anything slow between them
+    # and the opening event would let the GPU idle (a GPU that idled for tens of ms runs the first launch slower)
+    timed_plan = plan_steps(args.steps, 2 * ACTION_RING + args.warmup)
+    gc.collect()
+    gc.disable()                                           # (no collector pause between the opening event and the launches)
     run_steps(PREWARM_CHUNKS * ACTION_RING, 0)
     if args.steps % chunk:                                # (the odd-sized last chunk of the timed region: its buffers exist now)
         run_steps(args.steps % chunk + (chunk if args.steps > chunk else 0), 0)
@@ -394,8 +412,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     counters["stats"] = counters["launches"] = counters["steps"] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    run_steps(args.steps, 2 * ACTION_RING + args.warmup)
+    run_steps(args.steps, 0, timed_plan)
     e1.record()
+    gc.enable()
     sampler.sample_until(e1)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -475,8 +494,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         achieved = n * B_ALG / step_s / 1e9
         traffic, traffic_src = measured_traffic(n, kernel_of_loop, args.preset)
         launch_desc = {
-            "rollout": "env.step_many: %d steps per plantos_rollout call (one launch of the state-resident kernel %s per call; "
-                       "every step reads its own action vector and writes its own obs/reward/done buffers)" % (ACTION_RING, kernel_of_loop)
+            "rollout": "env.step_many: %d steps in %d plantos_rollout call(s) (%d steps per call, a remainder rides on the last; one launch of the "
+                       "state-resident kernel %s per call; every step reads its own action vector and writes its own obs/reward/done buffers)"
+                       % (args.steps, launches, chunk, kernel_of_loop)
                        + ("; consecutive launches pipelined on the device (plantos_set_pipelining)" if pipelined else ""),
             "graph": "CUDA graph of %d single-step plantos_step launches, replayed" % ACTION_RING
                      + ("; consecutive launches pipelined on the device (plantos_set_pipelining)" if pipelined else ""),
@@ -508,8 +528,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                          "traffic_unit": "steady-state DRAM bytes per step (ncu dram read+write, " + traffic_src + ")" if traffic else None,
                          "peak_source": peak_src, "basis": "algorithmic bytes (obs + reward + done + action = 441 B per env-step)",
                          "alg_bytes_per_env_step": B_ALG, "kernel": kernel_of_loop,
-                         "steps_per_launch": ACTION_RING if loop == "rollout" else 1,
-                         "avg_launch_us": step_s * 1e6 * (ACTION_RING if loop == "rollout" else 1)},
+                         "steps_per_launch": args.steps / max(1, launches),
+                         "avg_launch_us": ms * 1e3 / max(1, launches)},
             "step_launch": step_launch,
             "clocks": sampler.summary(),
             "ms_per_step_by_rank": [round(m / args.steps, 6) for m in per_rank_ms],
