@@ -562,10 +562,16 @@ class PlantOSVecEnv:
         all-reduce runs on the process group's own stream NEXT TO the steps enqueued afterwards (it is
         8 doubles: pure latency, which the following launches hide); `.wait()` makes the env's stream
         wait for it and returns the tensor."""
-        nat.check(self._lib.plantos_stats(self._h, self._stats.data_ptr(), int(clear), self._stream()))
-        if async_op:
-            return all_reduce_stats(self._stats, async_op=True) if all_reduce else PendingStats(self._stats, None)
-        return all_reduce_stats(self._stats) if all_reduce else self._stats
+        import torch.distributed as dist
+        reduce = all_reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        # (with a process group the snapshot goes straight into a fresh 64-byte tensor that is all-reduced in place:
+        # no copy kernel between the snapshot and the collective)
+        out = torch.empty_like(self._stats) if reduce else self._stats
+        nat.check(self._lib.plantos_stats(self._h, out.data_ptr(), int(clear), self._stream()))
+        if not reduce:
+            return PendingStats(out, None) if async_op else out
+        work = dist.all_reduce(out, op=dist.ReduceOp.SUM, async_op=async_op)
+        return PendingStats(out, work) if async_op else out
 
     # --------------------------------------------------------------- per-episode log (SB3 Monitor)
     EPISODE_DTYPE = np.dtype([("env", "<u4"), ("l", "<u4"), ("step_seq", "<u4"), ("flags", "<u4"),
