@@ -468,7 +468,16 @@ __device__ __forceinline__ void step_env_warp(const Params& p, const Tables& t, 
 
     // stage the rows the step can look at: x-R-1 .. x+R+1 (move of one row + LIDAR reach)
     const int lo = max(0, x - p.R - 1), hi = min(p.G - 1, x + p.R + 1);
-    for (int idx = lo * p.W + lane; idx < (hi + 1) * p.W; idx += 32) plane[idx] = types_e[idx];
+    // (four loads in flight per lane before the first store: a plain copy loop waits for every load in turn,
+    // which on the XL preset -- 134 words per env -- was four dependent global round trips)
+    for (int idx = lo * p.W + lane; idx < (hi + 1) * p.W; idx += 128) {
+        const int end = (hi + 1) * p.W;
+        uint64_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = idx + 32 * u < end ? types_e[idx + 32 * u] : 0ull;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (idx + 32 * u < end) plane[idx + 32 * u] = v[u];
+    }
     __syncwarp();
 
     int flagw = 0;
@@ -549,7 +558,10 @@ __device__ __forceinline__ void step_env_warp(const Params& p, const Tables& t, 
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kGenericWarps * 32)
+#ifndef PLANTOS_GENERIC_MINBLOCKS
+#define PLANTOS_GENERIC_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(kGenericWarps * 32, PLANTOS_GENERIC_MINBLOCKS)
 k_step_generic(const Params p, const StepIO io) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Tables t = load_tables(p, smem);
