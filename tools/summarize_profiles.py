@@ -130,6 +130,16 @@ if os.path.exists(rep):
 # ---- steady-state DRAM traffic
 import hashlib
 def kernel_source_sha():
+    # written by tools/gpu_evidence.sh at CAPTURE time (both DRAM stages must agree); falls back to the current tree
+    shas = set()
+    for st in ("dram_rollout", "dram_step"):
+        f = os.path.join(ev, f"kernel_source_sha_{st}.txt")
+        if os.path.exists(f):
+            shas.add(open(f).read().strip())
+    if len(shas) == 1:
+        return shas.pop()
+    if len(shas) > 1:
+        return "mixed"
     h = hashlib.sha256()
     for name in ("plantos_tile.cuh", "plantos_common.cuh", "plantos_generic.cuh"):
         h.update(open(os.path.join(root, "rl_env_b200", "csrc", name), "rb").read())
