@@ -180,7 +180,7 @@ def cpu_baseline(seconds: float = 12.0):
 
 
 REF_ENVS_PER_WORKER = 64      # fixed sample: 64 envs per host core
-REF_SECONDS = 10.0            # CPU time the K timed steps of the reference arm add up to
+REF_SECONDS = float(os.environ.get("PLANTOS_BENCH_REF_SECONDS", "10.0"))            # CPU time the K timed steps of the reference arm add up to
 
 
 def run_reference(args, rank: int):

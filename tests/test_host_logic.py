@@ -119,3 +119,30 @@ def test_philox_maze_mirror_matches_the_forks_generator_in_distribution():
     # a grid too small for a single room falls back to the cluster generator, like the fork (:463-467)
     small, _ = generate_maze_map(5, 0, 0, 6, 2, 3)
     assert (small != 1).sum() > 20
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line with the contract's
+    keys, the reference arm's `impl` / `cpu_baseline` / zero-copy `e2e`, the same metric and workload naming
+    as our arm.  (Timed sample shortened through PLANTOS_BENCH_REF_SECONDS.)"""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PLANTOS_BENCH_REF_SECONDS="1.5")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "1",
+                          "--steps", "3", "--warmup", "3"], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline", "impl"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "env_steps_per_sec" and d["unit"] == "env-steps/s"
+    assert d["steps"] == 3 and d["warmup"] == 3 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["value"] > 0 and d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert "training preset" in d["config"]["workload"] and d["config"]["sample_envs"] == 64 * d["cpu_baseline"]["cores"]
