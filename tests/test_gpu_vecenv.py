@@ -321,14 +321,15 @@ def test_pipelined_eager_steps_equal_plain_steps():
     a.close(); b.close()
 
 
-def test_pipelined_rollouts_equal_plain_steps():
+@pytest.mark.parametrize("n,preset,cur", [(16384, "training", None), (8192, "default", None), (4096, "training", "a2c")])
+def test_pipelined_rollouts_equal_plain_steps(n, preset, cur):
     """plantos_set_pipelining on step_many: consecutive multi-step launches (same output buffers, mixed with
     single steps into an observation ring) overlap on the device through the per-tile counters and give exactly
-    what plain single steps give, auto-resets included."""
+    what plain single steps give, auto-resets (and the curriculum wrapper) included."""
     import torch
     from rl_env_b200 import PlantOSVecEnv, PRESETS
-    n, ring = 16384, 4
-    kw = dict(PRESETS["training"], max_steps=23, seed=9, kernel="fast", full_infos=False)
+    ring = 4
+    kw = dict(PRESETS[preset], max_steps=23, seed=9, kernel="fast", full_infos=False, curriculum=cur)
     a, b = PlantOSVecEnv(n, **kw), PlantOSVecEnv(n, obs_ring=ring, **kw)
     b.set_pipelining(True)
     assert torch.equal(a.reset(), b.reset())
@@ -362,6 +363,39 @@ def test_pipelined_rollouts_equal_plain_steps():
     sa, sb = a.get_state(), b.get_state()
     assert all(torch.equal(sa[k], sb[k]) for k in sa)
     assert a.episode_stats(all_reduce=False) == b.episode_stats(all_reduce=False)
+    a.check(); b.check()
+    a.close(); b.close()
+
+
+def test_pipelined_rollouts_full_size_equal_plain_rollouts():
+    """BASELINE's per-GPU share (131 072 envs, staggered episode phases as in bench.py): 96 steps as six
+    pipelined 16-step launches into the SAME buffers against the same launches one at a time -- last
+    observations, rewards, flags, full state and episode statistics identical."""
+    import torch
+    from rl_env_b200 import PlantOSVecEnv, PRESETS
+    n = 131072
+    kw = dict(PRESETS["training"], seed=3, kernel="fast", full_infos=False)
+    a, b = PlantOSVecEnv(n, **kw), PlantOSVecEnv(n, **kw)
+    b.set_pipelining(True)
+    assert torch.equal(a.reset(), b.reset())
+    gid = torch.arange(n, device="cuda", dtype=torch.int64)
+    phase = (((gid * 2654435761) % 4294967296) % 1000).to(torch.int32)
+    a.set_state(scalars={"step_count": phase}); b.set_state(scalars={"step_count": phase})
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    acts = torch.randint(0, 5, (96, n), device="cuda", generator=g)
+    for c in range(6):                                      # b: six launches back to back, no host sync in between
+        outs_b = b.step_many(acts[16 * c:16 * c + 16], with_flags=True)
+    for c in range(6):
+        outs_a = a.step_many(acts[16 * c:16 * c + 16], with_flags=True)
+        torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    for x, y in zip(outs_a, outs_b):
+        assert torch.equal(x, y)
+    assert torch.equal(a.terminal_observation, b.terminal_observation)
+    sa, sb = a.get_state(), b.get_state()
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    sta, stb = a.episode_stats(all_reduce=False), b.episode_stats(all_reduce=False)
+    assert sta == stb and sta["episodes"] > 10000
     a.check(); b.check()
     a.close(); b.close()
 
