@@ -87,17 +87,13 @@ def measured_peak_gbs():
 def measured_traffic(envs_per_gpu: int, kernel: str, preset: str):
     """Steady-state DRAM bytes per STEP of the dominant kernel from the committed ncu capture
     (profiles/r2_traffic.json: application replay, no cache flush); only valid for the workload, the
-    kernel and the kernel SOURCES it was captured on (hash of the .cuh files), else null."""
+    kernel and the kernel CODE it was captured on (rl_env_b200.build.kernel_source_hash: comments do not count), else null."""
     try:
-        import hashlib
+        from rl_env_b200.build import kernel_source_hash
         with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             t = json.load(f)
-        h = hashlib.sha256()
-        for name in ("plantos_tile.cuh", "plantos_common.cuh", "plantos_generic.cuh"):
-            with open(os.path.join(ROOT, "rl_env_b200", "csrc", name), "rb") as f:
-                h.update(f.read())
         if (envs_per_gpu == int(t.get("envs", 0)) and preset == t.get("preset") and kernel in t.get("kernels", {})
-                and h.hexdigest()[:16] == t.get("kernel_source_sha")):
+                and kernel_source_hash() == t.get("kernel_source_sha")):
             return int(t["kernels"][kernel]["dram_bytes_per_step"]), t["kernels"][kernel].get("source", "")
     except Exception:
         pass

@@ -1,6 +1,6 @@
-// plantos_tile.cuh -- k_step_tile: the round-2 hot kernel.  ONE LANE PER ENV for the whole
-// simulation part of the step, the WHOLE WARP for the observation output, ONE BULK COPY per tile for
-// the state.
+// plantos_tile.cuh -- k_step_tile (one step per launch) and k_rollout_tile (K steps per launch, state resident
+// on the SM): the round-2 hot kernels.  ONE LANE PER ENV for the whole simulation part of the step, the WHOLE
+// WARP for the observation output, ONE BULK COPY per tile for the state.
 //
 // Same shape limits as k_step_fast (W == 1, VW == 4, G + R <= 32, C <= 16; R <= 6) plus: the LIDAR
 // sample offsets must be the reference's own (plantos_lidar_gen.cuh holds them as compile-time
@@ -26,8 +26,8 @@
 //      reads, one 128-bit streaming store -- fully coalesced, no float staging tile;
 //   4. a rover that changed rows pulls the one type row and the one nibble row that entered its window
 //      from the planes (loads issued before the expansion, stored into the cache after it).
-// 28 warps per SM (4 blocks x 7 warps, 72 registers): at the benchmark size every warp owns exactly one
-// tile.  Auto-reset and the ragged tail reuse the generic warp routines, as in k_step_fast.
+// k_step_tile: 28 warps per SM (14 blocks x 2 warps, 72 registers): at the benchmark size every warp owns exactly
+// one tile.  Auto-reset and the ragged tail reuse the generic warp routines, as in k_step_fast.
 #pragma once
 #include "plantos_fast.cuh"
 #include "plantos_lidar_gen.cuh"
@@ -691,10 +691,10 @@ __device__ __forceinline__ void tile_body(const Params& p, const RollIO& io) {
         }
 }
 
-// The two kernels: 28 warps per SM at 72 registers for the single step; for the state-resident rollout 14 warps
-// per SM (the code image needs its own buffer behind the rings) with 128 registers (8 blocks per SM), so that the
-// record it carries through the K steps does not push loop invariants out to local memory (a reload from there
-// stalled a warp like a global load: 23 % of the rollout kernel's stall samples before).
+// The two kernels: 28 warps per SM at 72 registers for the single step; for the state-resident rollout 16 warps
+// per SM (the code image needs its own buffer behind the rings: 22 KB per block) at 112 registers -- four warps
+// per scheduler; 128 registers measured 1 % slower, 96 registers spill in the step loop and 144 registers leave
+// only 7 blocks per SM (profiles/r2_summary.md).
 template <int R, int C>
 __global__ void __launch_bounds__(kTileWarps * 32, PLANTOS_TILE_MINBLOCKS)
 k_step_tile(const Params p, const RollIO io) { tile_body<R, C, false>(p, io); }

@@ -12,13 +12,7 @@
 OUT=gpurun_out/ev2
 mkdir -p $OUT
 # hash of the kernel sources the captures below are taken from (bench.py reports the DRAM figure only for these sources)
-python - <<'PY' > $OUT/kernel_source_sha_$1.txt
-import hashlib
-h = hashlib.sha256()
-for name in ("plantos_tile.cuh", "plantos_common.cuh", "plantos_generic.cuh"):
-    h.update(open("rl_env_b200/csrc/" + name, "rb").read())
-print(h.hexdigest()[:16])
-PY
+python -c "from rl_env_b200.build import kernel_source_hash; print(kernel_source_hash())" > $OUT/kernel_source_sha_$1.txt
 M=dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sectors_op_read.sum,lts__t_sectors_op_write.sum,gpu__time_duration.sum
 case "$1" in
 tests)

@@ -140,10 +140,9 @@ def kernel_source_sha():
         return shas.pop()
     if len(shas) > 1:
         return "mixed"
-    h = hashlib.sha256()
-    for name in ("plantos_tile.cuh", "plantos_common.cuh", "plantos_generic.cuh"):
-        h.update(open(os.path.join(root, "rl_env_b200", "csrc", name), "rb").read())
-    return h.hexdigest()[:16]
+    sys.path.insert(0, root)
+    from rl_env_b200.build import kernel_source_hash
+    return kernel_source_hash()
 traffic = {"envs": 131072, "preset": "training", "kernel_source_sha": kernel_source_sha(), "how": "ncu --replay-mode application --cache-control none (no cache flush), bench.py timed loop", "kernels": {}}
 for which, kname, steps in (("rollout", "k_rollout_tile", 16), ("step", "k_step_tile", 1)):
     path = os.path.join(ev, f"steady_dram_{which}.csv")
