@@ -11,9 +11,10 @@ Philox maps, i.i.d. uniform actions; the envs start at staggered 
 (step_count = hash(env id) mod max_steps), so about N / 1000 envs truncate and are regenerated in EVERY
 step of the timed region.
 
-Timed loop (`--loop`): `rollout` (default) = env.step_many, 16 steps per plantos_rollout call with
+Timed loop (`--loop`): `rollout` (default) = env.step_many, `--chunk` (32) steps per plantos_rollout call with
 pre-generated actions: every step reads its own action vector and writes its own observation / reward /
-done buffers, the K steps of a call are one launch of the state-resident kernel; `graph` = a replayed
+done buffers, the K steps of a call are one launch of the state-resident kernel, consecutive launches
+pipelined on the device (a --steps that is not a multiple of the chunk rides on the last call); `graph` = a replayed
 CUDA graph of 16 single-step plantos_step launches (round 1's loop; consecutive launches pipelined on
 the device unless --no-pipeline); `eager` = one plantos_step call per step.  The line always carries
 the single-launch-per-step numbers next to the headline (`step_launch`).
@@ -332,12 +333,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         stats_every = max(ACTION_RING, min(args.stats_every, max(1, args.steps // 2)) // ACTION_RING * ACTION_RING)
     counters = {"stats": 0, "launches": 0}
 
-    # chunks: ACTION_RING steps per rollout call / graph replay; a remainder shorter than ACTION_RING rides on
-    # the last chunk (rollout loop: one call of up to 2 * ACTION_RING - 1 steps), so that a short timed region
+    # chunks: `--chunk` steps per rollout call (ACTION_RING per graph replay); a remainder shorter than the chunk
+    # rides on the last call (rollout loop: one call of up to 2 * chunk - 1 steps), so that a short timed region
     # (--steps 20) is ONE call, not a 16-step call plus a 4-step call with a host round trip in between
-    pool2 = [torch.cat([pool[b], pool[(b + 1) % ACTION_POOL]]) for b in range(ACTION_POOL)]   # [2 * ACTION_RING, n] each
+    pool2 = [torch.cat([pool[(b + j) % ACTION_POOL] for j in range(4)]) for b in range(ACTION_POOL)]   # [4 * ACTION_RING, n] each
 
-    chunk = min(max(args.chunk, 1), ACTION_RING) if loop == "rollout" else ACTION_RING
+    chunk = min(max(args.chunk, 1), 2 * ACTION_RING) if loop == "rollout" else ACTION_RING
 
     pending_stats = []
 
@@ -507,7 +508,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        "kernel": kernel_name, "loop_kernel": kernel_of_loop, "maps": "philox seed 0", "state_bytes_per_env": state_bytes,
                        "actions": f"{ACTION_POOL * ACTION_RING} pre-generated i.i.d. uniform vectors, cycled",
                        "episode_phases": "all envs start at step 0" if args.no_stagger else f"staggered: step_count = hash(env id) mod {MAX_STEPS} (about N/{MAX_STEPS} auto-resets in every step)",
-                       "l2": f"outputs larger than L2: {ACTION_RING if loop != 'eager' else OBS_RING} observation buffers x {n * OBS_DIM * 4 / 1e6:.0f} MB "
+                       "l2": f"outputs larger than L2: {(chunk if loop == 'rollout' else ACTION_RING) if loop != 'eager' else OBS_RING} observation buffers x {n * OBS_DIM * 4 / 1e6:.0f} MB "
                              f"written round-robin vs 126 MB L2 (per-GPU state {n * state_bytes / 1e6:.0f} MB); no explicit flush",
                        "launch": launch_desc,
                        "untimed_steps_before_warmup": PREWARM_CHUNKS * ACTION_RING,
@@ -521,7 +522,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "traffic_unit": "steady-state DRAM bytes per step (ncu dram read+write, " + traffic_src + ")" if traffic else None,
+                         "traffic_unit": "steady-state DRAM bytes per step (ncu dram read+write at 16 steps per launch, " + traffic_src + ")" if traffic else None,
                          "peak_source": peak_src, "basis": "algorithmic bytes (obs + reward + done + action = 441 B per env-step)",
                          "alg_bytes_per_env_step": B_ALG, "kernel": kernel_of_loop,
                          "steps_per_launch": args.steps / max(1, launches),
@@ -561,8 +562,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-terminal-obs", action="store_true")
     ap.add_argument("--loop", default="rollout", choices=["rollout", "graph", "eager"],
-                    help="timed loop: step_many (16 steps per rollout launch), replayed graph of 16 step launches, or eager steps")
-    ap.add_argument("--chunk", type=int, default=ACTION_RING, help="rollout loop: steps per plantos_rollout call (<= %d)" % ACTION_RING)
+                    help="timed loop: step_many (--chunk steps per rollout launch), replayed graph of 16 step launches, or eager steps")
+    ap.add_argument("--chunk", type=int, default=2 * ACTION_RING, help="rollout loop: steps per plantos_rollout call (<= %d)" % (2 * ACTION_RING))
     ap.add_argument("--no-graph", action="store_true", help="same as --loop eager")
     ap.add_argument("--no-pipeline", action="store_true", help="full grid-wide dependency between consecutive step launches (graph / eager loops)")
     ap.add_argument("--no-stagger", action="store_true", help="all envs start at step 0 (no auto-reset before step 1000)")

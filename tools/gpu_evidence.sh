@@ -35,12 +35,12 @@ bench)
 presets)
   timeout 900 python tools/bench_presets.py 320 > $OUT/presets.log 2>&1; cat $OUT/presets.log ;;
 launches)
-  CMD="python bench.py --steps 64 --warmup 16 --no-cpu-baseline --e2e-steps 3 --no-step-launch"
+  CMD="python bench.py --chunk 16 --steps 64 --warmup 16 --no-cpu-baseline --e2e-steps 3 --no-step-launch"
   $CMD > $OUT/plain_launches.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 400 --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_launches.log 2>&1
   tail -n 2 $OUT/ncu_launches.log ;;
 rollout)
-  CMD="python bench.py --steps 48 --warmup 16 --no-cpu-baseline --e2e-steps 3 --no-step-launch"
+  CMD="python bench.py --chunk 16 --steps 48 --warmup 16 --no-cpu-baseline --e2e-steps 3 --no-step-launch"
   $CMD > $OUT/plain_full_rollout.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:k_rollout_tile -s 6 -c 1 -f -o $OUT/prof_rollout $CMD > $OUT/ncu_full_rollout.log 2>&1
   tail -n 2 $OUT/ncu_full_rollout.log ;;
@@ -55,7 +55,7 @@ others)
   ncu --set full --clock-control none --import-source on -k regex:'k_step_generic|k_reset_all|k_wrc_build|k_reset_done|k_step_fast' -s 10 -c 12 -f -o $OUT/prof_others $CMD > $OUT/ncu_full_others.log 2>&1
   tail -n 2 $OUT/ncu_full_others.log ;;
 dram_rollout)
-  CMD="python bench.py --steps 96 --warmup 16 --no-cpu-baseline --e2e-steps 3 --no-step-launch"
+  CMD="python bench.py --chunk 16 --steps 96 --warmup 16 --no-cpu-baseline --e2e-steps 3 --no-step-launch"
   $CMD > $OUT/plain_dram_rollout.log 2>&1 &&
   ncu --replay-mode application --cache-control none --clock-control none --metrics $M -k regex:k_rollout_tile -s 44 -c 3 --csv --log-file $OUT/steady_dram_rollout.csv $CMD > $OUT/ncu_dram_rollout.log 2>&1
   tail -n 4 $OUT/steady_dram_rollout.csv | cut -c1-300 ;;
