@@ -4,7 +4,8 @@ Only the env-step hot path of GammaKing2000/RL-Env (plantos_env.py:125-372 behin
 SB3 VecEnv) lives here: `csrc/` holds the sm_100a kernels and the C ABI of
 include/plantos.h, `vec_env.py` the Python mirror of the reference's VecEnv surface.
 """
-from .vec_env import PRESETS, GraphRollout, LazyInfos, MonitorCSV, PlantOSVecEnv, all_reduce_stats, shard_range  # noqa: F401
+from .vec_env import (PRESETS, GraphRollout, LazyInfos, MonitorCSV, PendingStats, PlantOSVecEnv,  # noqa: F401
+                      all_reduce_stats, shard_range)
 from ._native import PlantOSError  # noqa: F401
 
 
